@@ -1,0 +1,70 @@
+"""ctypes binding of libgsmvi_b200.so (the C ABI in include/gsmvi_b200.h).
+
+The library is the product path: there is no CPU or PyTorch fallback. If the shared object is missing
+or fails to load, importing any operator raises immediately."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgsmvi_b200.so")
+
+_lib = None
+
+
+class GsmviError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GsmviError(
+                "libgsmvi_b200.so not found at %s: build it with `python gsm-vi_b200/build.py` "
+                "(no CPU fallback exists)" % LIB_PATH)
+        _lib = ctypes.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+c_f = ctypes.c_float
+c_i = ctypes.c_int
+c_ll = ctypes.c_longlong
+c_p = ctypes.c_void_p
+
+
+def _declare(L):
+    L.gsmvi_abi_version.restype = c_i
+    L.gsmvi_gemm_tf32.restype = c_i
+    L.gsmvi_gemm_tf32.argtypes = [c_p, c_ll, c_ll, c_ll, c_i, c_p, c_ll, c_ll, c_ll, c_i, c_p, c_ll, c_i, c_i, c_i,
+                                  c_f, c_f, c_p, c_ll, c_p, c_i, c_i, c_i, c_i, c_i, c_p]
+
+
+def check(rc, what):
+    if rc != 0:
+        raise GsmviError("%s failed with status %d%s" % (what, rc, " (CUDA error)" if rc > 0 else ""))
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+KR_FULL, KR_A_LOWER, KR_B_LOWER, KR_A_UPPER, KR_B_UPPER = 0, 1, 2, 4, 8
+
+
+def gemm_tf32(A, B, C, M, N, K, a_mn=False, b_mn=False, alpha=1.0, beta=0.0, Cin=None, bias_n=None, npass=3,
+              tri=False, mirror=False, krange=0, neg_from=0x7fffffff):
+    """C[M,N] = alpha * op(A) op(B)^T + beta*Cin + bias_n. A, B, C are 2-D fp32 CUDA tensors (row-major views with
+    stride(1) == 1). K-major operand: [rows, K]; MN-major (a_mn/b_mn): [K, rows]."""
+    assert A.stride(1) == 1 and B.stride(1) == 1 and C.stride(1) == 1
+    rc = lib().gsmvi_gemm_tf32(ptr(A), A.shape[0], A.shape[1], A.stride(0), int(a_mn), ptr(B), B.shape[0], B.shape[1],
+                               B.stride(0), int(b_mn), ptr(C), C.stride(0), M, N, K, alpha, beta, ptr(Cin),
+                               Cin.stride(0) if Cin is not None else 0, ptr(bias_n), npass, int(tri), int(mirror),
+                               krange, neg_from, stream_ptr())
+    check(rc, "gsmvi_gemm_tf32")
+    return C

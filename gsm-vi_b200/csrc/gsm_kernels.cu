@@ -1,0 +1,283 @@
+// Bandwidth-bound kernels of the GSM iteration and its orchestration.
+//
+// gsm_update (gsmvi/gsm.py:31-58) restated for the device (derivation: SURVEY.md section 9, oracle/gsmvi_oracle.py
+// gsm_update):   per sample b, d = mu0 - x, w = Sigma0 g:
+//     vSv = <w,g>, mu_v = <d,g>, rho = 0.5 sqrt(1 + 4 (vSv + mu_v^2)) - 0.5           (gsm.py:12-14)
+//     alpha = 1/(1+rho),  beta = -alpha (1 + (vSv - mu_v)/(1 + rho + mu_v))            (gsm.py:18-21, g^T eps0 = vSv - mu_v)
+//     u = alpha w + beta d  (= mu_update),  e = d + u  (= mu - x)                     (gsm.py:21-22)
+//     mu = mu0 + mean_b u,   Sigma = Sigma0 + (D^T D - E^T E)/B                       (gsm.py:25-27, 53-56)
+// Three launches: W = G Sigma0 (tensor-core GEMM), the row pass below (HBM-bound, 20 B D bytes), and the signed
+// outer-product GEMM over T = [D; E] with the "+ Sigma0" and 1/B fused in its epilogue.
+#include "gsm_kernels.cuh"
+
+#include <math.h>
+
+namespace gsmvi {
+
+constexpr int RP_ROWS = 16;     // sample rows per CTA
+constexpr int RP_THREADS = 256;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One CTA handles RP_ROWS consecutive samples.  Pass 1 (a warp per row): the two dot products and the per-sample
+// scalars.  Pass 2 (a thread per 4 columns): rows d and e of T = [D; E] and the column sums of u.
+__global__ void __launch_bounds__(RP_THREADS) gsm_rowpass_kernel(const float* __restrict__ X, long long ldx,
+                                                                 const float* __restrict__ G, long long ldg,
+                                                                 const float* __restrict__ W, long long ldw,
+                                                                 const float* __restrict__ mu, float* __restrict__ T,
+                                                                 long long ldt, float* __restrict__ usum, int B, int D) {
+  __shared__ float s_alpha[RP_ROWS], s_beta[RP_ROWS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * RP_ROWS;
+  const bool vec = ((D & 3) == 0) && ((ldx & 3) == 0) && ((ldg & 3) == 0) && ((ldw & 3) == 0) && ((ldt & 3) == 0) &&
+                   (((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(W) |
+                      reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(mu)) & 15) == 0);
+  for (int r = warp; r < RP_ROWS; r += RP_THREADS / 32) {
+    const int b = row0 + r;
+    if (b >= B) break;
+    const float* x = X + b * ldx;
+    const float* g = G + b * ldg;
+    const float* w = W + b * ldw;
+    float vSv = 0.0f, mu_v = 0.0f;
+    if (vec) {
+      for (int j = lane * 4; j < D; j += 128) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + j);
+        const float4 gv = *reinterpret_cast<const float4*>(g + j);
+        const float4 wv = *reinterpret_cast<const float4*>(w + j);
+        const float4 mv = *reinterpret_cast<const float4*>(mu + j);
+        vSv += wv.x * gv.x + wv.y * gv.y + wv.z * gv.z + wv.w * gv.w;
+        mu_v += (mv.x - xv.x) * gv.x + (mv.y - xv.y) * gv.y + (mv.z - xv.z) * gv.z + (mv.w - xv.w) * gv.w;
+      }
+    } else {
+      for (int j = lane; j < D; j += 32) {
+        vSv += w[j] * g[j];
+        mu_v += (mu[j] - x[j]) * g[j];
+      }
+    }
+    vSv = warp_sum(vSv);
+    mu_v = warp_sum(mu_v);
+    if (lane == 0) {
+      const float rho = 0.5f * sqrtf(1.0f + 4.0f * (vSv + mu_v * mu_v)) - 0.5f;
+      const float alpha = 1.0f / (1.0f + rho);
+      const float beta = -alpha * (1.0f + (vSv - mu_v) / (1.0f + rho + mu_v));
+      s_alpha[r] = alpha;
+      s_beta[r] = beta;
+    }
+  }
+  __syncthreads();
+  const int nrows = min(RP_ROWS, B - row0);
+  if (vec) {
+    for (int j = threadIdx.x * 4; j < D; j += RP_THREADS * 4) {
+      const float4 mv = *reinterpret_cast<const float4*>(mu + j);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < nrows; ++r) {
+        const long long b = row0 + r;
+        const float4 xv = *reinterpret_cast<const float4*>(X + b * ldx + j);
+        const float4 wv = *reinterpret_cast<const float4*>(W + b * ldw + j);
+        const float al = s_alpha[r], be = s_beta[r];
+        float4 d, u, e;
+        d.x = mv.x - xv.x; d.y = mv.y - xv.y; d.z = mv.z - xv.z; d.w = mv.w - xv.w;
+        u.x = al * wv.x + be * d.x; u.y = al * wv.y + be * d.y; u.z = al * wv.z + be * d.z; u.w = al * wv.w + be * d.w;
+        e.x = d.x + u.x; e.y = d.y + u.y; e.z = d.z + u.z; e.w = d.w + u.w;
+        acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
+        *reinterpret_cast<float4*>(T + b * ldt + j) = d;
+        *reinterpret_cast<float4*>(T + (b + B) * ldt + j) = e;
+      }
+      atomicAdd(usum + j + 0, acc.x);
+      atomicAdd(usum + j + 1, acc.y);
+      atomicAdd(usum + j + 2, acc.z);
+      atomicAdd(usum + j + 3, acc.w);
+    }
+  } else {
+    for (int j = threadIdx.x; j < D; j += RP_THREADS) {
+      const float m = mu[j];
+      float acc = 0.0f;
+      for (int r = 0; r < nrows; ++r) {
+        const long long b = row0 + r;
+        const float d = m - X[b * ldx + j];
+        const float u = s_alpha[r] * W[b * ldw + j] + s_beta[r] * d;
+        acc += u;
+        T[b * ldt + j] = d;
+        T[(b + B) * ldt + j] = d + u;
+      }
+      atomicAdd(usum + j, acc);
+    }
+  }
+}
+
+// out[j] = a[j] + scale * s[j]
+__global__ void vec_axpy_kernel(const float* __restrict__ a, const float* __restrict__ s, float scale,
+                                float* __restrict__ out, int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) out[j] = (a ? a[j] : 0.0f) + scale * s[j];
+}
+
+// C[i,j] = A[i,j] + Bm[i,j]   (n x n; the multi-GPU path applies the all-reduced statistics with it)
+__global__ void mat_add_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ Bm, long long ldb,
+                               float* __restrict__ C, long long ldc, int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = blockIdx.y;
+  if (j < n) C[i * ldc + j] = A[i * lda + j] + Bm[i * ldb + j];
+}
+
+// ---------------------------------------------------------------------------------------------- Philox N(0,1)
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+// Philox4x32-10: counter = (element group, offset), key = seed.  Four uniforms -> four normals (Box-Muller).
+__global__ void philox_normal_kernel(float* __restrict__ Z, long long ldz, int B, int D, unsigned long long seed,
+                                     unsigned long long offset) {
+  const int groups_per_row = (D + 3) / 4;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long long>(B) * groups_per_row) return;
+  const int b = static_cast<int>(gid / groups_per_row);
+  const int j = static_cast<int>(gid % groups_per_row) * 4;
+  uint32_t c[4] = {static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), static_cast<uint32_t>(offset),
+                   static_cast<uint32_t>(offset >> 32)};
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const float u0 = (static_cast<float>(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u1 = (static_cast<float>(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = (static_cast<float>(c[2] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u3 = (static_cast<float>(c[3] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+  float s0, c0, s1, c1;
+  sincospif(2.0f * u1, &s0, &c0);
+  sincospif(2.0f * u3, &s1, &c1);
+  const float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+  float* row = Z + static_cast<long long>(b) * ldz;
+  if (j + 3 < D && (ldz & 3) == 0) {
+    *reinterpret_cast<float4*>(row + j) = make_float4(z[0], z[1], z[2], z[3]);
+  } else {
+    for (int t = 0; t < 4 && j + t < D; ++t) row[j + t] = z[t];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- orchestration
+
+static inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+int philox_normal(cudaStream_t stream, float* Z, long long ldz, int B, int D, unsigned long long seed,
+                  unsigned long long offset) {
+  if (!Z || B <= 0 || D <= 0 || ldz < D) return GSMVI_EINVAL;
+  const long long n = static_cast<long long>(B) * ((D + 3) / 4);
+  philox_normal_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(Z, ldz, B, D, seed, offset);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
+}
+
+int sample_mvn(cudaStream_t stream, const float* mu, const float* L, long long ldl, const float* Z, long long ldz,
+               float* X, long long ldx, int B, int D, int npass) {
+  // X[b,i] = mu[i] + sum_{k<=i} Z[b,k] L[i,k]
+  GemmOpts o;
+  o.npass = npass;
+  o.bias_n = mu;
+  o.krange = KR_B_LOWER;
+  MatView vz{Z, B, D, ldz}, vl{L, D, D, ldl};
+  return launch_gemm_tf32(stream, B, D, D, vz, vl, X, ldx, o);
+}
+
+int gauss_score(cudaStream_t stream, const float* X, long long ldx, const float* P, long long ldp, const float* c,
+                float* G, long long ldg, int B, int D, int npass) {
+  // G = -(X - m) P = -X P + c,  c = P m   (P symmetric: P[n,k] read K-major as-is)
+  GemmOpts o;
+  o.npass = npass;
+  o.alpha = -1.0f;
+  o.bias_n = c;
+  MatView vx{X, B, D, ldx}, vp{P, D, D, ldp};
+  return launch_gemm_tf32(stream, B, D, D, vx, vp, G, ldg, o);
+}
+
+size_t gsm_update_workspace_bytes(int B, int D) {
+  const long long ldw = round_up(D, 32);
+  // W [B x ldw] + T [2B x ldw] + usum [ldw]
+  return static_cast<size_t>((3LL * B + 1) * ldw) * sizeof(float);
+}
+
+int gsm_update(cudaStream_t stream, const float* X, long long ldx, const float* G, long long ldg, const float* mu,
+               const float* Sigma, long long lds, float* mu_out, float* Sigma_out, long long ldso, int B, int D,
+               int B_total, int mode, float* workspace, int npass) {
+  if (!X || !G || !mu || !Sigma || !mu_out || !Sigma_out || !workspace || B <= 0 || D <= 0 || B_total < B)
+    return GSMVI_EINVAL;
+  const long long ldw = round_up(D, 32);
+  float* W = workspace;
+  float* T = W + static_cast<long long>(B) * ldw;
+  float* usum = T + 2LL * B * ldw;
+  cudaError_t e = cudaMemsetAsync(usum, 0, ldw * sizeof(float), stream);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  // (i) W = G Sigma0   (Sigma0 symmetric)
+  {
+    GemmOpts o;
+    o.npass = npass;
+    MatView vg{G, B, D, ldg}, vs{Sigma, D, D, lds};
+    int rc = launch_gemm_tf32(stream, B, D, D, vg, vs, W, ldw, o);
+    if (rc != GSMVI_OK) return rc;
+  }
+  // (ii) row pass
+  gsm_rowpass_kernel<<<(B + RP_ROWS - 1) / RP_ROWS, RP_THREADS, 0, stream>>>(X, ldx, G, ldg, W, ldw, mu, T, ldw, usum, B, D);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return static_cast<int>(e);
+  // (iii) Sigma_out = [Sigma0 +] (D^T D - E^T E) / B_total : T is [2B, D] row-major = MN-major for both operands
+  {
+    GemmOpts o;
+    o.npass = npass;
+    o.a_mn = o.b_mn = true;
+    o.alpha = 1.0f / static_cast<float>(B_total);
+    o.tri = true;
+    o.mirror = true;
+    o.neg_from = B;
+    if (mode == 0) {
+      o.beta = 1.0f;
+      o.Cin = Sigma;
+      o.ldcin = lds;
+    }
+    MatView vt{T, 2LL * B, D, ldw};
+    // neg_from must be a multiple of BK for the per-k-block sign switch
+    if (B % BK != 0) {
+      // ragged batch: two launches (D^T D, then -= E^T E) instead of the signed single pass
+      GemmOpts o1 = o;
+      o1.neg_from = 0x7fffffff;
+      MatView vd{T, B, D, ldw}, ve{T + static_cast<long long>(B) * ldw, B, D, ldw};
+      int rc = launch_gemm_tf32(stream, D, D, B, vd, vd, Sigma_out, ldso, o1);
+      if (rc != GSMVI_OK) return rc;
+      GemmOpts o2 = o;
+      o2.neg_from = 0;
+      o2.beta = 1.0f;
+      o2.Cin = Sigma_out;
+      o2.ldcin = ldso;
+      rc = launch_gemm_tf32(stream, D, D, B, ve, ve, Sigma_out, ldso, o2);
+      if (rc != GSMVI_OK) return rc;
+    } else {
+      int rc = launch_gemm_tf32(stream, D, D, 2 * B, vt, vt, Sigma_out, ldso, o);
+      if (rc != GSMVI_OK) return rc;
+    }
+  }
+  // mu_out = [mu0 +] usum / B_total
+  vec_axpy_kernel<<<(D + 255) / 256, 256, 0, stream>>>(mode == 0 ? mu : nullptr, usum, 1.0f / static_cast<float>(B_total),
+                                                      mu_out, D);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
+}
+
+int gsm_apply_stats(cudaStream_t stream, const float* Sigma, long long lds, const float* dSigma, long long ldd,
+                    const float* mu, const float* dmu, float* Sigma_out, long long ldso, float* mu_out, int D) {
+  mat_add_kernel<<<dim3((D + 255) / 256, D), 256, 0, stream>>>(Sigma, lds, dSigma, ldd, Sigma_out, ldso, D);
+  vec_axpy_kernel<<<(D + 255) / 256, 256, 0, stream>>>(mu, dmu, 1.0f, mu_out, D);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
+}
+
+}  // namespace gsmvi

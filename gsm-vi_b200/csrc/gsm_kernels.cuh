@@ -1,0 +1,20 @@
+// GSM iteration pieces (gsm_kernels.cu): Philox normals, sampling, dense-Gaussian score, fused GSM update.
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace gsmvi {
+
+int philox_normal(cudaStream_t stream, float* Z, long long ldz, int B, int D, unsigned long long seed,
+                  unsigned long long offset);
+int sample_mvn(cudaStream_t stream, const float* mu, const float* L, long long ldl, const float* Z, long long ldz,
+               float* X, long long ldx, int B, int D, int npass);
+int gauss_score(cudaStream_t stream, const float* X, long long ldx, const float* P, long long ldp, const float* c,
+                float* G, long long ldg, int B, int D, int npass);
+size_t gsm_update_workspace_bytes(int B, int D);
+int gsm_update(cudaStream_t stream, const float* X, long long ldx, const float* G, long long ldg, const float* mu,
+               const float* Sigma, long long lds, float* mu_out, float* Sigma_out, long long ldso, int B, int D,
+               int B_total, int mode, float* workspace, int npass);
+int gsm_apply_stats(cudaStream_t stream, const float* Sigma, long long lds, const float* dSigma, long long ldd,
+                    const float* mu, const float* dmu, float* Sigma_out, long long ldso, float* mu_out, int D);
+
+}  // namespace gsmvi

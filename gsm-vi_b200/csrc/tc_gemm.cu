@@ -34,11 +34,11 @@ int make_tmap_2d(CUtensorMap* out, const MatView& v, int box_cols, int box_rows,
   return r == CUDA_SUCCESS ? GSMVI_OK : GSMVI_EDRIVER;
 }
 
-template <int NPASS, bool A_MN, bool B_MN>
+template <int NPASS, bool SPLIT_RN, bool A_MN, bool B_MN>
 static int launch_one(cudaStream_t stream, const GemmArgs& args, const CUtensorMap& ta, const CUtensorMap& tb, int grid) {
   using Cfg = GemmCfg<NPASS>;
   static bool attr_set = false;
-  auto kern = gemm_tf32_kernel<NPASS, A_MN, B_MN>;
+  auto kern = gemm_tf32_kernel<NPASS, SPLIT_RN, A_MN, B_MN>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -52,7 +52,7 @@ static int launch_one(cudaStream_t stream, const GemmArgs& args, const CUtensorM
 int launch_gemm_tf32(cudaStream_t stream, int M, int N, int K, const MatView& A, const MatView& B, float* C,
                      long long ldc, const GemmOpts& o) {
   if (M <= 0 || N <= 0 || K < 0 || !C) return GSMVI_EINVAL;
-  if (o.npass != 1 && o.npass != 3) return GSMVI_EINVAL;
+  if (o.npass < 1 || o.npass > 3) return GSMVI_EINVAL;
   if (o.tri && M != N) return GSMVI_EINVAL;
   GemmArgs a;
   a.M = M; a.N = N; a.K = K;
@@ -83,13 +83,14 @@ int launch_gemm_tf32(cudaStream_t stream, int M, int N, int K, const MatView& A,
     if (rc != GSMVI_OK) return rc;
   }
 
-#define GSMVI_DISPATCH(NP)                                                              \
-  if (!o.a_mn && !o.b_mn) return launch_one<NP, false, false>(stream, a, ta, tb, grid); \
-  if (o.a_mn && !o.b_mn) return launch_one<NP, true, false>(stream, a, ta, tb, grid);   \
-  if (!o.a_mn && o.b_mn) return launch_one<NP, false, true>(stream, a, ta, tb, grid);   \
-  return launch_one<NP, true, true>(stream, a, ta, tb, grid);
-  if (o.npass == 3) { GSMVI_DISPATCH(3) }
-  GSMVI_DISPATCH(1)
+#define GSMVI_DISPATCH(NP, RN)                                                              \
+  if (!o.a_mn && !o.b_mn) return launch_one<NP, RN, false, false>(stream, a, ta, tb, grid); \
+  if (o.a_mn && !o.b_mn) return launch_one<NP, RN, true, false>(stream, a, ta, tb, grid);   \
+  if (!o.a_mn && o.b_mn) return launch_one<NP, RN, false, true>(stream, a, ta, tb, grid);   \
+  return launch_one<NP, RN, true, true>(stream, a, ta, tb, grid);
+  if (o.npass == 3) { GSMVI_DISPATCH(3, true) }
+  if (o.npass == 2) { GSMVI_DISPATCH(3, false) }
+  GSMVI_DISPATCH(1, false)
 #undef GSMVI_DISPATCH
 }
 

@@ -14,7 +14,8 @@
 //    as three tcgen05.mma.kind::tf32 per k-slice.  TMEM accumulation also truncates (error grows linearly
 //    with the number of accumulating MMAs), so hi*hi is spread round-robin over three main accumulators and
 //    the small terms go to their own; the epilogue adds the four in fp32 round-to-nearest.
-//    1xTF32 mode skips the split (one accumulator).
+//    The default (precision 3) rounds hi to nearest instead and stores it too: ~8x more accurate products
+//    (fp32-grade) for ~10% more shared-memory traffic.  1xTF32 mode skips the split (one accumulator).
 //  * warp-specialised: warp0 = TMA producer, warp1 = MMA issuer + TMEM owner, warps 2..9 = converters,
 //    and the same eight warps drain TMEM in the epilogue (tcgen05.ld 32x32b) with a fused
 //    alpha/beta/bias update, optional lower-triangle-only tiles and mirrored (symmetric) stores.
@@ -28,6 +29,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include "../../include/gsmvi_b200.h"
 #include "ptx.cuh"
 
 namespace gsmvi {
@@ -96,7 +98,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(bool a_mn, bool b_mn, boo
          ((b_mn ? 1u : 0u) << 16) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
 }
 
-template <int NPASS, bool A_MN, bool B_MN>
+template <int NPASS, bool SPLIT_RN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_kernel(const GemmArgs args, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
   using Cfg = GemmCfg<NPASS>;
@@ -249,11 +251,24 @@ gemm_tf32_kernel(const GemmArgs args, const __grid_constant__ CUtensorMap tmA, c
         for (int j = 0; j < CHUNKS / (32 * NUM_CONV_WARPS); ++j) {
           const int c = ct + j * 32 * NUM_CONV_WARPS;
           const float4 v = *reinterpret_cast<const float4*>(st + c * 16);
-          float4 lo;  // the tensor core truncates v to tf32 itself; lo = rn_tf32(v - trunc_tf32(v))
-          lo.x = ptx::to_tf32(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
-          lo.y = ptx::to_tf32(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
-          lo.z = ptx::to_tf32(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
-          lo.w = ptx::to_tf32(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+          float4 lo;
+          if (SPLIT_RN) {
+            // precise split: hi = rn_tf32(v) overwrites the staged value, lo = rn_tf32(v - hi).  |lo| <= 2^-12 |v|,
+            // the dropped lo*lo term is <= 2^-24 and unbiased: fp32-grade products.
+            float4 hi;
+            hi.x = ptx::to_tf32(v.x); lo.x = ptx::to_tf32(v.x - hi.x);
+            hi.y = ptx::to_tf32(v.y); lo.y = ptx::to_tf32(v.y - hi.y);
+            hi.z = ptx::to_tf32(v.z); lo.z = ptx::to_tf32(v.z - hi.z);
+            hi.w = ptx::to_tf32(v.w); lo.w = ptx::to_tf32(v.w - hi.w);
+            *reinterpret_cast<float4*>(st + c * 16) = hi;
+          } else {
+            // fast split: the tensor core truncates v to tf32 itself, so only lo = rn_tf32(v - trunc_tf32(v)) is
+            // written.  lo in [0, 2^-10 |v|): the dropped lo*lo term is a one-sided ~2^-22 relative bias.
+            lo.x = ptx::to_tf32(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+            lo.y = ptx::to_tf32(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+            lo.z = ptx::to_tf32(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+            lo.w = ptx::to_tf32(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+          }
           *reinterpret_cast<float4*>(st + 2 * TILE_BYTES + c * 16) = lo;
         }
         ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
@@ -362,13 +377,12 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// status codes shared by the C ABI (include/gsmvi_b200.h)
-enum : int { GSMVI_OK = 0, GSMVI_EINVAL = -1, GSMVI_EALIGN = -2, GSMVI_EDRIVER = -3, GSMVI_EWORKSPACE = -4 };
+// status codes: GSMVI_OK / GSMVI_E* from the C ABI header
 
 int make_tmap_2d(CUtensorMap* out, const MatView& v, int box_cols, int box_rows, bool atom32);
 
 struct GemmOpts {
-  int npass = 3;          // 1 or 3
+  int npass = 3;          // precision: 1 = TF32, 2 = 3xTF32 fast (truncation split), 3 = 3xTF32 (round-to-nearest split)
   bool a_mn = false;      // A given as [K, M]
   bool b_mn = false;      // B given as [K, N]
   float alpha = 1.0f, beta = 0.0f;

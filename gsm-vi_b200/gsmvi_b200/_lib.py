@@ -68,3 +68,73 @@ def gemm_tf32(A, B, C, M, N, K, a_mn=False, b_mn=False, alpha=1.0, beta=0.0, Cin
                                krange, neg_from, stream_ptr())
     check(rc, "gsmvi_gemm_tf32")
     return C
+
+
+# ------------------------------------------------------------------------------------------------ GSM path
+c_ull = ctypes.c_ulonglong
+WS_POTRF, WS_GSM_UPDATE = 1, 2
+
+
+def _declare_gsm(L):
+    L.gsmvi_workspace_bytes.restype = c_ll
+    L.gsmvi_workspace_bytes.argtypes = [c_i, c_i, c_i]
+    L.gsmvi_potrf_check.restype = c_i
+    L.gsmvi_potrf_check.argtypes = [c_p, c_ll, c_p, c_ll, c_i, c_p, c_p, c_i, c_p]
+    L.gsmvi_philox_normal.restype = c_i
+    L.gsmvi_philox_normal.argtypes = [c_p, c_ll, c_i, c_i, c_ull, c_ull, c_p]
+    L.gsmvi_sample.restype = c_i
+    L.gsmvi_sample.argtypes = [c_p, c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p]
+    L.gsmvi_gauss_score.restype = c_i
+    L.gsmvi_gauss_score.argtypes = [c_p, c_ll, c_p, c_ll, c_p, c_p, c_ll, c_i, c_i, c_i, c_p]
+    L.gsmvi_gsm_update.restype = c_i
+    L.gsmvi_gsm_update.argtypes = [c_p, c_ll, c_p, c_ll, c_p, c_p, c_ll, c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_p, c_i, c_p]
+    L.gsmvi_gsm_apply_stats.restype = c_i
+    L.gsmvi_gsm_apply_stats.argtypes = [c_p, c_ll, c_p, c_ll, c_p, c_p, c_p, c_ll, c_p, c_i, c_p]
+
+
+_declare_base = _declare
+
+
+def _declare(L):  # noqa: F811  (extends the base declarations)
+    _declare_base(L)
+    _declare_gsm(L)
+
+
+def workspace_bytes(kind, B, D):
+    n = lib().gsmvi_workspace_bytes(kind, B, D)
+    if n < 0:
+        raise GsmviError("unknown workspace kind %d" % kind)
+    return n
+
+
+def potrf_check(Sigma, L_out, D, bad_flag, ws, npass=3):
+    """L_out <- chol(Sigma[:D,:D]); bad_flag (int32[1] device tensor) <- 0 if PD else 1.  No sync."""
+    check(lib().gsmvi_potrf_check(ptr(Sigma), Sigma.stride(0), ptr(L_out), L_out.stride(0), D, ptr(bad_flag), ptr(ws),
+                                  npass, stream_ptr()), "gsmvi_potrf_check")
+
+
+def philox_normal(Z, B, D, seed, offset):
+    check(lib().gsmvi_philox_normal(ptr(Z), Z.stride(0), B, D, seed & (2**64 - 1), offset & (2**64 - 1), stream_ptr()),
+          "gsmvi_philox_normal")
+
+
+def sample(mu, L_, Z, X, B, D, npass=3):
+    check(lib().gsmvi_sample(ptr(mu), ptr(L_), L_.stride(0), ptr(Z), Z.stride(0), ptr(X), X.stride(0), B, D, npass,
+                             stream_ptr()), "gsmvi_sample")
+
+
+def gauss_score(X, P, c, G, B, D, npass=3):
+    check(lib().gsmvi_gauss_score(ptr(X), X.stride(0), ptr(P), P.stride(0), ptr(c), ptr(G), G.stride(0), B, D, npass,
+                                  stream_ptr()), "gsmvi_gauss_score")
+
+
+def gsm_update_raw(X, G, mu, Sigma, mu_out, Sigma_out, B, D, B_total, mode, ws, npass=3):
+    check(lib().gsmvi_gsm_update(ptr(X), X.stride(0), ptr(G), G.stride(0), ptr(mu), ptr(Sigma), Sigma.stride(0),
+                                 ptr(mu_out), ptr(Sigma_out), Sigma_out.stride(0), B, D, B_total, mode, ptr(ws), npass,
+                                 stream_ptr()), "gsmvi_gsm_update")
+
+
+def gsm_apply_stats(Sigma, dSigma, mu, dmu, Sigma_out, mu_out, D):
+    check(lib().gsmvi_gsm_apply_stats(ptr(Sigma), Sigma.stride(0), ptr(dSigma), dSigma.stride(0), ptr(mu), ptr(dmu),
+                                      ptr(Sigma_out), Sigma_out.stride(0), ptr(mu_out), D, stream_ptr()),
+          "gsmvi_gsm_apply_stats")

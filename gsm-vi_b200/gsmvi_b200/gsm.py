@@ -1,0 +1,180 @@
+"""GSM: Gaussian score matching VI on B200 - drop-in for gsmvi/gsm.py (and gsmvi/gsm_numpy.py) of modichirag/GSM-VI.
+
+Same public surface: `gsm_update(samples, vs, mu0, S0) -> (mu, S)` (gsmvi/gsm.py:31-58) and
+`GSM(D, lp, lp_g).fit(key, mean, cov, batch_size, niter, nprint, verbose, check_goodness, monitor) -> (mean, cov)`
+(gsmvi/gsm.py:62-133).  The loop body runs as sm_100a kernels through libgsmvi_b200.so: blocked Cholesky (PD check +
+sampling factor), X = mu + Z L^T, score, fused GSM update.  Tensors are torch.float32 on the current CUDA device.
+"""
+import torch
+
+from . import _lib as L
+from ._util import device, key_to_seed, ld_of, new_mat, new_vec, to_dev
+
+
+def gsm_update(samples, vs, mu0, S0, npass=3):
+    """Drop-in for gsmvi/gsm.py:31-58.  samples, vs: [B, D]; mu0: [D]; S0: [D, D] (symmetric).  Returns (mu, S) as
+    new CUDA tensors."""
+    dev = device()
+    samples, vs, mu0, S0 = (to_dev(a, dev) for a in (samples, vs, mu0, S0))
+    assert samples.dim() == 2 and vs.dim() == 2  # gsm.py:48-49
+    B, D = samples.shape
+    Xb, X = new_mat(B, D, dev)
+    Gb, G = new_mat(B, D, dev)
+    Sb, S = new_mat(D, D, dev)
+    Ob, O = new_mat(D, D, dev)
+    X.copy_(samples)
+    G.copy_(vs)
+    S.copy_(S0)
+    mu = new_vec(D, dev)
+    mu[:D].copy_(mu0)
+    mu_out = new_vec(D, dev)
+    ws = torch.empty(L.workspace_bytes(L.WS_GSM_UPDATE, B, D) // 4, dtype=torch.float32, device=dev)
+    L.gsm_update_raw(Xb, Gb, mu, Sb, mu_out, Ob, B, D, B, 0, ws, npass)
+    return mu_out[:D].clone(), O.clone()
+
+
+class GSMEngine:
+    """Device-resident state and workspaces of one GSM fit; `step(i)` is one loop body of gsmvi/gsm.py:107-129
+    (sample -> score -> update -> goodness check -> accept/revert).  GSM.fit drives it; bench.py times it."""
+
+    def __init__(self, D, batch_size, lp_g, key, mean=None, cov=None, z_tape=None, npass=3, process_group=None,
+                 score_input="torch"):
+        dev = self.dev = device()
+        self.D, self.batch_size, self.lp_g, self.npass = D, batch_size, lp_g, npass
+        self.group, self.dist, self.rank, self.world = process_group, None, 0, 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.dist = dist
+            self.rank, self.world = dist.get_rank(process_group), dist.get_world_size(process_group)
+        if batch_size % self.world != 0:
+            raise ValueError("batch_size must be divisible by the number of ranks")
+        B = self.B = batch_size // self.world
+        self.seed = key_to_seed(key)
+        self.score_input = score_input
+        # state, double-buffered so a rejected update is simply not swapped in
+        self.Sb, self.S = new_mat(D, D, dev)
+        self.Snb, self.Sn = new_mat(D, D, dev)
+        self.Lb, _ = new_mat(D, D, dev)
+        self.Lnb, _ = new_mat(D, D, dev)
+        self.mu, self.mun = new_vec(D, dev), new_vec(D, dev)
+        if mean is not None:
+            self.mu[:D].copy_(to_dev(mean, dev))  # gsm.py:100-101 (default zeros)
+        if cov is None:
+            self.S.copy_(torch.eye(D, device=dev))  # gsm.py:102-103
+        else:
+            self.S.copy_(to_dev(cov, dev))
+        self.Zb, self.Z = new_mat(B, D, dev)
+        self.Xb, self.X = new_mat(B, D, dev)
+        self.Gb, self.G = new_mat(B, D, dev)
+        self.ws_p = torch.empty(L.workspace_bytes(L.WS_POTRF, B, D) // 4, dtype=torch.float32, device=dev)
+        self.ws_u = torch.empty(L.workspace_bytes(L.WS_GSM_UPDATE, B, D) // 4, dtype=torch.float32, device=dev)
+        self.bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        if self.world > 1:
+            self.dSb, _ = new_mat(D, D, dev)
+            self.dmu = new_vec(D, dev)
+        if z_tape is not None and not isinstance(z_tape, torch.Tensor):
+            z_tape = torch.as_tensor(z_tape, dtype=torch.float32)
+        if z_tape is not None:
+            assert z_tape.shape[1] == batch_size and z_tape.shape[2] == D
+        self.z_tape = z_tape
+        self.target = getattr(getattr(lp_g, "__self__", None), "_gsmvi_builtin_target", None)
+        self.n_reverts = 0
+        L.potrf_check(self.Sb, self.Lb, D, self.bad, self.ws_p, npass)
+        if int(self.bad.item()) != 0:
+            raise ValueError("initial covariance is not positive definite")
+
+    def launches_per_step(self):
+        """Kernels of libgsmvi_b200.so launched by one step (bench.py reports it as gpu_launches)."""
+        panels = (self.D + 127) // 128
+        potrf = 1 + panels + 2 * (panels - 1)
+        upd = 4 if self.B % 32 == 0 else 5
+        return (0 if self.z_tape is not None else 1) + 1 + (1 if self.target is not None else 0) + upd + potrf + \
+            (2 if self.world > 1 else 0)
+
+    def step(self, i):
+        D, B, npass = self.D, self.B, self.npass
+        # ---- sample (gsm.py:117-119)
+        if self.z_tape is not None:
+            self.Z.copy_(self.z_tape[i, self.rank * B:(self.rank + 1) * B], non_blocking=True)
+        else:
+            L.philox_normal(self.Zb, B, D, self.seed, i * self.world + self.rank)
+        L.sample(self.mu, self.Lb, self.Zb, self.Xb, B, D, npass)
+        # ---- score (gsm.py:121)
+        if self.target is not None:
+            L.gauss_score(self.Xb, self.target.Pb, self.target.c, self.Gb, B, D, npass)
+        elif self.score_input == "numpy":
+            self.G.copy_(to_dev(self.lp_g(self.X.cpu().numpy()), self.dev))
+        else:
+            self.G.copy_(to_dev(self.lp_g(self.X), self.dev))
+        # ---- update (gsm.py:122)
+        if self.world == 1:
+            L.gsm_update_raw(self.Xb, self.Gb, self.mu, self.Sb, self.mun, self.Snb, B, D, B, 0, self.ws_u, npass)
+        else:
+            L.gsm_update_raw(self.Xb, self.Gb, self.mu, self.Sb, self.dmu, self.dSb, B, D, self.batch_size, 1,
+                             self.ws_u, npass)
+            self.dist.all_reduce(self.dSb, group=self.group)
+            self.dist.all_reduce(self.dmu, group=self.group)
+            L.gsm_apply_stats(self.Sb, self.dSb, self.mu, self.dmu, self.Snb, self.mun, D)
+        # ---- goodness check = Cholesky of the new covariance, reused as the next sampling factor (gsm.py:125)
+        L.potrf_check(self.Snb, self.Lnb, D, self.bad, self.ws_p, npass)
+        ok = int(self.bad.item()) == 0  # the step's only device->host read (4 bytes)
+        if ok:  # gsm.py:126-127
+            self.Sb, self.Snb, self.S, self.Sn = self.Snb, self.Sb, self.Sn, self.S
+            self.Lb, self.Lnb = self.Lnb, self.Lb
+            self.mu, self.mun = self.mun, self.mu
+        else:
+            self.n_reverts += 1
+        return ok
+
+    def mean(self):
+        return self.mu[: self.D]
+
+    def cov(self):
+        return self.S
+
+
+class GSM:
+    """Wrapper class for using GSM updates to fit a distribution (gsmvi/gsm.py:62-76)."""
+
+    def __init__(self, D, lp, lp_g):
+        """D: number of parameters; lp: target log-probability (used only by the monitor); lp_g: score function,
+        called as lp_g(samples[B, D]) -> [B, D] on CUDA tensors.  A `targets.DenseGaussianTarget.lp_g` bound method is
+        recognised and evaluated by the built-in score GEMM instead of being called."""
+        self.D = D
+        self.lp = lp
+        self.lp_g = lp_g
+
+    def fit(self, key, mean=None, cov=None, batch_size=2, niter=5000, nprint=10, verbose=True, check_goodness=True,
+            monitor=None, *, z_tape=None, npass=3, process_group=None, score_input="torch"):
+        """Main function to fit a multivariate Gaussian to the target (gsmvi/gsm.py:79-133).
+
+        Reference arguments keep their meaning (check_goodness is accepted and, as in the reference, the covariance
+        is always checked; unlike the reference, niter < nprint does not raise ZeroDivisionError).  Extra keyword-only
+        arguments:
+          z_tape: optional [niter+1, batch_size, D] standard-normal draws used instead of the Philox stream
+                  (parity runs: the same tape is fed to the oracle)
+          npass: 3 = 3xTF32 tensor-core passes (fp32-grade), 1 = single TF32 pass
+          process_group: torch.distributed group; the batch is sharded across its ranks and the D x D statistics are
+                  all-reduced (one process per GPU)
+          score_input: "torch" passes CUDA tensors to lp_g; "numpy" passes host arrays (reference-style callables)
+        Returns (mean[D], cov[D, D]) as CUDA tensors."""
+        eng = GSMEngine(self.D, batch_size, self.lp_g, key, mean, cov, z_tape, npass, process_group, score_input)
+        if z_tape is not None:
+            assert eng.z_tape.shape[0] >= niter + 1
+        nevals = 1  # gsm.py:105
+        every = max(niter // max(nprint, 1), 1)
+        i = 0
+        for i in range(niter + 1):  # gsm.py:107
+            if verbose and (i % every == 0):  # gsm.py:108-109
+                print(f"Iteration {i} of {niter}")
+            if monitor is not None and (i % monitor.checkpoint) == 0:  # gsm.py:111-114
+                monitor(i, [eng.mean(), eng.cov()], self.lp, key, nevals=nevals)
+                nevals = 0
+            ok = eng.step(i)
+            nevals += batch_size  # gsm.py:123
+            if not ok and verbose:
+                print("Bad update for covariance matrix. Revert")  # gsm.py:128-129
+        if monitor is not None:  # gsm.py:131-132
+            monitor(i, [eng.mean(), eng.cov()], self.lp, key, nevals=nevals)
+        self.n_reverts = eng.n_reverts
+        return eng.mean().clone(), eng.cov().clone()

@@ -1,0 +1,42 @@
+"""Benchmark targets with a built-in device score.
+
+The reference's examples build a dense Gaussian target and hand GSM/BaM a Python `lp_g` (examples/
+example_gsm_numpy.py:8-31).  `DenseGaussianTarget` is that target with the score evaluated by the library's GEMM
+(G = -(X - m) P); its `lp_g` / `lp` are also ordinary callables on CUDA tensors, so it can be passed wherever a user
+callable is expected."""
+import numpy as np
+import torch
+
+from . import _lib as L
+from ._util import device, new_mat, new_vec
+
+
+class DenseGaussianTarget:
+    def __init__(self, mean, cov, dev=None):
+        dev = dev or device()
+        mean = np.asarray(mean, dtype=np.float64)
+        cov = np.asarray(cov, dtype=np.float64)
+        self.D = mean.shape[0]
+        P = np.linalg.inv(cov)
+        P = (P + P.T) / 2
+        self.mean64, self.cov64, self.P64 = mean, cov, P
+        self.Pb, self.P = new_mat(self.D, self.D, dev)
+        self.P.copy_(torch.as_tensor(P, dtype=torch.float32))
+        self.c = new_vec(self.D, dev)
+        self.c[: self.D].copy_(torch.as_tensor(P @ mean, dtype=torch.float32))
+        self.m = torch.as_tensor(mean, dtype=torch.float32, device=dev)
+        self._gsmvi_builtin_target = self
+
+    def lp_g(self, x):
+        """Score -(x - m) P, [B, D] -> [B, D] (examples/example_gsm_numpy.py:24-29), via the device GEMM."""
+        B = x.shape[0]
+        Xb, X = new_mat(B, self.D, x.device)
+        X.copy_(x)
+        Gb, G = new_mat(B, self.D, x.device)
+        L.gauss_score(Xb, self.Pb, self.c, Gb, B, self.D)
+        return G
+
+    def lp(self, x):
+        """Sum over the batch of the unnormalised log density (examples/example_gsm.py:34 convention)."""
+        d = x.to(torch.float32) - self.m
+        return -0.5 * torch.sum((d @ self.P) * d)

@@ -1,7 +1,15 @@
-/* gsmvi_b200.h - C ABI of libgsmvi_b200.so (work in progress).
- * All pointers are DEVICE pointers unless a name ends in _host. All functions are stream-ordered,
- * never synchronise unless documented, and return 0 on success, <0 for an invalid argument
- * (GSMVI_E*), >0 for a cudaError_t. */
+/* gsmvi_b200.h - C ABI of libgsmvi_b200.so: the B200-native GSM / BaM hot path of modichirag/GSM-VI.
+ *
+ * The reference has no FFI boundary (its boundary is the Python API); these entry points are
+ * what a replacement of its per-iteration host/XLA calls binds.  Each one names the reference code it replaces
+ * (paths relative to the reference repository).  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions: every pointer is a DEVICE pointer (fp32, row-major, leading dimension in elements, a multiple of 4,
+ * base 16-byte aligned) unless its name ends in _host.  Every function is ordered on `stream` (a cudaStream_t),
+ * never synchronises, never allocates, and returns 0 on success, <0 for an invalid argument (GSMVI_E*), >0 for a
+ * cudaError_t.  `npass` selects tensor-core precision: 3 = 3xTF32 with round-to-nearest split (fp32-grade, default),
+ * 2 = 3xTF32 with truncation split (faster, ~8x larger product error), 1 = single-pass TF32.
+ */
 #ifndef GSMVI_B200_H
 #define GSMVI_B200_H
 #ifdef __cplusplus
@@ -10,12 +18,61 @@ extern "C" {
 
 #define GSMVI_ABI_VERSION 1
 
+#define GSMVI_OK 0
+#define GSMVI_EINVAL (-1)     /* bad size / null pointer */
+#define GSMVI_EALIGN (-2)     /* pointer or leading dimension not 16-byte aligned */
+#define GSMVI_EDRIVER (-3)    /* cuTensorMapEncodeTiled unavailable / failed */
+#define GSMVI_EWORKSPACE (-4)
+
+/* workspace kinds for gsmvi_workspace_bytes */
+#define GSMVI_WS_POTRF 1
+#define GSMVI_WS_GSM_UPDATE 2
+
 int gsmvi_abi_version(void);
 
+/* Bytes of device scratch the call of that kind needs for batch B, dimension D (-1: unknown kind). */
+long long gsmvi_workspace_bytes(int kind, int B, int D);
+
+/* General tensor-core contraction C[M,N] = alpha * op(A) op(B)^T + beta * Cin + bias_n (diagnostics and tests; the
+ * engine under every call below).  a_mn/b_mn: operand stored [K, rows] instead of [rows, K]. */
 int gsmvi_gemm_tf32(const float* A, long long a_rows, long long a_cols, long long lda, int a_mn, const float* B,
                     long long b_rows, long long b_cols, long long ldb, int b_mn, float* C, long long ldc, int M, int N,
                     int K, float alpha, float beta, const float* Cin, long long ldcin, const float* bias_n, int npass,
                     int tri, int mirror, int krange, int neg_from, void* stream);
+
+/* L <- chol(Sigma) (lower, upper triangle zeroed), *bad_flag <- 0 if Sigma is positive definite else 1.
+ * Replaces GSM._check_goodness / BaM._check_goodness (gsmvi/gsm.py:136-150, gsmvi/bam.py:219-233: host
+ * np.linalg.cholesky) and the factorisation inside the sampler (gsmvi/gsm.py:119, gsmvi/bam.py:193). */
+int gsmvi_potrf_check(const float* Sigma, long long lds, float* L, long long ldl, int D, int* bad_flag,
+                      void* workspace, int npass, void* stream);
+
+/* Z[B,D] <- N(0,1), Philox4x32-10 keyed by seed, counter (element, offset).  Replaces the host RNG of
+ * np.random.seed / np.random.multivariate_normal (gsmvi/gsm.py:117-119). */
+int gsmvi_philox_normal(float* Z, long long ldz, int B, int D, unsigned long long seed, unsigned long long offset,
+                        void* stream);
+
+/* X[B,D] = mu + Z L^T : samples of N(mu, L L^T).  Replaces np.random.multivariate_normal (gsmvi/gsm.py:119,
+ * gsmvi/bam.py:193, gsmvi/monitors.py:106). */
+int gsmvi_sample(const float* mu, const float* L, long long ldl, const float* Z, long long ldz, float* X,
+                 long long ldx, int B, int D, int npass, void* stream);
+
+/* G[B,D] = -(X - m) P = -X P + c with c = P m: batched score of a dense Gaussian target.  Replaces lp_g of the
+ * benchmark targets (examples/example_gsm_numpy.py:24-29, examples/example_gsm.py:34-35). */
+int gsmvi_gauss_score(const float* X, long long ldx, const float* P, long long ldp, const float* c, float* G,
+                      long long ldg, int B, int D, int npass, void* stream);
+
+/* Fused GSM batch update.  Replaces gsm_update (gsmvi/gsm.py:31-58; _gsm_update_single gsmvi/gsm.py:8-28).
+ * mode 0: mu_out = mu + mean_b u_b, Sigma_out = Sigma + (D^T D - E^T E)/B_total (B_total == B).
+ * mode 1: partial statistics of a batch shard: mu_out = sum_b u_b / B_total, Sigma_out = (D^T D - E^T E)/B_total,
+ *         to be summed over shards (all-reduce) and applied with gsmvi_gsm_apply_stats.
+ * workspace: gsmvi_workspace_bytes(GSMVI_WS_GSM_UPDATE, B, D). Sigma_out must not alias Sigma. */
+int gsmvi_gsm_update(const float* X, long long ldx, const float* G, long long ldg, const float* mu,
+                     const float* Sigma, long long lds, float* mu_out, float* Sigma_out, long long ldso, int B, int D,
+                     int B_total, int mode, void* workspace, int npass, void* stream);
+
+/* Sigma_out = Sigma + dSigma, mu_out = mu + dmu (after the all-reduce of mode-1 statistics). */
+int gsmvi_gsm_apply_stats(const float* Sigma, long long lds, const float* dSigma, long long ldd, const float* mu,
+                          const float* dmu, float* Sigma_out, long long ldso, float* mu_out, int D, void* stream);
 
 #ifdef __cplusplus
 }

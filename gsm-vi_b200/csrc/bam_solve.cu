@@ -1,0 +1,505 @@
+// BaM covariance solve on the device.
+//
+// Reference (gsmvi/bam.py:59-67):  U = reg*Gamma + reg/(1+reg) gbar gbar^T,  V = S0 + reg*C + reg/(1+reg) (mu0-xbar)(mu0-xbar)^T,
+//   S = 2 (I + sqrtm(I + 4UV)^T)^{-1} V^T   (solves S U S + S = V; host scipy.linalg.sqrtm of a non-symmetric matrix),
+//   mu = mu0/(1+reg) + reg/(1+reg) (S gbar + xbar).
+// Device restatement (oracle/gsmvi_oracle.py bam_update): V = L L^T, M = I + 4 L^T U L (SPD, eigenvalues >= 1),
+//   N = M^{1/2} by a GEMM-bound coupled Newton-Schulz iteration, I + N = R R^T, T = L R^{-T}, S = 2 T T^T - symmetric
+//   PSD by construction, algebraically identical.  Low-rank variant (bam.py:72-114) with the exact factor
+//   Q = [sqrt(reg/B) (G-gbar)^T, sqrt(reg/(1+reg)) gbar] of U instead of a truncated SVD (Q Q^T = U, S is invariant).
+// Statistics (B-proportional) run in 3xTF32 on the tensor cores; everything D x D / K x K here is fp64 (dgemm.cu).
+#include "bam_solve.cuh"
+
+#include <math.h>
+
+#include "dgemm.cuh"
+
+namespace gsmvi {
+
+constexpr int NB64 = 64;
+constexpr int L64S = NB64 + 1;
+
+// ------------------------------------------------------------------------------------------------ small kernels
+
+// fp64 diagonal block (n <= 64): in-place Cholesky + inverse, one CTA; same contract as potrf_diag_kernel (potrf.cu).
+__global__ void __launch_bounds__(256, 1) potrf64_diag_kernel(double* __restrict__ a, long long lda, int n,
+                                                              double* __restrict__ linv, int* __restrict__ flag) {
+  extern __shared__ __align__(16) double sm64[];
+  double* s = sm64;
+  double* x = sm64 + NB64 * L64S;
+  __shared__ int bad;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) bad = 0;
+  for (int idx = tid; idx < NB64 * NB64; idx += 256) {
+    const int i = idx / NB64, j = idx % NB64;
+    s[i * L64S + j] = (i < n && j <= i) ? a[static_cast<long long>(i) * lda + j] : ((i == j) ? 1.0 : 0.0);
+    x[i * L64S + j] = 0.0;
+  }
+  for (int j = 0; j < n; ++j) {
+    __syncthreads();
+    const double p = s[j * L64S + j];
+    if (!(p > 0.0) || isinf(p)) {
+      if (tid == 0) bad = 1;
+    }
+    const double ip = 1.0 / p;
+    for (int i = j + 1 + warp; i < n; i += 8) {
+      const double lij = s[i * L64S + j] * ip;
+      for (int k = j + 1 + lane; k <= i; k += 32) s[i * L64S + k] -= lij * s[k * L64S + j];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < NB64 * NB64; idx += 256) {
+    const int i = idx / NB64, j = idx % NB64;
+    // scale columns lazily: L[i][j] = s[i][j] / sqrt(s[j][j]) below the diagonal
+    double v = 0.0;
+    if (j < i) v = s[i * L64S + j] / sqrt(s[j * L64S + j]);
+    x[i * L64S + j] = v;  // stage in x so the diagonal is still intact for other threads
+  }
+  __syncthreads();
+  for (int idx = tid; idx < NB64 * NB64; idx += 256) {
+    const int i = idx / NB64, j = idx % NB64;
+    s[i * L64S + j] = (j < i) ? x[i * L64S + j] : ((j == i) ? sqrt(s[i * L64S + i]) : 0.0);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < NB64 * NB64; idx += 256) x[(idx / NB64) * L64S + idx % NB64] = 0.0;
+  __syncthreads();
+  // inverse: thread c solves L y = e_c (column c of the inverse), all threads walk the same (i, k): broadcast reads of L
+  if (tid < NB64) {
+    const int c = tid;
+    for (int i = c; i < NB64; ++i) {
+      double acc = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; ++k) acc -= s[i * L64S + k] * x[k * L64S + c];
+      x[i * L64S + c] = acc / s[i * L64S + i];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < NB64 * NB64; idx += 256) {
+    const int i = idx / NB64, j = idx % NB64;
+    if (i < n && j < n) a[static_cast<long long>(i) * lda + j] = s[i * L64S + j];
+    linv[i * NB64 + j] = (i < n && j < n) ? x[i * L64S + j] : 0.0;
+  }
+  if (tid == 0 && bad) atomicOr(flag, 1);
+}
+
+// zero the strict upper triangle (and optionally symmetrise from the lower one)
+__global__ void tril64_kernel(double* __restrict__ A, long long lda, int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = blockIdx.y;
+  if (j < n && j > i) A[i * lda + j] = 0.0;
+}
+
+// U64 = reg*Gam + w gbar gbar^T ; V64 = S0 + reg*C + w dm dm^T   (w = reg/(1+reg), dm = mu0 - xbar)   bam.py:59-60
+__global__ void bam_uv_kernel(const float* __restrict__ Gam, long long ldg, const float* __restrict__ C, long long ldc,
+                              const float* __restrict__ S0, long long lds, const float* __restrict__ gbar,
+                              const float* __restrict__ xbar, const float* __restrict__ mu0, double reg,
+                              double* __restrict__ U, double* __restrict__ V, long long ldu, int D) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = blockIdx.y;
+  if (j >= D) return;
+  const double w = reg / (1.0 + reg);
+  const double gi = gbar[i], gj = gbar[j];
+  const double di = static_cast<double>(mu0[i]) - xbar[i], dj = static_cast<double>(mu0[j]) - xbar[j];
+  U[i * ldu + j] = reg * static_cast<double>(Gam[i * ldg + j]) + w * gi * gj;
+  V[i * ldu + j] = static_cast<double>(S0[i * lds + j]) + reg * static_cast<double>(C[i * ldc + j]) + w * di * dj;
+}
+
+// A = scale * A (+ diag_add on the diagonal)
+__global__ void scale_diag64_kernel(double* __restrict__ A, long long lda, int n, double scale, double diag_add) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = blockIdx.y;
+  if (j < n) A[i * lda + j] = scale * A[i * lda + j] + ((i == j) ? diag_add : 0.0);
+}
+
+__global__ void set_identity64_kernel(double* __restrict__ A, long long lda, int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = blockIdx.y;
+  if (j < n) A[i * lda + j] = (i == j) ? 1.0 : 0.0;
+}
+
+// out[0] += sum_ij (A[i][j] - d*delta_ij)^2 ; out[1] = max(out[1], max_i sum_j |A[i][j]|)  (inf-norm, via atomics on bits)
+__global__ void frob_inf64_kernel(const double* __restrict__ A, long long lda, int n, double d, double* __restrict__ out) {
+  const long long i = blockIdx.x;
+  double ss = 0.0, rs = 0.0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const double v = A[i * lda + j];
+    const double e = v - ((i == j) ? d : 0.0);
+    ss += e * e;
+    rs += fabs(v);
+  }
+  __shared__ double s1[256], s2[256];
+  s1[threadIdx.x] = ss;
+  s2[threadIdx.x] = rs;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s1[threadIdx.x] += s1[threadIdx.x + o];
+      s2[threadIdx.x] += s2[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    atomicAdd(out, s1[0]);
+    // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(out + 1), static_cast<unsigned long long>(__double_as_longlong(s2[0])));
+  }
+}
+
+// S32 = (float)(scale*S64) + jitter*I, symmetric by construction of S64 ; bam.py:198-199
+__global__ void bam_finish_cov_kernel(const double* __restrict__ S64, long long lds64, float* __restrict__ S32,
+                                      long long lds32, int D, double scale, double jitter) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = blockIdx.y;
+  if (j < D) {
+    // (cov + cov^T)/2 of bam.py:199: S64 is already exactly symmetric (mirrored stores), so this is the identity
+    const double v = 0.5 * (scale * S64[i * lds64 + j] + scale * S64[j * lds64 + i]) + ((i == j) ? jitter : 0.0);
+    S32[i * lds32 + j] = static_cast<float>(v);
+  }
+}
+
+// mu_out = mu0/(1+reg) + reg/(1+reg) (S gbar + xbar)   bam.py:67 ; one warp per row, fp64 S
+__global__ void bam_mean_kernel(const double* __restrict__ S64, long long lds, double scale, const float* __restrict__ gbar,
+                                const float* __restrict__ xbar, const float* __restrict__ mu0, double reg,
+                                float* __restrict__ mu_out, int D) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= D) return;
+  double acc = 0.0;
+  for (int j = lane; j < D; j += 32) acc += S64[static_cast<long long>(row) * lds + j] * static_cast<double>(gbar[j]);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0)
+    mu_out[row] = static_cast<float>(static_cast<double>(mu0[row]) / (1.0 + reg) +
+                                     reg / (1.0 + reg) * (scale * acc + static_cast<double>(xbar[row])));
+}
+
+// column sums of X and G: out_x[j] += sum_b X[b][j] (over this CTA's rows)
+constexpr int CS_ROWS = 32;
+__global__ void colsum2_kernel(const float* __restrict__ X, long long ldx, const float* __restrict__ G, long long ldg,
+                               int B, int D, float* __restrict__ sx, float* __restrict__ sg) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r0 = blockIdx.y * CS_ROWS;
+  if (j >= D) return;
+  float ax = 0.f, ag = 0.f;
+  const int r1 = min(r0 + CS_ROWS, B);
+  for (int b = r0; b < r1; ++b) {
+    ax += X[b * ldx + j];
+    ag += G[b * ldg + j];
+  }
+  atomicAdd(sx + j, ax);
+  atomicAdd(sg + j, ag);
+}
+
+// xbar = sx / Btot, gbar = sg / Btot (in place), then T = [X - xbar ; G - gbar]  ([2B, D] row-major)
+__global__ void center2_kernel(const float* __restrict__ X, long long ldx, const float* __restrict__ G, long long ldg,
+                               int B, int D, const float* __restrict__ xbar, const float* __restrict__ gbar,
+                               float* __restrict__ T, long long ldt) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long b = blockIdx.y;
+  if (j >= D) return;
+  T[b * ldt + j] = X[b * ldx + j] - xbar[j];
+  T[(b + B) * ldt + j] = G[b * ldg + j] - gbar[j];
+}
+
+__global__ void scale_vec2_kernel(float* __restrict__ a, float* __restrict__ b, float s, int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) {
+    a[j] *= s;
+    b[j] *= s;
+  }
+}
+
+// Q64[i][k] = sqrt(reg/Btot) * Gc[k][i]  (k < B) ; Q64[i][B] = sqrt(reg/(1+reg)) * gbar[i]   -> Q stored [D, K] row-major
+__global__ void bam_build_q_kernel(const float* __restrict__ Gc, long long ldgc, const float* __restrict__ gbar, int B,
+                                   int D, double reg, int Btot, double* __restrict__ Q, long long ldq) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = blockIdx.y;
+  if (k > B) return;
+  Q[i * ldq + k] = (k < B) ? sqrt(reg / Btot) * static_cast<double>(Gc[static_cast<long long>(k) * ldgc + i])
+                           : sqrt(reg / (1.0 + reg)) * static_cast<double>(gbar[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ fp64 building blocks
+
+static inline dim3 grid2(int n, int rows) { return dim3((n + 255) / 256, rows); }
+static inline cudaError_t last() { return cudaGetLastError(); }
+#define GSMVI_TRY(x)                \
+  do {                              \
+    int rc__ = (x);                 \
+    if (rc__ != GSMVI_OK) return rc__; \
+  } while (0)
+#define GSMVI_CUDA(x)                                          \
+  do {                                                         \
+    cudaError_t e__ = (x);                                     \
+    if (e__ != cudaSuccess) return static_cast<int>(e__);      \
+  } while (0)
+
+// In-place blocked Cholesky of the lower triangle of A (n x n fp64); upper triangle zeroed.  dinv receives the inverse
+// of every 64x64 diagonal block ([ceil(n/64)] x 64 x 64).  flag |= 1 on a bad pivot.
+static int potrf64_inplace(cudaStream_t st, double* A, long long lda, int n, double* dinv, int* flag) {
+  const int smem = 2 * NB64 * L64S * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GSMVI_CUDA(cudaFuncSetAttribute(potrf64_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  tril64_kernel<<<grid2(n, n), 256, 0, st>>>(A, lda, n);
+  for (int j0 = 0, blk = 0; j0 < n; j0 += NB64, ++blk) {
+    const int nb = min(NB64, n - j0), rest = n - j0 - nb;
+    double* a11 = A + static_cast<long long>(j0) * lda + j0;
+    double* inv = dinv + static_cast<long long>(blk) * NB64 * NB64;
+    potrf64_diag_kernel<<<1, 256, smem, st>>>(a11, lda, nb, inv, flag);
+    if (rest > 0) {
+      double* a21 = A + static_cast<long long>(j0 + nb) * lda + j0;
+      double* a22 = A + static_cast<long long>(j0 + nb) * lda + j0 + nb;
+      DgemmOpts t;  // L21 = A21 inv(L11)^T, in place (one tile column: each CTA reads only the rows it overwrites)
+      GSMVI_TRY(launch_dgemm(st, rest, nb, nb, a21, lda, false, inv, NB64, false, a21, lda, t));
+      DgemmOpts s;  // A22 -= L21 L21^T (lower)
+      s.alpha = -1.0;
+      s.beta = 1.0;
+      s.Cin = a22;
+      s.ldcin = lda;
+      s.tri = true;
+      GSMVI_TRY(launch_dgemm(st, rest, rest, nb, a21, lda, false, a21, lda, false, a22, lda, s));
+    }
+  }
+  GSMVI_CUDA(last());
+  return GSMVI_OK;
+}
+
+// T (m x n) <- Bm R^{-T}  i.e. solve T R^T = Bm for lower-triangular R (n x n) whose diagonal-block inverses are in dinv.
+// Bm and T may alias.  Left-looking over 64-column blocks: T_j = (Bm_j - T[:, :j0] R[j, :j0]^T) inv(R_jj)^T.
+static int trsm64_right_lt(cudaStream_t st, const double* Bm, long long ldb, const double* R, long long ldr,
+                           const double* dinv, double* T, long long ldt, int m, int n) {
+  for (int j0 = 0, blk = 0; j0 < n; j0 += NB64, ++blk) {
+    const int nb = min(NB64, n - j0);
+    double* tj = T + j0;
+    if (j0 > 0) {
+      DgemmOpts o;
+      o.alpha = -1.0;
+      o.beta = 1.0;
+      o.Cin = Bm + j0;
+      o.ldcin = ldb;
+      GSMVI_TRY(launch_dgemm(st, m, nb, j0, T, ldt, false, R + static_cast<long long>(j0) * ldr, ldr, false, tj, ldt, o));
+    } else if (T != Bm) {
+      GSMVI_CUDA(cudaMemcpy2DAsync(tj, ldt * sizeof(double), Bm, ldb * sizeof(double), nb * sizeof(double), m,
+                                   cudaMemcpyDeviceToDevice, st));
+    }
+    DgemmOpts o2;  // in place: one tile column
+    GSMVI_TRY(launch_dgemm(st, m, nb, nb, tj, ldt, false, dinv + static_cast<long long>(blk) * NB64 * NB64, NB64, false, tj,
+                           ldt, o2));
+  }
+  return GSMVI_OK;
+}
+
+// Coupled Newton-Schulz square root of the SPD matrix in Y (n x n, overwritten):  on return Y ~= M^{1/2}.
+// Y0 = M/c, Z0 = I;  P = (3I - Z Y)/2;  Y <- Y P;  Z <- P Z   (SURVEY.md section 8a row B2).  c = ||M||_inf >= lambda_max.
+// Needs 4 scratch n x n buffers.  Synchronises the stream once per iteration to read the residual ||I - ZY||_F.
+static int ns_sqrt64(cudaStream_t st, double* Y, long long ld, int n, double* Z, double* P, double* Y2, double* Z2,
+                     double* scal_dev, int max_iter, double tol, int* iters_out) {
+  double h[2];
+  GSMVI_CUDA(cudaMemsetAsync(scal_dev, 0, 2 * sizeof(double), st));
+  frob_inf64_kernel<<<n, 256, 0, st>>>(Y, ld, n, 0.0, scal_dev);
+  GSMVI_CUDA(cudaMemcpyAsync(h, scal_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GSMVI_CUDA(cudaStreamSynchronize(st));
+  const double c = h[1];
+  if (!(c > 0.0) || isinf(c) || isnan(c)) {
+    *iters_out = -1;
+    return GSMVI_OK;  // caller sees NaNs downstream; the PD check rejects the update
+  }
+  scale_diag64_kernel<<<grid2(n, n), 256, 0, st>>>(Y, ld, n, 1.0 / c, 0.0);
+  set_identity64_kernel<<<grid2(n, n), 256, 0, st>>>(Z, ld, n);
+  int it = 0;
+  bool last_round = false;
+  for (; it < max_iter; ++it) {
+    DgemmOpts p;  // P = 1.5 I - 0.5 Z Y      (Y symmetric: Y[k][j] read as Y[j][k])
+    p.alpha = -0.5;
+    p.diag_add = 1.5;
+    GSMVI_TRY(launch_dgemm(st, n, n, n, Z, ld, false, Y, ld, false, P, ld, p));
+    GSMVI_CUDA(cudaMemsetAsync(scal_dev, 0, 2 * sizeof(double), st));
+    frob_inf64_kernel<<<n, 256, 0, st>>>(P, ld, n, 1.0, scal_dev);  // ||P - I||_F = ||I - ZY||_F / 2
+    DgemmOpts o;
+    GSMVI_TRY(launch_dgemm(st, n, n, n, Y, ld, false, P, ld, true, Y2, ld, o));   // Y2 = Y P
+    GSMVI_TRY(launch_dgemm(st, n, n, n, P, ld, false, Z, ld, true, Z2, ld, o));   // Z2 = P Z
+    double* t = Y; Y = Y2; Y2 = t;
+    t = Z; Z = Z2; Z2 = t;
+    if (last_round) { ++it; break; }
+    GSMVI_CUDA(cudaMemcpyAsync(h, scal_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GSMVI_CUDA(cudaStreamSynchronize(st));
+    const double res = 2.0 * sqrt(h[0]);
+    if (isnan(res)) { ++it; break; }
+    if (res < tol) { ++it; break; }            // this update already used P with ||I - ZY|| < tol: converged
+    if (res < 1e-4) last_round = true;         // quadratic convergence: one more update reaches ~1e-9 or better
+  }
+  *iters_out = it;
+  // result lives in the current Y; if that is the caller's Y2 buffer, copy back (odd number of swaps)
+  if (it % 2 == 1) GSMVI_CUDA(cudaMemcpy2DAsync(Y2, ld * sizeof(double), Y, ld * sizeof(double), n * sizeof(double), n,
+                                                cudaMemcpyDeviceToDevice, st));
+  scale_diag64_kernel<<<grid2(n, n), 256, 0, st>>>((it % 2 == 1) ? Y2 : Y, ld, n, sqrt(c), 0.0);
+  GSMVI_CUDA(last());
+  return GSMVI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ public pieces
+
+static inline long long rup(long long v, long long m) { return (v + m - 1) / m * m; }
+
+size_t bam_stats_workspace_bytes(int B, int D) {
+  const long long ld = rup(D, 32);
+  // T = [Xc; Gc] [2B x ld] + C [D x ld] + Gam [D x ld] + xbar, gbar [2 ld]
+  return static_cast<size_t>((2LL * B + 2LL * D + 2) * ld) * sizeof(float);
+}
+
+size_t bam_solve_workspace_bytes(int B, int D, int lowrank) {
+  const long long ld = rup(D, 8);
+  const long long nblk = (D + NB64 - 1) / NB64;
+  if (!lowrank) {
+    // 6 D x D fp64 buffers + 2 sets of diagonal-block inverses + scalars
+    return static_cast<size_t>(6 * D * ld + 2 * nblk * NB64 * NB64 + 16) * sizeof(double);
+  }
+  const long long K = B + 1, ldk = rup(K, 8), kblk = (K + NB64 - 1) / NB64;
+  // U-free: V [D x ld], Q [D x ldk], A = VQ [D x ldk], W = A F [D x ldk], S [D x ld], 6 K x K buffers, inverses, scalars
+  return static_cast<size_t>(2 * D * ld + 3 * D * ldk + 6 * K * ldk + kblk * NB64 * NB64 + 16) * sizeof(double);
+}
+
+int bam_stats(cudaStream_t st, const float* X, long long ldx, const float* G, long long ldg, int B, int D, int Btot,
+              float* ws, int npass, int stage) {
+  // stage 0: column sums into xbar/gbar (unnormalised; all-reduce them across shards before stage 1)
+  // stage 1: xbar,gbar /= Btot; T = [X - xbar; G - gbar]; C = Xc^T Xc / Btot; Gam = Gc^T Gc / Btot (partial over this shard)
+  const long long ld = rup(D, 32);
+  float* T = ws;
+  float* C = T + 2LL * B * ld;
+  float* Gam = C + static_cast<long long>(D) * ld;
+  float* xbar = Gam + static_cast<long long>(D) * ld;
+  float* gbar = xbar + ld;
+  if (stage == 0) {
+    GSMVI_CUDA(cudaMemsetAsync(xbar, 0, 2 * ld * sizeof(float), st));
+    colsum2_kernel<<<dim3((D + 255) / 256, (B + CS_ROWS - 1) / CS_ROWS), 256, 0, st>>>(X, ldx, G, ldg, B, D, xbar, gbar);
+    GSMVI_CUDA(last());
+    return GSMVI_OK;
+  }
+  scale_vec2_kernel<<<(D + 255) / 256, 256, 0, st>>>(xbar, gbar, 1.0f / static_cast<float>(Btot), D);
+  center2_kernel<<<grid2(D, B), 256, 0, st>>>(X, ldx, G, ldg, B, D, xbar, gbar, T, ld);
+  GemmOpts o;
+  o.npass = npass;
+  o.a_mn = o.b_mn = true;
+  o.alpha = 1.0f / static_cast<float>(Btot);
+  o.tri = true;
+  o.mirror = true;
+  MatView vx{T, B, D, ld}, vg{T + static_cast<long long>(B) * ld, B, D, ld};
+  GSMVI_TRY(launch_gemm_tf32(st, D, D, B, vx, vx, C, ld, o));
+  GSMVI_TRY(launch_gemm_tf32(st, D, D, B, vg, vg, Gam, ld, o));
+  GSMVI_CUDA(last());
+  return GSMVI_OK;
+}
+
+int bam_solve_full(cudaStream_t st, const float* stats_ws, int B, int D, const float* mu0, const float* S0, long long lds0,
+                   double reg, double jitter, float* mu_out, float* S_out, long long ldso, double* ws, int max_ns,
+                   int* ns_iters_host, int* flag) {
+  const long long ld32 = rup(D, 32), ld = rup(D, 8);
+  const float* C = stats_ws + 2LL * B * ld32;
+  const float* Gam = C + static_cast<long long>(D) * ld32;
+  const float* xbar = Gam + static_cast<long long>(D) * ld32;
+  const float* gbar = xbar + ld32;
+  double* b0 = ws;                  // U      -> Z2
+  double* b1 = b0 + D * ld;         // V -> L (kept)
+  double* b2 = b1 + D * ld;         // U L    -> Z
+  double* b3 = b2 + D * ld;         // M      -> Y
+  double* b4 = b3 + D * ld;         // P      -> T = L R^{-T}
+  double* b5 = b4 + D * ld;         // Y2     -> S
+  const long long nblk = (D + NB64 - 1) / NB64;
+  double* dinvL = b5 + D * ld;
+  double* dinvR = dinvL + nblk * NB64 * NB64;
+  double* scal = dinvR + nblk * NB64 * NB64;
+  GSMVI_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  bam_uv_kernel<<<grid2(D, D), 256, 0, st>>>(Gam, ld32, C, ld32, S0, lds0, gbar, xbar, mu0, reg, b0, b1, ld, D);
+  GSMVI_TRY(potrf64_inplace(st, b1, ld, D, dinvL, flag));                          // V = L L^T
+  DgemmOpts o;
+  o.krange = KR_B_UPPER;  // B operand is L^T given as MN-major L: L[k][j] == 0 for k < j
+  GSMVI_TRY(launch_dgemm(st, D, D, D, b0, ld, false, b1, ld, true, b2, ld, o));    // b2 = U L
+  DgemmOpts m;
+  m.alpha = 4.0;
+  m.diag_add = 1.0;
+  m.tri = true;
+  m.mirror = true;
+  m.krange = KR_A_UPPER;  // A operand is L^T given as MN-major L: (L^T)[i][k] = L[k][i] == 0 for k < i
+  GSMVI_TRY(launch_dgemm(st, D, D, D, b1, ld, true, b2, ld, true, b3, ld, m));     // M = I + 4 L^T (U L)
+  int iters = 0;
+  GSMVI_TRY(ns_sqrt64(st, b3, ld, D, b2, b4, b5, b0, scal, max_ns, 1e-11, &iters));  // b3 = N = M^{1/2}
+  if (ns_iters_host) *ns_iters_host = iters;
+  scale_diag64_kernel<<<grid2(D, D), 256, 0, st>>>(b3, ld, D, 1.0, 1.0);          // I + N
+  GSMVI_TRY(potrf64_inplace(st, b3, ld, D, dinvR, flag));                          // I + N = R R^T
+  GSMVI_TRY(trsm64_right_lt(st, b1, ld, b3, ld, dinvR, b4, ld, D, D));             // T = L R^{-T}
+  DgemmOpts s;
+  s.tri = true;
+  s.mirror = true;
+  GSMVI_TRY(launch_dgemm(st, D, D, D, b4, ld, false, b4, ld, false, b5, ld, s));   // b5 = T T^T ; S = 2 b5
+  bam_mean_kernel<<<(D + 7) / 8, 256, 0, st>>>(b5, ld, 2.0, gbar, xbar, mu0, reg, mu_out, D);
+  bam_finish_cov_kernel<<<grid2(D, D), 256, 0, st>>>(b5, ld, S_out, ldso, D, 2.0, jitter);
+  GSMVI_CUDA(last());
+  return GSMVI_OK;
+}
+
+int bam_solve_lowrank(cudaStream_t st, const float* stats_ws, int B, int D, int Btot, const float* mu0, const float* S0,
+                      long long lds0, double reg, double jitter, float* mu_out, float* S_out, long long ldso, double* ws,
+                      int max_ns, int* ns_iters_host, int* flag) {
+  // bam.py:102-112 with Q Q^T = U exactly:  A = V Q;  H = Q^T V Q + I/4;  BB = (I/2 + H^{1/2})^2;  S = V - A BB^{-1} A^T.
+  // BB^{-1} = F^2 with F = (I/2 + H^{1/2})^{-1} = T1 T1^T, T1 = R2^{-T}, (I/2 + H^{1/2}) = R2 R2^T; S = V - (A F)(A F)^T.
+  const long long ld32 = rup(D, 32), ld = rup(D, 8);
+  const int K = B + 1;
+  const long long ldk = rup(K, 8), kblk = (K + NB64 - 1) / NB64;
+  const float* Tc = stats_ws;  // [Xc; Gc]
+  const float* C = stats_ws + 2LL * B * ld32;
+  const float* Gam = C + static_cast<long long>(D) * ld32;
+  const float* xbar = Gam + static_cast<long long>(D) * ld32;
+  const float* gbar = xbar + ld32;
+  double* V = ws;
+  double* Sb = V + D * ld;
+  double* Q = Sb + D * ld;
+  double* A = Q + D * ldk;
+  double* W = A + D * ldk;
+  double* k0 = W + D * ldk;  // H -> Y
+  double* k1 = k0 + K * ldk;
+  double* k2 = k1 + K * ldk;
+  double* k3 = k2 + K * ldk;
+  double* k4 = k3 + K * ldk;
+  double* k5 = k4 + K * ldk;
+  double* dinv = k5 + K * ldk;
+  double* scal = dinv + kblk * NB64 * NB64;
+  GSMVI_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  // V (fp64) from the statistics; U is not formed (Sb is used as the dummy U output)
+  bam_uv_kernel<<<grid2(D, D), 256, 0, st>>>(Gam, ld32, C, ld32, S0, lds0, gbar, xbar, mu0, reg, Sb, V, ld, D);
+  bam_build_q_kernel<<<dim3((K + 255) / 256, D), 256, 0, st>>>(Tc + static_cast<long long>(B) * ld32, ld32, gbar, B, D, reg,
+                                                               Btot, Q, ldk);
+  DgemmOpts o;
+  GSMVI_TRY(launch_dgemm(st, D, K, D, V, ld, false, Q, ldk, true, A, ldk, o));     // A = V Q   (V symmetric)
+  DgemmOpts h;
+  h.diag_add = 0.25;
+  h.tri = true;
+  h.mirror = true;
+  GSMVI_TRY(launch_dgemm(st, K, K, D, A, ldk, true, Q, ldk, true, k0, ldk, h));    // H = A^T Q + I/4
+  int iters = 0;
+  GSMVI_TRY(ns_sqrt64(st, k0, ldk, K, k1, k2, k3, k4, scal, max_ns, 1e-11, &iters));
+  if (ns_iters_host) *ns_iters_host = iters;
+  scale_diag64_kernel<<<grid2(K, K), 256, 0, st>>>(k0, ldk, K, 1.0, 0.5);          // I/2 + H^{1/2}
+  GSMVI_TRY(potrf64_inplace(st, k0, ldk, K, dinv, flag));                          // = R2 R2^T
+  set_identity64_kernel<<<grid2(K, K), 256, 0, st>>>(k1, ldk, K);
+  GSMVI_TRY(trsm64_right_lt(st, k1, ldk, k0, ldk, dinv, k1, ldk, K, K));           // T1 = R2^{-T}
+  DgemmOpts f;
+  f.tri = true;
+  f.mirror = true;
+  GSMVI_TRY(launch_dgemm(st, K, K, K, k1, ldk, false, k1, ldk, false, k2, ldk, f));  // F = T1 T1^T
+  GSMVI_TRY(launch_dgemm(st, D, K, K, A, ldk, false, k2, ldk, false, W, ldk, o));    // W = A F  (F symmetric)
+  DgemmOpts s;
+  s.alpha = -1.0;
+  s.beta = 1.0;
+  s.Cin = V;
+  s.ldcin = ld;
+  s.tri = true;
+  s.mirror = true;
+  GSMVI_TRY(launch_dgemm(st, D, D, K, W, ldk, false, W, ldk, false, Sb, ld, s));   // S = V - W W^T
+  bam_mean_kernel<<<(D + 7) / 8, 256, 0, st>>>(Sb, ld, 1.0, gbar, xbar, mu0, reg, mu_out, D);
+  bam_finish_cov_kernel<<<grid2(D, D), 256, 0, st>>>(Sb, ld, S_out, ldso, D, 1.0, jitter);
+  GSMVI_CUDA(last());
+  return GSMVI_OK;
+}
+
+}  // namespace gsmvi

@@ -1,0 +1,19 @@
+// FP64 GEMM used by the BaM solve (dgemm.cu).
+#pragma once
+#include "tc_gemm.cuh"  // KR_* flags, status codes
+
+namespace gsmvi {
+
+struct DgemmOpts {
+  double alpha = 1.0, beta = 0.0, diag_add = 0.0;
+  const double* Cin = nullptr;
+  long long ldcin = 0;
+  bool tri = false, mirror = false;
+  int krange = KR_FULL;
+};
+
+// C[M,N] = alpha * op(A) op(B)^T + beta*Cin + diag_add*I.  a_mn/b_mn: operand stored [K, rows].
+int launch_dgemm(cudaStream_t stream, int M, int N, int K, const double* A, long long lda, bool a_mn, const double* B,
+                 long long ldb, bool b_mn, double* C, long long ldc, const DgemmOpts& o);
+
+}  // namespace gsmvi

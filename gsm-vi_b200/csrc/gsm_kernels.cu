@@ -6,8 +6,11 @@
 //     alpha = 1/(1+rho),  beta = -alpha (1 + (vSv - mu_v)/(1 + rho + mu_v))            (gsm.py:18-21, g^T eps0 = vSv - mu_v)
 //     u = alpha w + beta d  (= mu_update),  e = d + u  (= mu - x)                     (gsm.py:21-22)
 //     mu = mu0 + mean_b u,   Sigma = Sigma0 + (D^T D - E^T E)/B                       (gsm.py:25-27, 53-56)
-// Three launches: W = G Sigma0 (tensor-core GEMM), the row pass below (HBM-bound, 20 B D bytes), and the signed
-// outer-product GEMM over T = [D; E] with the "+ Sigma0" and 1/B fused in its epilogue.
+// The difference of the two Gram matrices cancels to ~1% of either near convergence, so it is formed as
+//     D^T D - E^T E = -(E^T U + U^T D)            (E = D + U; exact identity, every term already small)
+// which one GEMM computes from T = [E; U; D]: A = T[0:2B] and B = T[B:3B] (both MN-major), K = 2B.
+// Three launches: W = G Sigma0 (tensor-core GEMM), the row pass below (HBM-bound, 24 B D bytes), and that GEMM
+// with the "+ Sigma0" and -1/B fused in its epilogue (lower tiles only, mirrored stores).
 #include "gsm_kernels.cuh"
 
 #include <math.h>
@@ -24,7 +27,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // One CTA handles RP_ROWS consecutive samples.  Pass 1 (a warp per row): the two dot products and the per-sample
-// scalars.  Pass 2 (a thread per 4 columns): rows d and e of T = [D; E] and the column sums of u.
+// scalars.  Pass 2 (a thread per 4 columns): rows e, u, d of T = [E; U; D] and the column sums of u.
 __global__ void __launch_bounds__(RP_THREADS) gsm_rowpass_kernel(const float* __restrict__ X, long long ldx,
                                                                  const float* __restrict__ G, long long ldg,
                                                                  const float* __restrict__ W, long long ldw,
@@ -84,8 +87,9 @@ __global__ void __launch_bounds__(RP_THREADS) gsm_rowpass_kernel(const float* __
         u.x = al * wv.x + be * d.x; u.y = al * wv.y + be * d.y; u.z = al * wv.z + be * d.z; u.w = al * wv.w + be * d.w;
         e.x = d.x + u.x; e.y = d.y + u.y; e.z = d.z + u.z; e.w = d.w + u.w;
         acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
-        *reinterpret_cast<float4*>(T + b * ldt + j) = d;
-        *reinterpret_cast<float4*>(T + (b + B) * ldt + j) = e;
+        *reinterpret_cast<float4*>(T + b * ldt + j) = e;
+        *reinterpret_cast<float4*>(T + (b + B) * ldt + j) = u;
+        *reinterpret_cast<float4*>(T + (b + 2LL * B) * ldt + j) = d;
       }
       atomicAdd(usum + j + 0, acc.x);
       atomicAdd(usum + j + 1, acc.y);
@@ -101,8 +105,9 @@ __global__ void __launch_bounds__(RP_THREADS) gsm_rowpass_kernel(const float* __
         const float d = m - X[b * ldx + j];
         const float u = s_alpha[r] * W[b * ldw + j] + s_beta[r] * d;
         acc += u;
-        T[b * ldt + j] = d;
-        T[(b + B) * ldt + j] = d + u;
+        T[b * ldt + j] = d + u;
+        T[(b + B) * ldt + j] = u;
+        T[(b + 2LL * B) * ldt + j] = d;
       }
       atomicAdd(usum + j, acc);
     }
@@ -203,8 +208,8 @@ int gauss_score(cudaStream_t stream, const float* X, long long ldx, const float*
 
 size_t gsm_update_workspace_bytes(int B, int D) {
   const long long ldw = round_up(D, 32);
-  // W [B x ldw] + T [2B x ldw] + usum [ldw]
-  return static_cast<size_t>((3LL * B + 1) * ldw) * sizeof(float);
+  // W [B x ldw] + T = [E; U; D] [3B x ldw] + usum [ldw]
+  return static_cast<size_t>((4LL * B + 1) * ldw) * sizeof(float);
 }
 
 int gsm_update(cudaStream_t stream, const float* X, long long ldx, const float* G, long long ldg, const float* mu,
@@ -215,7 +220,7 @@ int gsm_update(cudaStream_t stream, const float* X, long long ldx, const float* 
   const long long ldw = round_up(D, 32);
   float* W = workspace;
   float* T = W + static_cast<long long>(B) * ldw;
-  float* usum = T + 2LL * B * ldw;
+  float* usum = T + 3LL * B * ldw;
   cudaError_t e = cudaMemsetAsync(usum, 0, ldw * sizeof(float), stream);
   if (e != cudaSuccess) return static_cast<int>(e);
   // (i) W = G Sigma0   (Sigma0 symmetric)
@@ -230,40 +235,22 @@ int gsm_update(cudaStream_t stream, const float* X, long long ldx, const float* 
   gsm_rowpass_kernel<<<(B + RP_ROWS - 1) / RP_ROWS, RP_THREADS, 0, stream>>>(X, ldx, G, ldg, W, ldw, mu, T, ldw, usum, B, D);
   e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
-  // (iii) Sigma_out = [Sigma0 +] (D^T D - E^T E) / B_total : T is [2B, D] row-major = MN-major for both operands
+  // (iii) Sigma_out = [Sigma0] - (E^T U + U^T D) / B_total : rows of T are K, so both operands are MN-major views
   {
     GemmOpts o;
     o.npass = npass;
     o.a_mn = o.b_mn = true;
-    o.alpha = 1.0f / static_cast<float>(B_total);
+    o.alpha = -1.0f / static_cast<float>(B_total);
     o.tri = true;
     o.mirror = true;
-    o.neg_from = B;
     if (mode == 0) {
       o.beta = 1.0f;
       o.Cin = Sigma;
       o.ldcin = lds;
     }
-    MatView vt{T, 2LL * B, D, ldw};
-    // neg_from must be a multiple of BK for the per-k-block sign switch
-    if (B % BK != 0) {
-      // ragged batch: two launches (D^T D, then -= E^T E) instead of the signed single pass
-      GemmOpts o1 = o;
-      o1.neg_from = 0x7fffffff;
-      MatView vd{T, B, D, ldw}, ve{T + static_cast<long long>(B) * ldw, B, D, ldw};
-      int rc = launch_gemm_tf32(stream, D, D, B, vd, vd, Sigma_out, ldso, o1);
-      if (rc != GSMVI_OK) return rc;
-      GemmOpts o2 = o;
-      o2.neg_from = 0;
-      o2.beta = 1.0f;
-      o2.Cin = Sigma_out;
-      o2.ldcin = ldso;
-      rc = launch_gemm_tf32(stream, D, D, B, ve, ve, Sigma_out, ldso, o2);
-      if (rc != GSMVI_OK) return rc;
-    } else {
-      int rc = launch_gemm_tf32(stream, D, D, 2 * B, vt, vt, Sigma_out, ldso, o);
-      if (rc != GSMVI_OK) return rc;
-    }
+    MatView va{T, 2LL * B, D, ldw}, vb{T + static_cast<long long>(B) * ldw, 2LL * B, D, ldw};
+    int rc = launch_gemm_tf32(stream, D, D, 2 * B, va, vb, Sigma_out, ldso, o);
+    if (rc != GSMVI_OK) return rc;
   }
   // mu_out = [mu0 +] usum / B_total
   vec_axpy_kernel<<<(D + 255) / 256, 256, 0, stream>>>(mode == 0 ? mu : nullptr, usum, 1.0f / static_cast<float>(B_total),

@@ -87,7 +87,7 @@ class GSMEngine:
         """Kernels of libgsmvi_b200.so launched by one step (bench.py reports it as gpu_launches)."""
         panels = (self.D + 127) // 128
         potrf = 1 + panels + 2 * (panels - 1)
-        upd = 4 if self.B % 32 == 0 else 5
+        upd = 4
         return (0 if self.z_tape is not None else 1) + 1 + (1 if self.target is not None else 0) + upd + potrf + \
             (2 if self.world > 1 else 0)
 

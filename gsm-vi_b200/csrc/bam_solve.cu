@@ -7,10 +7,13 @@
 //   N = M^{1/2} by a GEMM-bound coupled Newton-Schulz iteration, I + N = R R^T, T = L R^{-T}, S = 2 T T^T - symmetric
 //   PSD by construction, algebraically identical.  Low-rank variant (bam.py:72-114) with the exact factor
 //   Q = [sqrt(reg/B) (G-gbar)^T, sqrt(reg/(1+reg)) gbar] of U instead of a truncated SVD (Q Q^T = U, S is invariant).
-// Statistics (B-proportional) run in 3xTF32 on the tensor cores; everything D x D / K x K here is fp64 (dgemm.cu).
+// Samples and scores come from the fp32 tensor-core path; the statistics and everything D x D / K x K here are fp64
+// (dgemm.cu): V = S0 + reg*C amplifies C's rounding by reg, and the solve mixes scales of 1 and ~1e9.
 #include "bam_solve.cuh"
 
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "dgemm.cuh"
 
@@ -88,19 +91,18 @@ __global__ void tril64_kernel(double* __restrict__ A, long long lda, int n) {
   if (j < n && j > i) A[i * lda + j] = 0.0;
 }
 
-// U64 = reg*Gam + w gbar gbar^T ; V64 = S0 + reg*C + w dm dm^T   (w = reg/(1+reg), dm = mu0 - xbar)   bam.py:59-60
-__global__ void bam_uv_kernel(const float* __restrict__ Gam, long long ldg, const float* __restrict__ C, long long ldc,
-                              const float* __restrict__ S0, long long lds, const float* __restrict__ gbar,
-                              const float* __restrict__ xbar, const float* __restrict__ mu0, double reg,
-                              double* __restrict__ U, double* __restrict__ V, long long ldu, int D) {
+// V64 = S0 + reg*C + w dm dm^T   (w = reg/(1+reg), dm = mu0 - xbar)   bam.py:60.   U (bam.py:59) is never formed: it
+// only enters through its exact factor Q (bam_build_q_kernel), which keeps U's rank / PSD structure out of reach of
+// rounding (rounding Gamma's entries independently perturbs the unit eigenvalues of I + 4 L^T U L by ~4 reg |L|^2 eps).
+__global__ void bam_v_kernel(const double* __restrict__ C, long long ldc, const float* __restrict__ S0, long long lds,
+                             const double* __restrict__ xbar, const float* __restrict__ mu0, double reg,
+                             double* __restrict__ V, long long ldv, int D) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const long long i = blockIdx.y;
   if (j >= D) return;
   const double w = reg / (1.0 + reg);
-  const double gi = gbar[i], gj = gbar[j];
   const double di = static_cast<double>(mu0[i]) - xbar[i], dj = static_cast<double>(mu0[j]) - xbar[j];
-  U[i * ldu + j] = reg * static_cast<double>(Gam[i * ldg + j]) + w * gi * gj;
-  V[i * ldu + j] = static_cast<double>(S0[i * lds + j]) + reg * static_cast<double>(C[i * ldc + j]) + w * di * dj;
+  V[i * ldv + j] = static_cast<double>(S0[i * lds + j]) + reg * C[i * ldc + j] + w * di * dj;
 }
 
 // A = scale * A (+ diag_add on the diagonal)
@@ -157,30 +159,30 @@ __global__ void bam_finish_cov_kernel(const double* __restrict__ S64, long long 
 }
 
 // mu_out = mu0/(1+reg) + reg/(1+reg) (S gbar + xbar)   bam.py:67 ; one warp per row, fp64 S
-__global__ void bam_mean_kernel(const double* __restrict__ S64, long long lds, double scale, const float* __restrict__ gbar,
-                                const float* __restrict__ xbar, const float* __restrict__ mu0, double reg,
+__global__ void bam_mean_kernel(const double* __restrict__ S64, long long lds, double scale, const double* __restrict__ gbar,
+                                const double* __restrict__ xbar, const float* __restrict__ mu0, double reg,
                                 float* __restrict__ mu_out, int D) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= D) return;
   double acc = 0.0;
-  for (int j = lane; j < D; j += 32) acc += S64[static_cast<long long>(row) * lds + j] * static_cast<double>(gbar[j]);
+  for (int j = lane; j < D; j += 32) acc += S64[static_cast<long long>(row) * lds + j] * gbar[j];
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0)
     mu_out[row] = static_cast<float>(static_cast<double>(mu0[row]) / (1.0 + reg) +
-                                     reg / (1.0 + reg) * (scale * acc + static_cast<double>(xbar[row])));
+                                     reg / (1.0 + reg) * (scale * acc + xbar[row]));
 }
 
-// column sums of X and G: out_x[j] += sum_b X[b][j] (over this CTA's rows)
+// column sums of X and G in fp64: sx[j] += sum_b X[b][j] (over this CTA's rows)
 constexpr int CS_ROWS = 32;
 __global__ void colsum2_kernel(const float* __restrict__ X, long long ldx, const float* __restrict__ G, long long ldg,
-                               int B, int D, float* __restrict__ sx, float* __restrict__ sg) {
+                               int B, int D, double* __restrict__ sx, double* __restrict__ sg) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int r0 = blockIdx.y * CS_ROWS;
   if (j >= D) return;
-  float ax = 0.f, ag = 0.f;
+  double ax = 0.0, ag = 0.0;
   const int r1 = min(r0 + CS_ROWS, B);
-  for (int b = r0; b < r1; ++b) {
+  for (long long b = r0; b < r1; ++b) {
     ax += X[b * ldx + j];
     ag += G[b * ldg + j];
   }
@@ -188,18 +190,18 @@ __global__ void colsum2_kernel(const float* __restrict__ X, long long ldx, const
   atomicAdd(sg + j, ag);
 }
 
-// xbar = sx / Btot, gbar = sg / Btot (in place), then T = [X - xbar ; G - gbar]  ([2B, D] row-major)
+// T = [X - xbar ; G - gbar]  ([2B, D] row-major, fp64)
 __global__ void center2_kernel(const float* __restrict__ X, long long ldx, const float* __restrict__ G, long long ldg,
-                               int B, int D, const float* __restrict__ xbar, const float* __restrict__ gbar,
-                               float* __restrict__ T, long long ldt) {
+                               int B, int D, const double* __restrict__ xbar, const double* __restrict__ gbar,
+                               double* __restrict__ T, long long ldt) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const long long b = blockIdx.y;
   if (j >= D) return;
-  T[b * ldt + j] = X[b * ldx + j] - xbar[j];
-  T[(b + B) * ldt + j] = G[b * ldg + j] - gbar[j];
+  T[b * ldt + j] = static_cast<double>(X[b * ldx + j]) - xbar[j];
+  T[(b + B) * ldt + j] = static_cast<double>(G[b * ldg + j]) - gbar[j];
 }
 
-__global__ void scale_vec2_kernel(float* __restrict__ a, float* __restrict__ b, float s, int n) {
+__global__ void scale_vec2_kernel(double* __restrict__ a, double* __restrict__ b, double s, int n) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) {
     a[j] *= s;
@@ -208,13 +210,12 @@ __global__ void scale_vec2_kernel(float* __restrict__ a, float* __restrict__ b, 
 }
 
 // Q64[i][k] = sqrt(reg/Btot) * Gc[k][i]  (k < B) ; Q64[i][B] = sqrt(reg/(1+reg)) * gbar[i]   -> Q stored [D, K] row-major
-__global__ void bam_build_q_kernel(const float* __restrict__ Gc, long long ldgc, const float* __restrict__ gbar, int B,
+__global__ void bam_build_q_kernel(const double* __restrict__ Gc, long long ldgc, const double* __restrict__ gbar, int B,
                                    int D, double reg, int Btot, double* __restrict__ Q, long long ldq) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const long long i = blockIdx.y;
   if (k > B) return;
-  Q[i * ldq + k] = (k < B) ? sqrt(reg / Btot) * static_cast<double>(Gc[static_cast<long long>(k) * ldgc + i])
-                           : sqrt(reg / (1.0 + reg)) * static_cast<double>(gbar[i]);
+  Q[i * ldq + k] = (k < B) ? sqrt(reg / Btot) * Gc[static_cast<long long>(k) * ldgc + i] : sqrt(reg / (1.0 + reg)) * gbar[i];
 }
 
 // ------------------------------------------------------------------------------------------------ fp64 building blocks
@@ -290,11 +291,36 @@ static int trsm64_right_lt(cudaStream_t st, const double* Bm, long long ldb, con
   return GSMVI_OK;
 }
 
+// Debug trace (GSMVI_DEBUG=1): synchronise and print ||A||_F, ||A||_inf and the PD flag after a stage.
+static bool dbg_on() {
+  static int on = -1;
+  if (on < 0) on = getenv("GSMVI_DEBUG") ? 1 : 0;
+  return on == 1;
+}
+static void dbg_stage(cudaStream_t st, const char* name, const double* A, long long ld, int n, double* scal, const int* flag) {
+  if (!dbg_on()) return;
+  double h[2];
+  int f = -1;
+  cudaMemsetAsync(scal, 0, 2 * sizeof(double), st);
+  frob_inf64_kernel<<<n, 256, 0, st>>>(A, ld, n, 0.0, scal);
+  cudaMemcpyAsync(h, scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(&f, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  fprintf(stderr, "[gsmvi debug] %-22s n=%d frob=%.6e inf=%.6e flag=%d cuda=%d\n", name, n, sqrt(h[0]), h[1], f, (int)e);
+}
+
 // Coupled Newton-Schulz square root of the SPD matrix in Y (n x n, overwritten):  on return Y ~= M^{1/2}.
-// Y0 = M/c, Z0 = I;  P = (3I - Z Y)/2;  Y <- Y P;  Z <- P Z   (SURVEY.md section 8a row B2).  c = ||M||_inf >= lambda_max.
-// Needs 4 scratch n x n buffers.  Synchronises the stream once per iteration to read the residual ||I - ZY||_F.
+//   Y0 = M/c, Z0 = I;  T = Z Y;  P = a I + b T;  Y <- Y P;  Z <- P Z        
+// c = ||M||_inf >= lambda_max.  Plain Newton-Schulz is (a, b) = (3/2, -1/2); while the spectrum of T is still wide
+// the scaled coefficients of Chen & Chow are used: with lo a lower bound on sqrt(lambda_min(T)),
+// alpha = sqrt(3 / (1 + lo + lo^2)), (a, b) = (3 alpha / 2, -alpha^3 / 2), lo <- a lo + b lo^3, which roughly halves the
+// iteration count (19 instead of 38 at kappa(M) = 3.5e11).  lam_min is a lower bound on lambda_min(M).
+// All three products are taken exactly as written (no symmetry shortcut such as Z Y^T): the coupled iteration is
+// stable under rounding only while Y and Z keep their exact coupling - symmetrising either iterate makes it diverge
+// at kappa ~ 1e11 (measured).  Needs 4 scratch n x n buffers.  Synchronises the stream once per iteration
+// to read the residual ||I - Z Y||_F.
 static int ns_sqrt64(cudaStream_t st, double* Y, long long ld, int n, double* Z, double* P, double* Y2, double* Z2,
-                     double* scal_dev, int max_iter, double tol, int* iters_out) {
+                     double* scal_dev, int max_iter, double tol, double lam_min, int* iters_out) {
   double h[2];
   GSMVI_CUDA(cudaMemsetAsync(scal_dev, 0, 2 * sizeof(double), st));
   frob_inf64_kernel<<<n, 256, 0, st>>>(Y, ld, n, 0.0, scal_dev);
@@ -307,15 +333,24 @@ static int ns_sqrt64(cudaStream_t st, double* Y, long long ld, int n, double* Z,
   }
   scale_diag64_kernel<<<grid2(n, n), 256, 0, st>>>(Y, ld, n, 1.0 / c, 0.0);
   set_identity64_kernel<<<grid2(n, n), 256, 0, st>>>(Z, ld, n);
+  double lo = sqrt(fmin(fmax(lam_min / c, 1e-300), 1.0));
   int it = 0;
   bool last_round = false;
+  double prev_res = 1e300;
   for (; it < max_iter; ++it) {
-    DgemmOpts p;  // P = 1.5 I - 0.5 Z Y      (Y symmetric: Y[k][j] read as Y[j][k])
-    p.alpha = -0.5;
-    p.diag_add = 1.5;
-    GSMVI_TRY(launch_dgemm(st, n, n, n, Z, ld, false, Y, ld, false, P, ld, p));
+    double a = 1.5, b = -0.5;
+    if (lo < 0.9 && !last_round) {
+      const double al = sqrt(3.0 / (1.0 + lo + lo * lo));
+      a = 1.5 * al;
+      b = -0.5 * al * al * al;
+      lo = a * lo + b * lo * lo * lo;
+    }
+    DgemmOpts p;  // P = a I + b Z Y   (B operand MN-major: the product is exactly Z Y)
+    p.alpha = b;
+    p.diag_add = a;
+    GSMVI_TRY(launch_dgemm(st, n, n, n, Z, ld, false, Y, ld, true, P, ld, p));
     GSMVI_CUDA(cudaMemsetAsync(scal_dev, 0, 2 * sizeof(double), st));
-    frob_inf64_kernel<<<n, 256, 0, st>>>(P, ld, n, 1.0, scal_dev);  // ||P - I||_F = ||I - ZY||_F / 2
+    frob_inf64_kernel<<<n, 256, 0, st>>>(P, ld, n, a + b, scal_dev);  // ||P - (a+b) I||_F = |b| ||I - Z Y||_F
     DgemmOpts o;
     GSMVI_TRY(launch_dgemm(st, n, n, n, Y, ld, false, P, ld, true, Y2, ld, o));   // Y2 = Y P
     GSMVI_TRY(launch_dgemm(st, n, n, n, P, ld, false, Z, ld, true, Z2, ld, o));   // Z2 = P Z
@@ -324,10 +359,13 @@ static int ns_sqrt64(cudaStream_t st, double* Y, long long ld, int n, double* Z,
     if (last_round) { ++it; break; }
     GSMVI_CUDA(cudaMemcpyAsync(h, scal_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     GSMVI_CUDA(cudaStreamSynchronize(st));
-    const double res = 2.0 * sqrt(h[0]);
-    if (isnan(res)) { ++it; break; }
+    const double res = sqrt(h[0]) / fabs(b);
+    if (dbg_on()) fprintf(stderr, "[gsmvi debug]   NS it=%d a=%.4f b=%.4f res=%.6e\n", it, a, b, res);
+    if (isnan(res) || isinf(res)) { ++it; break; }
     if (res < tol) { ++it; break; }            // this update already used P with ||I - ZY|| < tol: converged
-    if (res < 1e-4) last_round = true;         // quadratic convergence: one more update reaches ~1e-9 or better
+    if (res < 1e-4 && a == 1.5) last_round = true;   // quadratic convergence: one more plain update reaches ~1e-9
+    if (res < 1e-2 && res > 0.5 * prev_res) last_round = true;  // stagnating at the rounding floor
+    prev_res = res;
   }
   *iters_out = it;
   // result lives in the current Y; if that is the caller's Y2 buffer, copy back (odd number of swaps)
@@ -343,91 +381,99 @@ static int ns_sqrt64(cudaStream_t st, double* Y, long long ld, int n, double* Z,
 static inline long long rup(long long v, long long m) { return (v + m - 1) / m * m; }
 
 size_t bam_stats_workspace_bytes(int B, int D) {
-  const long long ld = rup(D, 32);
-  // T = [Xc; Gc] [2B x ld] + C [D x ld] + Gam [D x ld] + xbar, gbar [2 ld]
-  return static_cast<size_t>((2LL * B + 2LL * D + 2) * ld) * sizeof(float);
+  const long long ld = rup(D, 8);
+  // fp64: T = [Xc; Gc] [2B x ld] + C [D x ld] + xbar, gbar [2 ld]
+  return static_cast<size_t>((2LL * B + D + 2) * ld) * sizeof(double);
 }
 
 size_t bam_solve_workspace_bytes(int B, int D, int lowrank) {
   const long long ld = rup(D, 8);
   const long long nblk = (D + NB64 - 1) / NB64;
-  if (!lowrank) {
-    // 6 D x D fp64 buffers + 2 sets of diagonal-block inverses + scalars
-    return static_cast<size_t>(6 * D * ld + 2 * nblk * NB64 * NB64 + 16) * sizeof(double);
-  }
   const long long K = B + 1, ldk = rup(K, 8), kblk = (K + NB64 - 1) / NB64;
-  // U-free: V [D x ld], Q [D x ldk], A = VQ [D x ldk], W = A F [D x ldk], S [D x ld], 6 K x K buffers, inverses, scalars
+  if (!lowrank) {
+    // 6 D x D fp64 buffers + Q, W [D x ldk] + 2 sets of diagonal-block inverses + scalars
+    return static_cast<size_t>(6 * D * ld + 2 * D * ldk + 2 * nblk * NB64 * NB64 + 16) * sizeof(double);
+  }
+  // V [D x ld], S [D x ld], Q, A = VQ, W = A F [D x ldk], 6 K x K buffers, inverses, scalars
   return static_cast<size_t>(2 * D * ld + 3 * D * ldk + 6 * K * ldk + kblk * NB64 * NB64 + 16) * sizeof(double);
 }
 
 int bam_stats(cudaStream_t st, const float* X, long long ldx, const float* G, long long ldg, int B, int D, int Btot,
-              float* ws, int npass, int stage) {
+              double* ws, int stage) {
+  // fp64 statistics from the fp32 samples / scores.  V = S0 + reg*C multiplies C's rounding by reg (~100 early in the
+  // paper's schedule), so C, the means and the centred rows are kept in fp64; X and G stay fp32.
   // stage 0: column sums into xbar/gbar (unnormalised; all-reduce them across shards before stage 1)
-  // stage 1: xbar,gbar /= Btot; T = [X - xbar; G - gbar]; C = Xc^T Xc / Btot; Gam = Gc^T Gc / Btot (partial over this shard)
-  const long long ld = rup(D, 32);
-  float* T = ws;
-  float* C = T + 2LL * B * ld;
-  float* Gam = C + static_cast<long long>(D) * ld;
-  float* xbar = Gam + static_cast<long long>(D) * ld;
-  float* gbar = xbar + ld;
+  // stage 1: xbar,gbar /= Btot; T = [X - xbar; G - gbar]; C = Xc^T Xc / Btot (partial over this shard)
+  const long long ld = rup(D, 8);
+  double* T = ws;
+  double* C = T + 2LL * B * ld;
+  double* xbar = C + static_cast<long long>(D) * ld;
+  double* gbar = xbar + ld;
   if (stage == 0) {
-    GSMVI_CUDA(cudaMemsetAsync(xbar, 0, 2 * ld * sizeof(float), st));
+    GSMVI_CUDA(cudaMemsetAsync(xbar, 0, 2 * ld * sizeof(double), st));
     colsum2_kernel<<<dim3((D + 255) / 256, (B + CS_ROWS - 1) / CS_ROWS), 256, 0, st>>>(X, ldx, G, ldg, B, D, xbar, gbar);
     GSMVI_CUDA(last());
     return GSMVI_OK;
   }
-  scale_vec2_kernel<<<(D + 255) / 256, 256, 0, st>>>(xbar, gbar, 1.0f / static_cast<float>(Btot), D);
+  scale_vec2_kernel<<<(D + 255) / 256, 256, 0, st>>>(xbar, gbar, 1.0 / static_cast<double>(Btot), D);
   center2_kernel<<<grid2(D, B), 256, 0, st>>>(X, ldx, G, ldg, B, D, xbar, gbar, T, ld);
-  GemmOpts o;
-  o.npass = npass;
-  o.a_mn = o.b_mn = true;
-  o.alpha = 1.0f / static_cast<float>(Btot);
+  DgemmOpts o;
+  o.alpha = 1.0 / static_cast<double>(Btot);
   o.tri = true;
   o.mirror = true;
-  MatView vx{T, B, D, ld}, vg{T + static_cast<long long>(B) * ld, B, D, ld};
-  GSMVI_TRY(launch_gemm_tf32(st, D, D, B, vx, vx, C, ld, o));
-  GSMVI_TRY(launch_gemm_tf32(st, D, D, B, vg, vg, Gam, ld, o));
+  GSMVI_TRY(launch_dgemm(st, D, D, B, T, ld, true, T, ld, true, C, ld, o));  // C = Xc^T Xc / Btot (rows of T are K)
   GSMVI_CUDA(last());
   return GSMVI_OK;
 }
 
-int bam_solve_full(cudaStream_t st, const float* stats_ws, int B, int D, const float* mu0, const float* S0, long long lds0,
-                   double reg, double jitter, float* mu_out, float* S_out, long long ldso, double* ws, int max_ns,
-                   int* ns_iters_host, int* flag) {
-  const long long ld32 = rup(D, 32), ld = rup(D, 8);
-  const float* C = stats_ws + 2LL * B * ld32;
-  const float* Gam = C + static_cast<long long>(D) * ld32;
-  const float* xbar = Gam + static_cast<long long>(D) * ld32;
-  const float* gbar = xbar + ld32;
-  double* b0 = ws;                  // U      -> Z2
+int bam_solve_full(cudaStream_t st, const double* stats_ws, int B, int D, int Btot, const float* mu0, const float* S0,
+                   long long lds0, double reg, double jitter, float* mu_out, float* S_out, long long ldso, double* ws,
+                   int max_ns, int* ns_iters_host, int* flag) {
+  const long long ld = rup(D, 8);
+  const int K = B + 1;
+  const long long ldk = rup(K, 8);
+  const double* Tc = stats_ws;  // [Xc; Gc]
+  const double* C = stats_ws + 2LL * B * ld;
+  const double* xbar = C + static_cast<long long>(D) * ld;
+  const double* gbar = xbar + ld;
+  double* b0 = ws;                  // Z2
   double* b1 = b0 + D * ld;         // V -> L (kept)
-  double* b2 = b1 + D * ld;         // U L    -> Z
-  double* b3 = b2 + D * ld;         // M      -> Y
+  double* b2 = b1 + D * ld;         // Z
+  double* b3 = b2 + D * ld;         // M      -> Y -> N -> R
   double* b4 = b3 + D * ld;         // P      -> T = L R^{-T}
-  double* b5 = b4 + D * ld;         // Y2     -> S
+  double* b5 = b4 + D * ld;         // Y2     -> T T^T
+  double* Q = b5 + D * ld;          // [D x ldk]
+  double* W = Q + D * ldk;          // [D x ldk]  L^T Q
   const long long nblk = (D + NB64 - 1) / NB64;
-  double* dinvL = b5 + D * ld;
+  double* dinvL = W + D * ldk;
   double* dinvR = dinvL + nblk * NB64 * NB64;
   double* scal = dinvR + nblk * NB64 * NB64;
   GSMVI_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
-  bam_uv_kernel<<<grid2(D, D), 256, 0, st>>>(Gam, ld32, C, ld32, S0, lds0, gbar, xbar, mu0, reg, b0, b1, ld, D);
+  bam_v_kernel<<<grid2(D, D), 256, 0, st>>>(C, ld, S0, lds0, xbar, mu0, reg, b1, ld, D);
+  dbg_stage(st, "V", b1, ld, D, scal, flag);
   GSMVI_TRY(potrf64_inplace(st, b1, ld, D, dinvL, flag));                          // V = L L^T
+  dbg_stage(st, "L=chol(V)", b1, ld, D, scal, flag);
+  bam_build_q_kernel<<<dim3((K + 255) / 256, D), 256, 0, st>>>(Tc + static_cast<long long>(B) * ld, ld, gbar, B, D, reg,
+                                                               Btot, Q, ldk);     // Q Q^T = U
   DgemmOpts o;
-  o.krange = KR_B_UPPER;  // B operand is L^T given as MN-major L: L[k][j] == 0 for k < j
-  GSMVI_TRY(launch_dgemm(st, D, D, D, b0, ld, false, b1, ld, true, b2, ld, o));    // b2 = U L
+  o.krange = KR_A_UPPER;  // A operand is L^T given as MN-major L: (L^T)[i][k] = L[k][i] == 0 for k < i
+  GSMVI_TRY(launch_dgemm(st, D, K, D, b1, ld, true, Q, ldk, true, W, ldk, o));     // W = L^T Q
   DgemmOpts m;
   m.alpha = 4.0;
   m.diag_add = 1.0;
   m.tri = true;
   m.mirror = true;
-  m.krange = KR_A_UPPER;  // A operand is L^T given as MN-major L: (L^T)[i][k] = L[k][i] == 0 for k < i
-  GSMVI_TRY(launch_dgemm(st, D, D, D, b1, ld, true, b2, ld, true, b3, ld, m));     // M = I + 4 L^T (U L)
+  GSMVI_TRY(launch_dgemm(st, D, D, K, W, ldk, false, W, ldk, false, b3, ld, m));   // M = I + 4 W W^T  (= I + 4 L^T U L)
+  dbg_stage(st, "M", b3, ld, D, scal, flag);
   int iters = 0;
-  GSMVI_TRY(ns_sqrt64(st, b3, ld, D, b2, b4, b5, b0, scal, max_ns, 1e-11, &iters));  // b3 = N = M^{1/2}
+  GSMVI_TRY(ns_sqrt64(st, b3, ld, D, b2, b4, b5, b0, scal, max_ns, 1e-11, 1.0, &iters));  // b3 = N = M^{1/2}
   if (ns_iters_host) *ns_iters_host = iters;
+  dbg_stage(st, "N=sqrt(M)", b3, ld, D, scal, flag);
   scale_diag64_kernel<<<grid2(D, D), 256, 0, st>>>(b3, ld, D, 1.0, 1.0);          // I + N
   GSMVI_TRY(potrf64_inplace(st, b3, ld, D, dinvR, flag));                          // I + N = R R^T
+  dbg_stage(st, "R=chol(I+N)", b3, ld, D, scal, flag);
   GSMVI_TRY(trsm64_right_lt(st, b1, ld, b3, ld, dinvR, b4, ld, D, D));             // T = L R^{-T}
+  dbg_stage(st, "T=L R^-T", b4, ld, D, scal, flag);
   DgemmOpts s;
   s.tri = true;
   s.mirror = true;
@@ -438,19 +484,18 @@ int bam_solve_full(cudaStream_t st, const float* stats_ws, int B, int D, const f
   return GSMVI_OK;
 }
 
-int bam_solve_lowrank(cudaStream_t st, const float* stats_ws, int B, int D, int Btot, const float* mu0, const float* S0,
+int bam_solve_lowrank(cudaStream_t st, const double* stats_ws, int B, int D, int Btot, const float* mu0, const float* S0,
                       long long lds0, double reg, double jitter, float* mu_out, float* S_out, long long ldso, double* ws,
                       int max_ns, int* ns_iters_host, int* flag) {
   // bam.py:102-112 with Q Q^T = U exactly:  A = V Q;  H = Q^T V Q + I/4;  BB = (I/2 + H^{1/2})^2;  S = V - A BB^{-1} A^T.
   // BB^{-1} = F^2 with F = (I/2 + H^{1/2})^{-1} = T1 T1^T, T1 = R2^{-T}, (I/2 + H^{1/2}) = R2 R2^T; S = V - (A F)(A F)^T.
-  const long long ld32 = rup(D, 32), ld = rup(D, 8);
+  const long long ld = rup(D, 8);
   const int K = B + 1;
   const long long ldk = rup(K, 8), kblk = (K + NB64 - 1) / NB64;
-  const float* Tc = stats_ws;  // [Xc; Gc]
-  const float* C = stats_ws + 2LL * B * ld32;
-  const float* Gam = C + static_cast<long long>(D) * ld32;
-  const float* xbar = Gam + static_cast<long long>(D) * ld32;
-  const float* gbar = xbar + ld32;
+  const double* Tc = stats_ws;  // [Xc; Gc]
+  const double* C = stats_ws + 2LL * B * ld;
+  const double* xbar = C + static_cast<long long>(D) * ld;
+  const double* gbar = xbar + ld;
   double* V = ws;
   double* Sb = V + D * ld;
   double* Q = Sb + D * ld;
@@ -465,9 +510,8 @@ int bam_solve_lowrank(cudaStream_t st, const float* stats_ws, int B, int D, int 
   double* dinv = k5 + K * ldk;
   double* scal = dinv + kblk * NB64 * NB64;
   GSMVI_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
-  // V (fp64) from the statistics; U is not formed (Sb is used as the dummy U output)
-  bam_uv_kernel<<<grid2(D, D), 256, 0, st>>>(Gam, ld32, C, ld32, S0, lds0, gbar, xbar, mu0, reg, Sb, V, ld, D);
-  bam_build_q_kernel<<<dim3((K + 255) / 256, D), 256, 0, st>>>(Tc + static_cast<long long>(B) * ld32, ld32, gbar, B, D, reg,
+  bam_v_kernel<<<grid2(D, D), 256, 0, st>>>(C, ld, S0, lds0, xbar, mu0, reg, V, ld, D);
+  bam_build_q_kernel<<<dim3((K + 255) / 256, D), 256, 0, st>>>(Tc + static_cast<long long>(B) * ld, ld, gbar, B, D, reg,
                                                                Btot, Q, ldk);
   DgemmOpts o;
   GSMVI_TRY(launch_dgemm(st, D, K, D, V, ld, false, Q, ldk, true, A, ldk, o));     // A = V Q   (V symmetric)
@@ -477,7 +521,7 @@ int bam_solve_lowrank(cudaStream_t st, const float* stats_ws, int B, int D, int 
   h.mirror = true;
   GSMVI_TRY(launch_dgemm(st, K, K, D, A, ldk, true, Q, ldk, true, k0, ldk, h));    // H = A^T Q + I/4
   int iters = 0;
-  GSMVI_TRY(ns_sqrt64(st, k0, ldk, K, k1, k2, k3, k4, scal, max_ns, 1e-11, &iters));
+  GSMVI_TRY(ns_sqrt64(st, k0, ldk, K, k1, k2, k3, k4, scal, max_ns, 1e-11, 0.25, &iters));
   if (ns_iters_host) *ns_iters_host = iters;
   scale_diag64_kernel<<<grid2(K, K), 256, 0, st>>>(k0, ldk, K, 1.0, 0.5);          // I/2 + H^{1/2}
   GSMVI_TRY(potrf64_inplace(st, k0, ldk, K, dinv, flag));                          // = R2 R2^T

@@ -8,15 +8,15 @@ size_t bam_stats_workspace_bytes(int B, int D);
 size_t bam_solve_workspace_bytes(int B, int D, int lowrank);
 
 // stage 0: unnormalised column sums of this shard's X, G into the workspace (xbar/gbar slots);
-// stage 1: normalise by Btot, centre, and form C = Xc^T Xc / Btot, Gam = Gc^T Gc / Btot (3xTF32 tensor-core GEMMs).
+// stage 1: normalise by Btot, centre, and form C = Xc^T Xc / Btot, all in fp64; Gamma is never formed.
 int bam_stats(cudaStream_t st, const float* X, long long ldx, const float* G, long long ldg, int B, int D, int Btot,
-              float* ws, int npass, int stage);
+              double* ws, int stage);
 
-int bam_solve_full(cudaStream_t st, const float* stats_ws, int B, int D, const float* mu0, const float* S0, long long lds0,
-                   double reg, double jitter, float* mu_out, float* S_out, long long ldso, double* ws, int max_ns,
+int bam_solve_full(cudaStream_t st, const double* stats_ws, int B, int D, int Btot, const float* mu0, const float* S0,
+                   long long lds0, double reg, double jitter, float* mu_out, float* S_out, long long ldso, double* ws, int max_ns,
                    int* ns_iters_host, int* flag);
 
-int bam_solve_lowrank(cudaStream_t st, const float* stats_ws, int B, int D, int Btot, const float* mu0, const float* S0,
+int bam_solve_lowrank(cudaStream_t st, const double* stats_ws, int B, int D, int Btot, const float* mu0, const float* S0,
                       long long lds0, double reg, double jitter, float* mu_out, float* S_out, long long ldso, double* ws,
                       int max_ns, int* ns_iters_host, int* flag);
 

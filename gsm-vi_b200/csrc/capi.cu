@@ -1,7 +1,10 @@
 // C-ABI of libgsmvi_b200.so (declared in include/gsmvi_b200.h). Plain pointers and sizes only; no torch types.
 #include "../../include/gsmvi_b200.h"
 
+#include "bam_solve.cuh"
+#include "dgemm.cuh"
 #include "gsm_kernels.cuh"
+#include "monitor.cuh"
 #include "potrf.cuh"
 #include "tc_gemm.cuh"
 
@@ -17,6 +20,9 @@ long long gsmvi_workspace_bytes(int kind, int B, int D) {
   switch (kind) {
     case GSMVI_WS_POTRF: return static_cast<long long>(potrf_workspace_bytes(D));
     case GSMVI_WS_GSM_UPDATE: return static_cast<long long>(gsm_update_workspace_bytes(B, D));
+    case GSMVI_WS_BAM_STATS: return static_cast<long long>(bam_stats_workspace_bytes(B, D));
+    case GSMVI_WS_BAM_SOLVE: return static_cast<long long>(bam_solve_workspace_bytes(B, D, 0));
+    case GSMVI_WS_BAM_SOLVE_LOWRANK: return static_cast<long long>(bam_solve_workspace_bytes(B, D, 1));
     default: return -1;
   }
 }
@@ -75,6 +81,53 @@ int gsmvi_gsm_apply_stats(const float* Sigma, long long lds, const float* dSigma
                           const float* dmu, float* Sigma_out, long long ldso, float* mu_out, int D, void* stream) {
   if (!Sigma || !dSigma || !mu || !dmu || !Sigma_out || !mu_out || D <= 0) return GSMVI_EINVAL;
   return gsm_apply_stats(S(stream), Sigma, lds, dSigma, ldd, mu, dmu, Sigma_out, ldso, mu_out, D);
+}
+
+int gsmvi_dgemm(const double* A, long long lda, int a_mn, const double* B, long long ldb, int b_mn, double* C,
+                long long ldc, int M, int N, int K, double alpha, double beta, const double* Cin, long long ldcin,
+                double diag_add, int tri, int mirror, int krange, void* stream) {
+  DgemmOpts o;
+  o.alpha = alpha;
+  o.beta = beta;
+  o.diag_add = diag_add;
+  o.Cin = Cin;
+  o.ldcin = ldcin;
+  o.tri = tri != 0;
+  o.mirror = mirror != 0;
+  o.krange = krange;
+  return launch_dgemm(S(stream), M, N, K, A, lda, a_mn != 0, B, ldb, b_mn != 0, C, ldc, o);
+}
+
+int gsmvi_bam_stats(const float* X, long long ldx, const float* G, long long ldg, int B, int D, int B_total,
+                    void* stats_workspace, int npass, int stage, void* stream) {
+  if (!X || !G || !stats_workspace || B <= 0 || D <= 0 || B_total < B || (stage != 0 && stage != 1)) return GSMVI_EINVAL;
+  (void)npass;
+  return bam_stats(S(stream), X, ldx, G, ldg, B, D, B_total, static_cast<double*>(stats_workspace), stage);
+}
+
+int gsmvi_bam_solve(const void* stats_workspace, int B, int D, int B_total, const float* mu0, const float* Sigma0, long long lds0,
+                    double reg, double jitter, float* mu_out, float* Sigma_out, long long ldso, void* solve_workspace,
+                    int max_ns_iters, int* ns_iters_host, int* bad_flag, void* stream) {
+  if (!stats_workspace || !mu0 || !Sigma0 || !mu_out || !Sigma_out || !solve_workspace || !bad_flag || B <= 0 || D <= 0)
+    return GSMVI_EINVAL;
+  return bam_solve_full(S(stream), static_cast<const double*>(stats_workspace), B, D, B_total, mu0, Sigma0, lds0, reg, jitter, mu_out,
+                        Sigma_out, ldso, static_cast<double*>(solve_workspace), max_ns_iters, ns_iters_host, bad_flag);
+}
+
+int gsmvi_bam_solve_lowrank(const void* stats_workspace, int B, int D, int B_total, const float* mu0, const float* Sigma0,
+                            long long lds0, double reg, double jitter, float* mu_out, float* Sigma_out, long long ldso,
+                            void* solve_workspace, int max_ns_iters, int* ns_iters_host, int* bad_flag, void* stream) {
+  if (!stats_workspace || !mu0 || !Sigma0 || !mu_out || !Sigma_out || !solve_workspace || !bad_flag || B <= 0 || D <= 0)
+    return GSMVI_EINVAL;
+  return bam_solve_lowrank(S(stream), static_cast<const double*>(stats_workspace), B, D, B_total, mu0, Sigma0, lds0, reg,
+                           jitter, mu_out, Sigma_out, ldso, static_cast<double*>(solve_workspace), max_ns_iters,
+                           ns_iters_host, bad_flag);
+}
+
+int gsmvi_gauss_logq_reduce(const float* Z_or_X, long long ld, int N, int D, const float* mu, const float* L,
+                            long long ldl, int from_z, double* out, void* stream) {
+  if (from_z) return gauss_logq_from_z(S(stream), Z_or_X, ld, N, D, L, ldl, out);
+  return gauss_logq_from_x(S(stream), Z_or_X, ld, N, D, mu, L, ldl, out);
 }
 
 }  // extern "C"

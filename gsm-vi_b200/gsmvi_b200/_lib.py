@@ -138,3 +138,78 @@ def gsm_apply_stats(Sigma, dSigma, mu, dmu, Sigma_out, mu_out, D):
     check(lib().gsmvi_gsm_apply_stats(ptr(Sigma), Sigma.stride(0), ptr(dSigma), dSigma.stride(0), ptr(mu), ptr(dmu),
                                       ptr(Sigma_out), Sigma_out.stride(0), ptr(mu_out), D, stream_ptr()),
           "gsmvi_gsm_apply_stats")
+
+
+# ------------------------------------------------------------------------------------------------ BaM path
+c_d = ctypes.c_double
+WS_BAM_STATS, WS_BAM_SOLVE, WS_BAM_SOLVE_LOWRANK = 3, 4, 5
+
+
+def _declare_bam(L):
+    L.gsmvi_dgemm.restype = c_i
+    L.gsmvi_dgemm.argtypes = [c_p, c_ll, c_i, c_p, c_ll, c_i, c_p, c_ll, c_i, c_i, c_i, c_d, c_d, c_p, c_ll, c_d, c_i,
+                              c_i, c_i, c_p]
+    L.gsmvi_bam_stats.restype = c_i
+    L.gsmvi_bam_stats.argtypes = [c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p, c_i, c_i, c_p]
+    L.gsmvi_bam_solve.restype = c_i
+    L.gsmvi_bam_solve.argtypes = [c_p, c_i, c_i, c_i, c_p, c_p, c_ll, c_d, c_d, c_p, c_p, c_ll, c_p, c_i,
+                                  ctypes.POINTER(c_i), c_p, c_p]
+    L.gsmvi_bam_solve_lowrank.restype = c_i
+    L.gsmvi_bam_solve_lowrank.argtypes = [c_p, c_i, c_i, c_i, c_p, c_p, c_ll, c_d, c_d, c_p, c_p, c_ll, c_p, c_i,
+                                          ctypes.POINTER(c_i), c_p, c_p]
+
+
+_declare_gsm_level = _declare
+
+
+def _declare(L):  # noqa: F811
+    _declare_gsm_level(L)
+    _declare_bam(L)
+
+
+def dgemm(A, B, C, M, N, K, a_mn=False, b_mn=False, alpha=1.0, beta=0.0, Cin=None, diag_add=0.0, tri=False,
+          mirror=False, krange=0):
+    check(lib().gsmvi_dgemm(ptr(A), A.stride(0), int(a_mn), ptr(B), B.stride(0), int(b_mn), ptr(C), C.stride(0), M, N, K,
+                            alpha, beta, ptr(Cin), Cin.stride(0) if Cin is not None else 0, diag_add, int(tri),
+                            int(mirror), krange, stream_ptr()), "gsmvi_dgemm")
+    return C
+
+
+def bam_stats(X, G, B, D, B_total, stats_ws, stage, npass=3):
+    check(lib().gsmvi_bam_stats(ptr(X), X.stride(0), ptr(G), G.stride(0), B, D, B_total, ptr(stats_ws), npass, stage,
+                                stream_ptr()), "gsmvi_bam_stats")
+
+
+def bam_solve(stats_ws, B, D, B_total, mu0, Sigma0, reg, jitter, mu_out, Sigma_out, solve_ws, bad_flag, lowrank=False,
+              max_ns=200):
+    """Returns the number of Newton-Schulz iterations run.  Synchronises the current stream."""
+    it = c_i(0)
+    if lowrank:
+        rc = lib().gsmvi_bam_solve_lowrank(ptr(stats_ws), B, D, B_total, ptr(mu0), ptr(Sigma0), Sigma0.stride(0),
+                                           float(reg), float(jitter), ptr(mu_out), ptr(Sigma_out), Sigma_out.stride(0),
+                                           ptr(solve_ws), max_ns, ctypes.byref(it), ptr(bad_flag), stream_ptr())
+    else:
+        rc = lib().gsmvi_bam_solve(ptr(stats_ws), B, D, B_total, ptr(mu0), ptr(Sigma0), Sigma0.stride(0), float(reg),
+                                   float(jitter), ptr(mu_out), ptr(Sigma_out), Sigma_out.stride(0), ptr(solve_ws),
+                                   max_ns, ctypes.byref(it), ptr(bad_flag), stream_ptr())
+    check(rc, "gsmvi_bam_solve_lowrank" if lowrank else "gsmvi_bam_solve")
+    return it.value
+
+
+# ------------------------------------------------------------------------------------------------ monitor
+def _declare_mon(L):
+    L.gsmvi_gauss_logq_reduce.restype = c_i
+    L.gsmvi_gauss_logq_reduce.argtypes = [c_p, c_ll, c_i, c_i, c_p, c_p, c_ll, c_i, c_p, c_p]
+
+
+_declare_bam_level = _declare
+
+
+def _declare(L):  # noqa: F811
+    _declare_bam_level(L)
+    _declare_mon(L)
+
+
+def gauss_logq_reduce(Z_or_X, N, D, mu, L_, out, from_z):
+    check(lib().gsmvi_gauss_logq_reduce(ptr(Z_or_X), Z_or_X.stride(0), N, D, ptr(mu), ptr(L_), L_.stride(0), int(from_z),
+                                        ptr(out), stream_ptr()), "gsmvi_gauss_logq_reduce")

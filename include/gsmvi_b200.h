@@ -27,6 +27,9 @@ extern "C" {
 /* workspace kinds for gsmvi_workspace_bytes */
 #define GSMVI_WS_POTRF 1
 #define GSMVI_WS_GSM_UPDATE 2
+#define GSMVI_WS_BAM_STATS 3
+#define GSMVI_WS_BAM_SOLVE 4
+#define GSMVI_WS_BAM_SOLVE_LOWRANK 5
 
 int gsmvi_abi_version(void);
 
@@ -73,6 +76,50 @@ int gsmvi_gsm_update(const float* X, long long ldx, const float* G, long long ld
 /* Sigma_out = Sigma + dSigma, mu_out = mu + dmu (after the all-reduce of mode-1 statistics). */
 int gsmvi_gsm_apply_stats(const float* Sigma, long long lds, const float* dSigma, long long ldd, const float* mu,
                           const float* dmu, float* Sigma_out, long long ldso, float* mu_out, int D, void* stream);
+
+/* fp64 contraction C = alpha * op(A) op(B)^T + beta * Cin + diag_add * I (the engine of the BaM solve; exported for
+ * tests and diagnostics). */
+int gsmvi_dgemm(const double* A, long long lda, int a_mn, const double* B, long long ldb, int b_mn, double* C,
+                long long ldc, int M, int N, int K, double alpha, double beta, const double* Cin, long long ldcin,
+                double diag_add, int tri, int mirror, int krange, void* stream);
+
+/* BaM batch statistics.  Replaces gsmvi/bam.py:49-57 (xbar, C, gbar; vmapped outer products there).  Inputs are the
+ * fp32 samples / scores; the statistics are fp64 (V = S0 + reg*C multiplies C's rounding by reg, ~100 early on).
+ * stats_workspace (gsmvi_workspace_bytes(GSMVI_WS_BAM_STATS, B, D)) layout, in DOUBLES with ld = roundup(D, 8):
+ *   [Xc; Gc] (2B x ld) | C (D x ld) | xbar (ld) | gbar (ld).
+ * stage 0: xbar, gbar <- column SUMS of this shard (all-reduce them across shards, then)
+ * stage 1: xbar, gbar /= B_total; Xc = X - xbar, Gc = G - gbar; C = Xc^T Xc / B_total (shard partial: all-reduce the C
+ *          region across shards).  Gamma (gsmvi/bam.py:57) is never formed: the solve uses U's exact factor built from
+ *          Gc, so that rounding cannot break U's rank / PSD structure.  npass is ignored (kept for ABI stability). */
+int gsmvi_bam_stats(const float* X, long long ldx, const float* G, long long ldg, int B, int D, int B_total,
+                    void* stats_workspace, int npass, int stage, void* stream);
+
+/* BaM covariance/mean update from the statistics.  Replaces bam_update's solve (gsmvi/bam.py:59-67, get_sqrt
+ * gsmvi/bam.py:19-28: host scipy.linalg.sqrtm) plus the jitter and symmetrisation of BaM.fit (gsmvi/bam.py:198-199):
+ *   V = L L^T, M = I + 4 L^T U L (formed as I + 4 W W^T, W = L^T Q, Q Q^T = U exactly), N = M^(1/2) (fp64 scaled
+ *   Newton-Schulz), S = 2 L (I+N)^-1 L^T, Sigma_out = S + jitter I,
+ *   mu_out = mu0/(1+reg) + reg/(1+reg) (S gbar + xbar).
+ * fp64 internally; SYNCHRONISES `stream` once per Newton-Schulz iteration (residual read).  *ns_iters_host <- iterations
+ * run (host int); *bad_flag (device int) <- 1 if V or I+N was not positive definite (outputs are then garbage).
+ * solve_workspace: gsmvi_workspace_bytes(GSMVI_WS_BAM_SOLVE, B, D) bytes, 16-byte aligned. */
+int gsmvi_bam_solve(const void* stats_workspace, int B, int D, int B_total, const float* mu0, const float* Sigma0,
+                    long long lds0, double reg, double jitter, float* mu_out, float* Sigma_out, long long ldso, void* solve_workspace,
+                    int max_ns_iters, int* ns_iters_host, int* bad_flag, void* stream);
+
+/* Low-rank BaM update (K = B + 1 < D).  Replaces bam_lowrank_update (gsmvi/bam.py:72-114) and compute_Q
+ * (gsmvi/bam.py:10-17: host ARPACK svds) with the exact factor Q = [sqrt(reg/B) Gc^T, sqrt(reg/(1+reg)) gbar] of U:
+ *   A = V Q, H = A^T Q + I/4, BB = (I/2 + H^(1/2))^2, S = V - A BB^-1 A^T.  Same conventions as gsmvi_bam_solve;
+ * workspace kind GSMVI_WS_BAM_SOLVE_LOWRANK. */
+int gsmvi_bam_solve_lowrank(const void* stats_workspace, int B, int D, int B_total, const float* mu0, const float* Sigma0,
+                            long long lds0, double reg, double jitter, float* mu_out, float* Sigma_out, long long ldso,
+                            void* solve_workspace, int max_ns_iters, int* ns_iters_host, int* bad_flag, void* stream);
+
+/* *out (device double) <- sum_b log N(x_b | mu, L L^T), b < N.  Replaces MultivariateNormal(mu, cov).log_prob inside
+ * reverse_kl / forward_kl of the monitor (gsmvi/monitors.py:10-22, 107-113).
+ * from_z = 1: rows of Z_or_X are the standard-normal draws z_b of samples x_b = mu + L z_b (reverse KL: only |z|^2 and
+ *             log det are needed; mu unused);  from_z = 0: rows are arbitrary points x_b (forward KL). */
+int gsmvi_gauss_logq_reduce(const float* Z_or_X, long long ld, int N, int D, const float* mu, const float* L,
+                            long long ldl, int from_z, double* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -210,12 +210,15 @@ __global__ void scale_vec2_kernel(double* __restrict__ a, double* __restrict__ b
 }
 
 // Q64[i][k] = sqrt(reg/Btot) * Gc[k][i]  (k < B) ; Q64[i][B] = sqrt(reg/(1+reg)) * gbar[i]   -> Q stored [D, K] row-major
+// With the batch sharded over `world` ranks every rank builds the columns of its own samples and the gbar column scaled
+// by 1/sqrt(world), so that the shard Gram matrices sum to U.
 __global__ void bam_build_q_kernel(const double* __restrict__ Gc, long long ldgc, const double* __restrict__ gbar, int B,
-                                   int D, double reg, int Btot, double* __restrict__ Q, long long ldq) {
+                                   int D, double reg, int Btot, int world, double* __restrict__ Q, long long ldq) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const long long i = blockIdx.y;
   if (k > B) return;
-  Q[i * ldq + k] = (k < B) ? sqrt(reg / Btot) * Gc[static_cast<long long>(k) * ldgc + i] : sqrt(reg / (1.0 + reg)) * gbar[i];
+  Q[i * ldq + k] = (k < B) ? sqrt(reg / Btot) * Gc[static_cast<long long>(k) * ldgc + i]
+                           : sqrt(reg / ((1.0 + reg) * world)) * gbar[i];
 }
 
 // ------------------------------------------------------------------------------------------------ fp64 building blocks
@@ -428,7 +431,9 @@ int bam_stats(cudaStream_t st, const float* X, long long ldx, const float* G, lo
 
 int bam_solve_full(cudaStream_t st, const double* stats_ws, int B, int D, int Btot, const float* mu0, const float* S0,
                    long long lds0, double reg, double jitter, float* mu_out, float* S_out, long long ldso, double* ws,
-                   int max_ns, int* ns_iters_host, int* flag) {
+                   int max_ns, int* ns_iters_host, int* flag, int world, int phase) {
+  // phase 0: everything.  Sharded batch (world > 1): phase 1 stops after this rank's partial
+  // M_r = I/world + 4 W_r W_r^T (D x ld doubles at ws + 3 D ld: sum it over ranks), phase 2 resumes at the square root.
   const long long ld = rup(D, 8);
   const int K = B + 1;
   const long long ldk = rup(K, 8);
@@ -448,23 +453,29 @@ int bam_solve_full(cudaStream_t st, const double* stats_ws, int B, int D, int Bt
   double* dinvL = W + D * ldk;
   double* dinvR = dinvL + nblk * NB64 * NB64;
   double* scal = dinvR + nblk * NB64 * NB64;
+  if (phase != 2) {
   GSMVI_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
   bam_v_kernel<<<grid2(D, D), 256, 0, st>>>(C, ld, S0, lds0, xbar, mu0, reg, b1, ld, D);
   dbg_stage(st, "V", b1, ld, D, scal, flag);
   GSMVI_TRY(potrf64_inplace(st, b1, ld, D, dinvL, flag));                          // V = L L^T
   dbg_stage(st, "L=chol(V)", b1, ld, D, scal, flag);
   bam_build_q_kernel<<<dim3((K + 255) / 256, D), 256, 0, st>>>(Tc + static_cast<long long>(B) * ld, ld, gbar, B, D, reg,
-                                                               Btot, Q, ldk);     // Q Q^T = U
+                                                               Btot, world, Q, ldk);  // sum over ranks of Q Q^T = U
   DgemmOpts o;
   o.krange = KR_A_UPPER;  // A operand is L^T given as MN-major L: (L^T)[i][k] = L[k][i] == 0 for k < i
   GSMVI_TRY(launch_dgemm(st, D, K, D, b1, ld, true, Q, ldk, true, W, ldk, o));     // W = L^T Q
   DgemmOpts m;
   m.alpha = 4.0;
-  m.diag_add = 1.0;
+  m.diag_add = 1.0 / world;
   m.tri = true;
   m.mirror = true;
   GSMVI_TRY(launch_dgemm(st, D, D, K, W, ldk, false, W, ldk, false, b3, ld, m));   // M = I + 4 W W^T  (= I + 4 L^T U L)
   dbg_stage(st, "M", b3, ld, D, scal, flag);
+  }
+  if (phase == 1) {
+    GSMVI_CUDA(last());
+    return GSMVI_OK;
+  }
   int iters = 0;
   GSMVI_TRY(ns_sqrt64(st, b3, ld, D, b2, b4, b5, b0, scal, max_ns, 1e-11, 1.0, &iters));  // b3 = N = M^{1/2}
   if (ns_iters_host) *ns_iters_host = iters;
@@ -512,7 +523,7 @@ int bam_solve_lowrank(cudaStream_t st, const double* stats_ws, int B, int D, int
   GSMVI_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
   bam_v_kernel<<<grid2(D, D), 256, 0, st>>>(C, ld, S0, lds0, xbar, mu0, reg, V, ld, D);
   bam_build_q_kernel<<<dim3((K + 255) / 256, D), 256, 0, st>>>(Tc + static_cast<long long>(B) * ld, ld, gbar, B, D, reg,
-                                                               Btot, Q, ldk);
+                                                               Btot, 1, Q, ldk);
   DgemmOpts o;
   GSMVI_TRY(launch_dgemm(st, D, K, D, V, ld, false, Q, ldk, true, A, ldk, o));     // A = V Q   (V symmetric)
   DgemmOpts h;

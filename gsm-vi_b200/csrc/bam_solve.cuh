@@ -14,7 +14,7 @@ int bam_stats(cudaStream_t st, const float* X, long long ldx, const float* G, lo
 
 int bam_solve_full(cudaStream_t st, const double* stats_ws, int B, int D, int Btot, const float* mu0, const float* S0,
                    long long lds0, double reg, double jitter, float* mu_out, float* S_out, long long ldso, double* ws, int max_ns,
-                   int* ns_iters_host, int* flag);
+                   int* ns_iters_host, int* flag, int world, int phase);
 
 int bam_solve_lowrank(cudaStream_t st, const double* stats_ws, int B, int D, int Btot, const float* mu0, const float* S0,
                       long long lds0, double reg, double jitter, float* mu_out, float* S_out, long long ldso, double* ws,

@@ -107,11 +107,13 @@ int gsmvi_bam_stats(const float* X, long long ldx, const float* G, long long ldg
 
 int gsmvi_bam_solve(const void* stats_workspace, int B, int D, int B_total, const float* mu0, const float* Sigma0, long long lds0,
                     double reg, double jitter, float* mu_out, float* Sigma_out, long long ldso, void* solve_workspace,
-                    int max_ns_iters, int* ns_iters_host, int* bad_flag, void* stream) {
-  if (!stats_workspace || !mu0 || !Sigma0 || !mu_out || !Sigma_out || !solve_workspace || !bad_flag || B <= 0 || D <= 0)
+                    int max_ns_iters, int* ns_iters_host, int* bad_flag, int world, int phase, void* stream) {
+  if (!stats_workspace || !mu0 || !Sigma0 || !mu_out || !Sigma_out || !solve_workspace || !bad_flag || B <= 0 || D <= 0 ||
+      world < 1 || phase < 0 || phase > 2)
     return GSMVI_EINVAL;
   return bam_solve_full(S(stream), static_cast<const double*>(stats_workspace), B, D, B_total, mu0, Sigma0, lds0, reg, jitter, mu_out,
-                        Sigma_out, ldso, static_cast<double*>(solve_workspace), max_ns_iters, ns_iters_host, bad_flag);
+                        Sigma_out, ldso, static_cast<double*>(solve_workspace), max_ns_iters, ns_iters_host, bad_flag, world,
+                        phase);
 }
 
 int gsmvi_bam_solve_lowrank(const void* stats_workspace, int B, int D, int B_total, const float* mu0, const float* Sigma0,

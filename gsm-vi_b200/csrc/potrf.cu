@@ -5,12 +5,15 @@
 // np.linalg.cholesky in _check_goodness (gsm.py:136-150, bam.py:219-233).  One factorisation serves both: the flag
 // accepts/rejects the update, and on accept L is the next iteration's sampling factor.
 //
-// Per 128-column panel:  (1) one CTA factors the 128x128 diagonal block in shared memory and also forms its
-// inverse; (2) TRSM as a GEMM  L21 = A21 * inv(L11)^T;  (3) SYRK trailing update  A22 -= L21 L21^T, lower tiles
-// only - both on the tcgen05 3xTF32 GEMM.
+// Per 128-column panel, two launches:  (1) a multi-CTA panel kernel - CTA 0 factors the 128x128 diagonal block in shared
+// memory / registers and publishes it through a release flag, the other CTAs prefetch their rows of the panel, acquire
+// the flag and solve L21 L11^T = A21 one row per thread in registers;  (2) the SYRK trailing update
+// A22 -= L21 L21^T on lower tiles, on the tcgen05 3xTF32 GEMM.
 #include "potrf.cuh"
 
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace gsmvi {
 
@@ -23,23 +26,17 @@ __global__ void tril_copy_kernel(const float* __restrict__ A, long long lda, flo
   if (j < n) L[static_cast<long long>(i) * ldl + j] = (j <= i) ? A[static_cast<long long>(i) * lda + j] : 0.0f;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Diagonal-block kernel: factor the n x n (n <= 128) block at `a` (lower triangle read, leading dimension lda) in
-// place and write inv(L11) (lower triangular, row-major, leading dimension NB, zero/identity padded) to `linv`.
-// A non-positive or non-finite pivot sets *flag (bit 0); the factorisation then continues with NaNs and the caller
-// discards the result.
-//
-// One CTA, 256 threads, everything in shared memory / registers.  The block is processed in four 32-column panels:
+// Shared-memory building blocks of the panel kernel: the 128x128 block is processed in four 32-column sub-panels:
 //   (1) warp 0 factors the 32x32 diagonal block, one row per lane in registers, pivots broadcast with shuffles;
 //   (2) a thread per row below solves its 32 panel entries against that block by forward substitution (registers);
 //   (3) all threads apply the rank-32 update to the trailing lower triangle in 4x4 register tiles.
-// The inverse is then formed by 32x32 blocks: diagonal blocks by per-column substitution in registers, off-diagonal
-// blocks X[I][J] = -X[I][I] sum_K L[I][K] X[K][J] in 4x4 register tiles, by block distance.
 constexpr int DS = NB + 4;  // shared-memory leading dimension: rows stay 16-byte aligned, quarter-warps hit distinct banks
 
+// acc[r][c] += sum_k Arows[r * lda_][k] * Brows[c * ldb_][k]   (both row-major over k; kbeg, kend multiples of 4).
+// Callers pick the row strides so that the lanes of a quarter-warp touch CONSECUTIVE rows: with a leading dimension of
+// 4 (mod 32) words, eight consecutive rows cover all 32 banks for a float4 access (conflict-free).
 __device__ __forceinline__ void tile4x4_mac(const float* __restrict__ Arows, int lda_, const float* __restrict__ Brows,
                                             int ldb_, int kbeg, int kend, float (&acc)[4][4]) {
-  // acc[r][c] += sum_k Arows[r][k] * Brows[c][k]   (both row-major over k; kbeg, kend multiples of 4)
   for (int k = kbeg; k < kend; k += 4) {
     float4 a[4], b[4];
 #pragma unroll
@@ -61,7 +58,8 @@ __device__ __forceinline__ void chol32_step(float (&row)[32], int lane, float* d
   if constexpr (J < 32) {
     const float d = __shfl_sync(0xffffffffu, row[J], J);
     if (!(d > 0.0f) || isinf(d)) isbad = 1;
-    const float r = 1.0f / sqrtf(d);
+    float r = rsqrtf(d);
+    r = r * (1.5f - 0.5f * d * r * r);          // one Newton step: full fp32 accuracy without the slow sqrt + divide
     row[J] = (lane == J) ? d * r : row[J] * r;  // l_jj = sqrt(d), l_ij = a_ij / l_jj
     if (lane == J) dinv_out[J] = r;
 #pragma unroll
@@ -73,22 +71,10 @@ __device__ __forceinline__ void chol32_step(float (&row)[32], int lane, float* d
   }
 }
 
-__global__ void __launch_bounds__(256, 1) potrf_diag_kernel(float* __restrict__ a, long long lda, int n,
-                                                            float* __restrict__ linv, int* __restrict__ flag) {
-  extern __shared__ __align__(16) float sm[];
-  float* s = sm;             // [NB][DS]  working block -> L11
-  float* x = sm + NB * DS;   // [NB][DS]  inverse, stored TRANSPOSED: x[c][r] = inv(L)[r][c]
-  __shared__ float dinv[NB];
-  __shared__ int bad;
+// Factor the n x n (n <= 128) block held in shared memory `s` (leading dimension DS, lower triangle valid, identity
+// padded) in place; dinv[j] <- 1 / L[j][j].  Returns (in every thread) whether a pivot was non-positive / non-finite.
+__device__ __forceinline__ bool factor_block_smem(float* s, float* dinv, int* bad_smem) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) bad = 0;
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int i = idx >> 7, j = idx & (NB - 1);
-    s[i * DS + j] = (i < n && j <= i) ? a[static_cast<long long>(i) * lda + j] : ((i == j) ? 1.0f : 0.0f);
-    x[i * DS + j] = 0.0f;
-  }
-  __syncthreads();
-
   for (int p = 0; p < NB / 32; ++p) {
     const int c0 = 32 * p;
     // ---- (1) 32x32 diagonal block, warp 0, row `lane` in registers
@@ -100,7 +86,7 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(float* __restrict__ 
       chol32_step<0>(row, lane, dinv + c0, isbad);
 #pragma unroll
       for (int k = 0; k < 32; ++k) s[(c0 + lane) * DS + c0 + k] = (k <= lane) ? row[k] : 0.0f;
-      if (isbad && lane == 0) bad = 1;
+      if (isbad && lane == 0) *bad_smem = 1;
     }
     __syncthreads();
     // ---- (2) rows below: x L11^T = a  by forward substitution, one thread per row
@@ -113,96 +99,209 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(float* __restrict__ 
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float acc = v[j];
+        float acc0 = v[j], acc1 = 0.0f;
         const float* lrow = s + (c0 + j) * DS + c0;  // broadcast reads
 #pragma unroll
-        for (int k = 0; k < j; ++k) acc -= v[k] * lrow[k];
-        v[j] = acc * dinv[c0 + j];
+        for (int k = 0; k + 1 < j; k += 2) {
+          acc0 -= v[k] * lrow[k];
+          acc1 -= v[k + 1] * lrow[k + 1];
+        }
+        if (j & 1) acc0 -= v[j - 1] * lrow[j - 1];
+        v[j] = (acc0 + acc1) * dinv[c0 + j];
       }
 #pragma unroll
       for (int k = 0; k < 32; k += 4)
         *reinterpret_cast<float4*>(s + tid * DS + c0 + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
     }
     __syncthreads();
-    // ---- (3) trailing update: S[i][k] -= sum_c P[i][c] P[k][c], lower 4x4 tiles of the (NB-c0-32)^2 block
-    const int m0 = c0 + 32, mt = (NB - m0) / 4;  // tiles per side
-    for (int t = tid; t < mt * (mt + 1) / 2; t += 256) {
-      int ti = static_cast<int>((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
-      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-      while (ti * (ti + 1) / 2 > t) --ti;
-      const int tj = t - ti * (ti + 1) / 2;
-      const int i0 = m0 + 4 * ti, k0 = m0 + 4 * tj;
+    // ---- (3) trailing update: S[i][k] -= sum_c P[i][c] P[k][c] on the lower triangle of the (NB-c0-32)^2 block.
+    // Interleaved 4x4 tiles: thread (ti, tj) owns rows m0 + ti + r*mt and columns m0 + tj + c*mt, so neighbouring
+    // lanes read neighbouring rows (bank-conflict-free float4 loads).  Elements above the diagonal are skipped.
+    const int m0 = c0 + 32, mt = (NB - m0) / 4;  // mt = 24, 16, 8, 0
+    for (int t = tid; t < mt * mt; t += 256) {
+      const int ti = t % mt, tj = t / mt;
       float acc[4][4] = {};
-      tile4x4_mac(s + i0 * DS, DS, s + k0 * DS, DS, c0, c0 + 32, acc);
+      tile4x4_mac(s + (m0 + ti) * DS, mt * DS, s + (m0 + tj) * DS, mt * DS, c0, c0 + 32, acc);
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (k0 + c <= i0 + r) s[(i0 + r) * DS + k0 + c] -= acc[r][c];
+        for (int c = 0; c < 4; ++c) {
+          const int i = m0 + ti + r * mt, k = m0 + tj + c * mt;
+          if (k <= i) s[i * DS + k] -= acc[r][c];
+        }
     }
     __syncthreads();
+  }
+  return *bad_smem != 0;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Panel kernel: one launch factors the 128-wide panel starting at column j0 of the n x n matrix L (in place).
+//   CTA 0            : Cholesky of the nb x nb diagonal block (shared memory / registers), written back with explicit
+//                      zeros above the diagonal, then publishes `epoch` through *ready (release).
+//   CTA t = 1, 2, ...: TRSM of rows r0 = j0 + nb + 128 (t-1) ...: prefetches its 128 x 128 tile of A21 into shared memory
+//                      while CTA 0 works, acquires the flag, loads L11, and solves X L11^T = A21 one row per thread in
+//                      registers (fp32 FMAs: no explicit inverse, no tensor-core rounding), 32 columns at a time.
+// All CTAs are co-resident (at most 1 + 31 CTAs of one per SM), so the spin-wait cannot deadlock.
+// A non-positive or non-finite pivot sets *flag (bit 0); the panel is then garbage and the caller discards L.
+__global__ void __launch_bounds__(256, 1) potrf_panel_kernel(float* __restrict__ Lm, long long ld, int n, int j0, int nb,
+                                                             int* __restrict__ flag, unsigned* __restrict__ ready,
+                                                             unsigned epoch) {
+  extern __shared__ __align__(16) float sm[];
+  float* s = sm;            // [NB][DS]  diagonal block (CTA 0) / L11 (TRSM CTAs)
+  float* at = sm + NB * DS; // [NB][DS]  TRSM CTAs: their rows of A21 -> L21
+  __shared__ float dinv[NB];
+  __shared__ int bad;
+  const int tid = threadIdx.x;
+  float* a11 = Lm + static_cast<long long>(j0) * ld + j0;
+  const bool vec_ok = (nb == NB) && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(a11) & 15) == 0);
+  if (tid == 0) bad = 0;
+
+  if (blockIdx.x == 0) {
+    // ---------------- diagonal block
+    if (vec_ok) {
+      float4 v[16];  // 4096 float4: 16 loads per thread issued back to back, then stored
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int q = tid + e * 256, i = q >> 5, j4 = (q & 31) * 4;
+        v[e] = (j4 <= i) ? *reinterpret_cast<const float4*>(a11 + static_cast<long long>(i) * ld + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int q = tid + e * 256, i = q >> 5, j4 = (q & 31) * 4;
+        float4 t = v[e];
+        if (j4 + 1 > i) t.y = 0.f;
+        if (j4 + 2 > i) t.z = 0.f;
+        if (j4 + 3 > i) t.w = 0.f;
+        *reinterpret_cast<float4*>(s + i * DS + j4) = t;
+      }
+    } else {
+      for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int i = idx >> 7, j = idx & (NB - 1);
+        s[i * DS + j] = (i < nb && j <= i) ? a11[static_cast<long long>(i) * ld + j] : ((i == j) ? 1.0f : 0.0f);
+      }
+    }
+    __syncthreads();
+    const bool isbad = factor_block_smem(s, dinv, &bad);
+    if (vec_ok) {
+#pragma unroll 4
+      for (int e = 0; e < 16; ++e) {
+        const int q = tid + e * 256, i = q >> 5, j4 = (q & 31) * 4;
+        *reinterpret_cast<float4*>(a11 + static_cast<long long>(i) * ld + j4) = *reinterpret_cast<const float4*>(s + i * DS + j4);
+      }
+    } else {
+      for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int i = idx >> 7, j = idx & (NB - 1);
+        if (i < nb && j < nb) a11[static_cast<long long>(i) * ld + j] = (j <= i) ? s[i * DS + j] : 0.0f;
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      if (isbad) atomicOr(flag, 1);
+      st_release_u32(ready, epoch);
+    }
+    return;
   }
 
-  // ---- inverse, diagonal 32x32 blocks: thread (g, c) solves L[g] y = e_c in registers; x holds inv(L)^T
-  if (tid < NB) {
-    const int g = tid >> 5, c = tid & 31, o = g * 32;
-    float y[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float acc = (i == c) ? 1.0f : 0.0f;
-      const float* lrow = s + (o + i) * DS + o;
-#pragma unroll
-      for (int k = 0; k < i; ++k) acc -= lrow[k] * y[k];  // y[k] == 0 for k < c
-      y[i] = acc * dinv[o + i];
+  // ---------------- TRSM rows (nb == NB whenever rows below exist)
+  const int r0 = j0 + nb + (blockIdx.x - 1) * NB;
+  const int rows = min(NB, n - r0);
+  float* a21 = Lm + static_cast<long long>(r0) * ld + j0;
+  for (int q = tid; q < NB * 32; q += 256) {  // prefetch this CTA's rows while CTA 0 factors
+    const int i = q >> 5, j4 = (q & 31) * 4;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < rows) {
+      if (vec_ok) t = *reinterpret_cast<const float4*>(a21 + static_cast<long long>(i) * ld + j4);
+      else { t.x = a21[static_cast<long long>(i) * ld + j4]; t.y = a21[static_cast<long long>(i) * ld + j4 + 1];
+             t.z = a21[static_cast<long long>(i) * ld + j4 + 2]; t.w = a21[static_cast<long long>(i) * ld + j4 + 3]; }
     }
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(x + (o + c) * DS + o + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+    *reinterpret_cast<float4*>(at + i * DS + j4) = t;
+  }
+  if (tid == 0) {
+    const long long t0 = clock64();
+    while (ld_acquire_u32(ready) != epoch) {
+      __nanosleep(64);
+      if (clock64() - t0 > 4000000000LL) { printf("gsmvi: potrf panel watchdog (j0=%d)\n", j0); __trap(); }
+    }
   }
   __syncthreads();
-  // ---- off-diagonal blocks by block distance d (I = J + d).  With XT = inv(L)^T stored row-major in x:
-  //   T[r][c]  = sum_k L[I*32+r][k] * XT[J*32+c][k],   k in [J*32, I*32)
-  //   X[I][J][r][c] = - sum_kk XT... : inv(L)[I*32+r][I*32+kk] = XT[I*32+kk][I*32+r]  (needs a column walk), so the
-  //   second product is taken from a transposed copy of the diagonal block inverse kept in `tmp`.
-  float* tmp = sm + 2 * NB * DS;   // [96][36]  T, row-major
-  float* dgi = tmp + 96 * 36;      // [NB][36]  inv(L[I][I]) row-major (not transposed), all four diagonal blocks
-  for (int idx = tid; idx < NB * 32; idx += 256) {
-    const int r = idx >> 5, c = idx & 31, o = (r >> 5) * 32;
-    dgi[r * 36 + c] = x[(o + c) * DS + r];  // inv(L)[r][o+c]
+  for (int q = tid; q < NB * 32; q += 256) {  // L11 (just published; lower triangle + explicit zeros)
+    const int i = q >> 5, j4 = (q & 31) * 4;
+    float4 t;
+    if (vec_ok) t = __ldcg(reinterpret_cast<const float4*>(a11 + static_cast<long long>(i) * ld + j4));
+    else { t.x = __ldcg(a11 + static_cast<long long>(i) * ld + j4); t.y = __ldcg(a11 + static_cast<long long>(i) * ld + j4 + 1);
+           t.z = __ldcg(a11 + static_cast<long long>(i) * ld + j4 + 2); t.w = __ldcg(a11 + static_cast<long long>(i) * ld + j4 + 3); }
+    *reinterpret_cast<float4*>(s + i * DS + j4) = t;
   }
   __syncthreads();
-  for (int d = 1; d < NB / 32; ++d) {
-    const int nblk = NB / 32 - d;
-    for (int t = tid; t < nblk * 64; t += 256) {  // 64 4x4 tiles per 32x32 block
-      const int b = t >> 6, tr = (t >> 3) & 7, tc = t & 7;
-      const int I = b + d, J = b;
-      float acc[4][4] = {};
-      tile4x4_mac(s + (I * 32 + 4 * tr) * DS, DS, x + (J * 32 + 4 * tc) * DS, DS, J * 32, I * 32, acc);
+  if (tid < NB) dinv[tid] = 1.0f / s[tid * DS + tid];
+  __syncthreads();
+  if (tid < rows) {
+    float* myrow = at + tid * DS;
+#pragma unroll 1
+    for (int J = 0; J < NB / 32; ++J) {
+      float v[32];
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+      for (int k = 0; k < 32; k += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(myrow + 32 * J + k);
+        v[k] = t.x; v[k + 1] = t.y; v[k + 2] = t.z; v[k + 3] = t.w;
+      }
+#pragma unroll 1
+      for (int I = 0; I < J; ++I) {  // v -= X_I L11[J][I]^T
+        float xp[32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmp[(b * 32 + 4 * tc + c) * 36 + 4 * tr + r] = acc[r][c];  // store T^T: tmp[c][r]
+        for (int k = 0; k < 32; k += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(myrow + 32 * I + k);
+          xp[k] = t.x; xp[k + 1] = t.y; xp[k + 2] = t.z; xp[k + 3] = t.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float* lr = s + (32 * J + j) * DS + 32 * I;  // broadcast reads
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            a0 += xp[k] * lr[k];
+            a1 += xp[k + 1] * lr[k + 1];
+          }
+          v[j] -= a0 + a1;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {  // in-block forward substitution
+        float acc0 = v[j], acc1 = 0.0f;
+        const float* lrow = s + (32 * J + j) * DS + 32 * J;
+#pragma unroll
+        for (int k = 0; k + 1 < j; k += 2) {
+          acc0 -= v[k] * lrow[k];
+          acc1 -= v[k + 1] * lrow[k + 1];
+        }
+        if (j & 1) acc0 -= v[j - 1] * lrow[j - 1];
+        v[j] = (acc0 + acc1) * dinv[32 * J + j];
+      }
+#pragma unroll
+      for (int k = 0; k < 32; k += 4)
+        *reinterpret_cast<float4*>(myrow + 32 * J + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
     }
-    __syncthreads();
-    for (int t = tid; t < nblk * 64; t += 256) {
-      const int b = t >> 6, tr = (t >> 3) & 7, tc = t & 7;
-      const int I = b + d, J = b;
-      // X[I][J][r][c] = - sum_kk inv(L[I][I])[r][kk] * T[kk][c] = - sum_kk dgi[I*32+r][kk] * tmp[c][kk]
-      float acc[4][4] = {};
-      tile4x4_mac(dgi + (I * 32 + 4 * tr) * 36, 36, tmp + (b * 32 + 4 * tc) * 36, 36, 0, 32, acc);
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) x[(J * 32 + 4 * tc + c) * DS + I * 32 + 4 * tr + r] = -acc[r][c];
+  }
+  __syncthreads();
+  for (int q = tid; q < NB * 32; q += 256) {
+    const int i = q >> 5, j4 = (q & 31) * 4;
+    if (i < rows) {
+      const float4 t = *reinterpret_cast<const float4*>(at + i * DS + j4);
+      if (vec_ok) *reinterpret_cast<float4*>(a21 + static_cast<long long>(i) * ld + j4) = t;
+      else { a21[static_cast<long long>(i) * ld + j4] = t.x; a21[static_cast<long long>(i) * ld + j4 + 1] = t.y;
+             a21[static_cast<long long>(i) * ld + j4 + 2] = t.z; a21[static_cast<long long>(i) * ld + j4 + 3] = t.w; }
     }
-    __syncthreads();
   }
-  // ---- write back L11 (explicit zeros above the diagonal) and inv(L11)
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int i = idx >> 7, j = idx & (NB - 1);
-    if (i < n && j < n) a[static_cast<long long>(i) * lda + j] = (j <= i) ? s[i * DS + j] : 0.0f;
-    linv[i * NB + j] = (i < n && j < n && j <= i) ? x[j * DS + i] : 0.0f;
-  }
-  if (tid == 0 && bad) atomicOr(flag, 1);
 }
 
 size_t potrf_workspace_bytes(int n) {
@@ -214,30 +313,28 @@ int potrf_lower(cudaStream_t stream, const float* A, long long lda, float* L, lo
                 float* workspace, int npass) {
   if (n <= 0 || !A || !L || !flag || !workspace) return GSMVI_EINVAL;
   static bool attr_set = false;
-  const int smem = (2 * NB * DS + 96 * 36 + NB * 36) * sizeof(float);
+  const int smem = 2 * NB * DS * sizeof(float);
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
+  unsigned* ready = reinterpret_cast<unsigned*>(workspace);
   cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), stream);
   if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaMemsetAsync(ready, 0, sizeof(unsigned), stream);
+  if (e != cudaSuccess) return static_cast<int>(e);
   tril_copy_kernel<<<dim3((n + 255) / 256, n), 256, 0, stream>>>(A, lda, L, ldl, n);
+  unsigned epoch = 0;
   for (int j0 = 0; j0 < n; j0 += NB) {
     const int nb = min(NB, n - j0);
     const int rest = n - j0 - nb;
-    float* l11 = L + static_cast<long long>(j0) * ldl + j0;
-    potrf_diag_kernel<<<1, 256, smem, stream>>>(l11, ldl, nb, workspace, flag);
+    // panel: diagonal block (CTA 0) + TRSM of the rows below (one CTA per 128 rows)
+    potrf_panel_kernel<<<1 + (rest + NB - 1) / NB, 256, smem, stream>>>(L, ldl, n, j0, nb, flag, ready, ++epoch);
     if (rest > 0) {
       float* a21 = L + static_cast<long long>(j0 + nb) * ldl + j0;
       float* a22 = L + static_cast<long long>(j0 + nb) * ldl + j0 + nb;
-      // TRSM: L21 = A21 * inv(L11)^T, in place (each CTA reads only the rows it then overwrites)
-      GemmOpts t;
-      t.npass = npass;
-      MatView va{a21, rest, nb, ldl}, vb{workspace, nb, nb, NB};
-      int rc = launch_gemm_tf32(stream, rest, nb, nb, va, vb, a21, ldl, t);
-      if (rc != GSMVI_OK) return rc;
-      // SYRK: A22 -= L21 L21^T on the lower tiles
+      // SYRK: A22 -= L21 L21^T on the lower tiles (tcgen05 3xTF32 GEMM)
       GemmOpts s;
       s.npass = npass;
       s.alpha = -1.0f;
@@ -246,7 +343,7 @@ int potrf_lower(cudaStream_t stream, const float* A, long long lda, float* L, lo
       s.ldcin = ldl;
       s.tri = true;
       MatView vl{a21, rest, nb, ldl};
-      rc = launch_gemm_tf32(stream, rest, rest, nb, vl, vl, a22, ldl, s);
+      int rc = launch_gemm_tf32(stream, rest, rest, nb, vl, vl, a22, ldl, s);
       if (rc != GSMVI_OK) return rc;
     }
   }

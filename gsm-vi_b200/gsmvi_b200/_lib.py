@@ -153,7 +153,7 @@ def _declare_bam(L):
     L.gsmvi_bam_stats.argtypes = [c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p, c_i, c_i, c_p]
     L.gsmvi_bam_solve.restype = c_i
     L.gsmvi_bam_solve.argtypes = [c_p, c_i, c_i, c_i, c_p, c_p, c_ll, c_d, c_d, c_p, c_p, c_ll, c_p, c_i,
-                                  ctypes.POINTER(c_i), c_p, c_p]
+                                  ctypes.POINTER(c_i), c_p, c_i, c_i, c_p]
     L.gsmvi_bam_solve_lowrank.restype = c_i
     L.gsmvi_bam_solve_lowrank.argtypes = [c_p, c_i, c_i, c_i, c_p, c_p, c_ll, c_d, c_d, c_p, c_p, c_ll, c_p, c_i,
                                           ctypes.POINTER(c_i), c_p, c_p]
@@ -181,7 +181,7 @@ def bam_stats(X, G, B, D, B_total, stats_ws, stage, npass=3):
 
 
 def bam_solve(stats_ws, B, D, B_total, mu0, Sigma0, reg, jitter, mu_out, Sigma_out, solve_ws, bad_flag, lowrank=False,
-              max_ns=200):
+              max_ns=200, world=1, phase=0):
     """Returns the number of Newton-Schulz iterations run.  Synchronises the current stream."""
     it = c_i(0)
     if lowrank:
@@ -191,7 +191,7 @@ def bam_solve(stats_ws, B, D, B_total, mu0, Sigma0, reg, jitter, mu_out, Sigma_o
     else:
         rc = lib().gsmvi_bam_solve(ptr(stats_ws), B, D, B_total, ptr(mu0), ptr(Sigma0), Sigma0.stride(0), float(reg),
                                    float(jitter), ptr(mu_out), ptr(Sigma_out), Sigma_out.stride(0), ptr(solve_ws),
-                                   max_ns, ctypes.byref(it), ptr(bad_flag), stream_ptr())
+                                   max_ns, ctypes.byref(it), ptr(bad_flag), world, phase, stream_ptr())
     check(rc, "gsmvi_bam_solve_lowrank" if lowrank else "gsmvi_bam_solve")
     return it.value
 

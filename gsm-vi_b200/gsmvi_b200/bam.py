@@ -135,8 +135,15 @@ class BaMEngine:
         L.bam_stats(self.Xb, self.Gb, B, D, self.batch_size, self.ws_s, 1, npass)
         if self.world > 1:
             self.dist.all_reduce(self._stats_views()[0], group=self.group)
-        it = L.bam_solve(self.ws_s, B, D, self.batch_size, self.mu, self.Sb, reg, self.jitter, self.mun, self.Snb,
-                         self.ws_v, self.bad2, lowrank=self.use_lowrank, max_ns=self.max_ns)
+        args = (self.ws_s, B, D, self.batch_size, self.mu, self.Sb, reg, self.jitter, self.mun, self.Snb, self.ws_v,
+                self.bad2)
+        if self.world == 1:
+            it = L.bam_solve(*args, lowrank=self.use_lowrank, max_ns=self.max_ns)
+        else:  # shard partials of M = I + 4 W W^T are summed between the two phases of the solve
+            L.bam_solve(*args, max_ns=self.max_ns, world=self.world, phase=1)
+            ld = (D + 7) // 8 * 8
+            self.dist.all_reduce(self.ws_v[3 * D * ld: 4 * D * ld], group=self.group)
+            it = L.bam_solve(*args, max_ns=self.max_ns, world=self.world, phase=2)
         self.ns_iters.append(it)
         return it
 

@@ -86,7 +86,7 @@ class GSMEngine:
     def launches_per_step(self):
         """Kernels of libgsmvi_b200.so launched by one step (bench.py reports it as gpu_launches)."""
         panels = (self.D + 127) // 128
-        potrf = 1 + panels + 2 * (panels - 1)
+        potrf = 1 + panels + (panels - 1)  # tril copy, panel kernels, SYRK GEMMs
         upd = 4
         return (0 if self.z_tape is not None else 1) + 1 + (1 if self.target is not None else 0) + upd + potrf + \
             (2 if self.world > 1 else 0)

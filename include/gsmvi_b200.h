@@ -101,10 +101,13 @@ int gsmvi_bam_stats(const float* X, long long ldx, const float* G, long long ldg
  *   mu_out = mu0/(1+reg) + reg/(1+reg) (S gbar + xbar).
  * fp64 internally; SYNCHRONISES `stream` once per Newton-Schulz iteration (residual read).  *ns_iters_host <- iterations
  * run (host int); *bad_flag (device int) <- 1 if V or I+N was not positive definite (outputs are then garbage).
- * solve_workspace: gsmvi_workspace_bytes(GSMVI_WS_BAM_SOLVE, B, D) bytes, 16-byte aligned. */
+ * solve_workspace: gsmvi_workspace_bytes(GSMVI_WS_BAM_SOLVE, B, D) bytes, 16-byte aligned.
+ * Sharded batch: world = number of shards, B = this shard's rows.  phase 0 = whole solve (world must be 1);
+ * phase 1 = up to this shard's partial M_r = I/world + 4 W_r W_r^T, stored as D x roundup(D,8) doubles at
+ * solve_workspace + 3*D*roundup(D,8) doubles - all-reduce (sum) it across shards - then phase 2 = the rest. */
 int gsmvi_bam_solve(const void* stats_workspace, int B, int D, int B_total, const float* mu0, const float* Sigma0,
                     long long lds0, double reg, double jitter, float* mu_out, float* Sigma_out, long long ldso, void* solve_workspace,
-                    int max_ns_iters, int* ns_iters_host, int* bad_flag, void* stream);
+                    int max_ns_iters, int* ns_iters_host, int* bad_flag, int world, int phase, void* stream);
 
 /* Low-rank BaM update (K = B + 1 < D).  Replaces bam_lowrank_update (gsmvi/bam.py:72-114) and compute_Q
  * (gsmvi/bam.py:10-17: host ARPACK svds) with the exact factor Q = [sqrt(reg/B) Gc^T, sqrt(reg/(1+reg)) gbar] of U:

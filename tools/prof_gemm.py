@@ -1,0 +1,23 @@
+"""The four batch-sized GEMM launches of one GSM step at D = B = 4096, repeated; target of the ncu --set full capture."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gsm-vi_b200"))
+import torch
+from gsmvi_b200 import _lib as L
+D = B = int(os.environ.get("GSMVI_PROF_D", "4096"))
+g = torch.Generator().manual_seed(0)
+Z = torch.randn(B, D, generator=g).cuda()
+Lm = torch.tril(torch.randn(D, D, generator=g)).cuda() / D**0.5
+P = torch.randn(D, D, generator=g).cuda(); P = (P + P.t()) / 2
+T = torch.randn(3 * B, D, generator=g).cuda()
+S = torch.eye(D).cuda()
+X = torch.empty(B, D, device="cuda"); G = torch.empty(B, D, device="cuda"); W = torch.empty(B, D, device="cuda")
+So = torch.empty(D, D, device="cuda"); bias = torch.zeros(D, device="cuda")
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+for _ in range(reps):
+    L.gemm_tf32(Z, Lm, X, B, D, D, krange=L.KR_B_LOWER, bias_n=bias)                      # sample
+    L.gemm_tf32(X, P, G, B, D, D, alpha=-1.0, bias_n=bias)                               # score
+    L.gemm_tf32(G, S, W, B, D, D)                                                        # W = G Sigma
+    L.gemm_tf32(T[:2 * B], T[B:], So, D, D, 2 * B, a_mn=True, b_mn=True, alpha=-1.0 / B, beta=1.0, Cin=S, tri=True, mirror=True)
+torch.cuda.synchronize()
+print("done")

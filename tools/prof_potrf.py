@@ -1,0 +1,13 @@
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gsm-vi_b200"))
+import torch
+from gsmvi_b200 import _lib as L
+D = 1024
+g = torch.Generator().manual_seed(0)
+A = torch.randn(D, D, generator=g).cuda(); S = A @ A.t() / D + 0.1 * torch.eye(D, device="cuda")
+Lo = torch.empty(D, D, device="cuda"); bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+ws = torch.empty(L.workspace_bytes(L.WS_POTRF, 0, D) // 4, device="cuda")
+for _ in range(3):
+    L.potrf_check(S, Lo, D, bad, ws)
+torch.cuda.synchronize(); print("ok", int(bad.item()))

@@ -3,6 +3,7 @@
 
 #include "bam_solve.cuh"
 #include "dgemm.cuh"
+#include "gsm_ensemble.cuh"
 #include "gsm_kernels.cuh"
 #include "monitor.cuh"
 #include "potrf.cuh"
@@ -130,6 +131,11 @@ int gsmvi_gauss_logq_reduce(const float* Z_or_X, long long ld, int N, int D, con
                             long long ldl, int from_z, double* out, void* stream) {
   if (from_z) return gauss_logq_from_z(S(stream), Z_or_X, ld, N, D, L, ldl, out);
   return gauss_logq_from_x(S(stream), Z_or_X, ld, N, D, mu, L, ldl, out);
+}
+
+int gsmvi_gsm_ensemble_fit(const float* P, const float* c, float* mu, float* Sigma, int F, int D, int B, int niter,
+                           unsigned long long seed, const float* z_tape, int* reverts, void* stream) {
+  return gsm_ensemble_fit(S(stream), P, c, mu, Sigma, F, D, B, niter, seed, z_tape, reverts);
 }
 
 }  // extern "C"

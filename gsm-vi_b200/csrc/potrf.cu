@@ -10,6 +10,7 @@
 // the flag and solve L21 L11^T = A21 one row per thread in registers;  (2) the SYRK trailing update
 // A22 -= L21 L21^T on lower tiles, on the tcgen05 3xTF32 GEMM.
 #include "potrf.cuh"
+#include "chol_block.cuh"
 
 #include <math.h>
 #include <stdio.h>
@@ -48,26 +49,6 @@ __device__ __forceinline__ void tile4x4_mac(const float* __restrict__ Arows, int
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         acc[r][c] += a[r].x * b[c].x + a[r].y * b[c].y + a[r].z * b[c].z + a[r].w * b[c].w;
-  }
-}
-
-// One column step of the warp-level 32x32 Cholesky (row `lane` of the block lives in row[0..31]); the recursion on the
-// template parameter forces full unrolling so that row[] is only ever indexed statically (stays in registers).
-template <int J>
-__device__ __forceinline__ void chol32_step(float (&row)[32], int lane, float* dinv_out, int& isbad) {
-  if constexpr (J < 32) {
-    const float d = __shfl_sync(0xffffffffu, row[J], J);
-    if (!(d > 0.0f) || isinf(d)) isbad = 1;
-    float r = rsqrtf(d);
-    r = r * (1.5f - 0.5f * d * r * r);          // one Newton step: full fp32 accuracy without the slow sqrt + divide
-    row[J] = (lane == J) ? d * r : row[J] * r;  // l_jj = sqrt(d), l_ij = a_ij / l_jj
-    if (lane == J) dinv_out[J] = r;
-#pragma unroll
-    for (int k = J + 1; k < 32; ++k) {
-      const float lk = __shfl_sync(0xffffffffu, row[J], k);
-      if (lane >= k) row[k] -= row[J] * lk;
-    }
-    chol32_step<J + 1>(row, lane, dinv_out, isbad);
   }
 }
 

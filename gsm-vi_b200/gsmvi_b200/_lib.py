@@ -213,3 +213,22 @@ def _declare(L):  # noqa: F811
 def gauss_logq_reduce(Z_or_X, N, D, mu, L_, out, from_z):
     check(lib().gsmvi_gauss_logq_reduce(ptr(Z_or_X), Z_or_X.stride(0), N, D, ptr(mu), ptr(L_), L_.stride(0), int(from_z),
                                         ptr(out), stream_ptr()), "gsmvi_gauss_logq_reduce")
+
+
+# ------------------------------------------------------------------------------------------------ ensemble
+def _declare_ens(L):
+    L.gsmvi_gsm_ensemble_fit.restype = c_i
+    L.gsmvi_gsm_ensemble_fit.argtypes = [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_ull, c_p, c_p, c_p]
+
+
+_declare_mon_level = _declare
+
+
+def _declare(L):  # noqa: F811
+    _declare_mon_level(L)
+    _declare_ens(L)
+
+
+def gsm_ensemble_fit_raw(P, c, mu, Sigma, F, D, B, niter, seed, z_tape, reverts):
+    check(lib().gsmvi_gsm_ensemble_fit(ptr(P), ptr(c), ptr(mu), ptr(Sigma), F, D, B, niter, seed & (2**64 - 1), ptr(z_tape),
+                                       ptr(reverts), stream_ptr()), "gsmvi_gsm_ensemble_fit")

@@ -207,16 +207,18 @@ def run_ours(args):
     ldw = (D + 31) // 32 * 32
     W = ws[: Bl * ldw].view(Bl, ldw)
     T = ws[Bl * ldw: 4 * Bl * ldw].view(3 * Bl, ldw)
+    Tlo = ws[4 * Bl * ldw: 7 * Bl * ldw].view(3 * Bl, ldw)
     for _ in range(nrep):
         evs[0].record()
-        L.sample(eng.mu, eng.Lb, eng.Zb, eng.Xb, Bl, D, npass)
+        L.sample(eng.mu, eng.Lhi, eng.Zb, eng.Xb, Bl, D, npass, L_lo=eng.Llo)
         evs[1].record()
-        L.gauss_score(eng.Xb, tgt.Pb, tgt.c, eng.Gb, Bl, D, npass)
+        L.gauss_score(eng.Xb, tgt.Phib, tgt.c, eng.Gb, Bl, D, npass, P_lo=tgt.Plob)
         evs[2].record()
-        L.gemm_tf32(eng.Gb[:, :D], eng.Sb[:, :D], W[:, :D], Bl, D, D, npass=npass)
+        L.gemm_tf32(eng.Gb[:, :D], eng.Shi[:, :D], W[:, :D], Bl, D, D, npass=npass, B_lo=eng.Slo[:, :D])
         evs[3].record()
         L.gemm_tf32(T[: 2 * Bl, :D], T[Bl:, :D], eng.Snb[:, :D], D, D, 2 * Bl, a_mn=True, b_mn=True, alpha=-1.0 / B,
-                    beta=1.0, Cin=eng.Sb[:, :D], tri=True, mirror=True, npass=npass)
+                    beta=1.0, Cin=eng.Sb[:, :D], tri=True, mirror=True, npass=npass, A_lo=Tlo[: 2 * Bl, :D],
+                    B_lo=Tlo[Bl:, :D])
         evs[4].record()
         torch.cuda.synchronize()
         gemm_ms += sum(evs[k].elapsed_time(evs[k + 1]) for k in range(4))

@@ -31,7 +31,7 @@ long long gsmvi_workspace_bytes(int kind, int B, int D) {
 int gsmvi_gemm_tf32(const float* A, long long a_rows, long long a_cols, long long lda, int a_mn, const float* B,
                     long long b_rows, long long b_cols, long long ldb, int b_mn, float* C, long long ldc, int M, int N,
                     int K, float alpha, float beta, const float* Cin, long long ldcin, const float* bias_n, int npass,
-                    int tri, int mirror, int krange, int neg_from, void* stream) {
+                    int tri, int mirror, int krange, int neg_from, const float* A_lo, const float* B_lo, void* stream) {
   GemmOpts o;
   o.npass = npass;
   o.a_mn = a_mn != 0;
@@ -45,7 +45,7 @@ int gsmvi_gemm_tf32(const float* A, long long a_rows, long long a_cols, long lon
   o.mirror = mirror != 0;
   o.krange = krange;
   o.neg_from = neg_from;
-  MatView a{A, a_rows, a_cols, lda}, b{B, b_rows, b_cols, ldb};
+  MatView a{A, a_rows, a_cols, lda, A_lo}, b{B, b_rows, b_cols, ldb, B_lo};
   return launch_gemm_tf32(S(stream), M, N, K, a, b, C, ldc, o);
 }
 
@@ -59,22 +59,28 @@ int gsmvi_philox_normal(float* Z, long long ldz, int B, int D, unsigned long lon
   return philox_normal(S(stream), Z, ldz, B, D, seed, offset);
 }
 
-int gsmvi_sample(const float* mu, const float* L, long long ldl, const float* Z, long long ldz, float* X,
-                 long long ldx, int B, int D, int npass, void* stream) {
-  if (!mu || !L || !Z || !X || B <= 0 || D <= 0) return GSMVI_EINVAL;
-  return sample_mvn(S(stream), mu, L, ldl, Z, ldz, X, ldx, B, D, npass);
+int gsmvi_tf32_split(const float* A, long long lda, float* A_hi, float* A_lo, long long ldo, int rows, int cols,
+                     void* stream) {
+  return tf32_split(S(stream), A, lda, A_hi, A_lo, ldo, rows, cols);
 }
 
-int gsmvi_gauss_score(const float* X, long long ldx, const float* P, long long ldp, const float* c, float* G,
-                      long long ldg, int B, int D, int npass, void* stream) {
+int gsmvi_sample(const float* mu, const float* L, const float* L_lo, long long ldl, const float* Z, long long ldz,
+                 float* X, long long ldx, int B, int D, int npass, void* stream) {
+  if (!mu || !L || !Z || !X || B <= 0 || D <= 0) return GSMVI_EINVAL;
+  return sample_mvn(S(stream), mu, L, L_lo, ldl, Z, ldz, X, ldx, B, D, npass);
+}
+
+int gsmvi_gauss_score(const float* X, long long ldx, const float* P, const float* P_lo, long long ldp, const float* c,
+                      float* G, long long ldg, int B, int D, int npass, void* stream) {
   if (!X || !P || !c || !G || B <= 0 || D <= 0) return GSMVI_EINVAL;
-  return gauss_score(S(stream), X, ldx, P, ldp, c, G, ldg, B, D, npass);
+  return gauss_score(S(stream), X, ldx, P, P_lo, ldp, c, G, ldg, B, D, npass);
 }
 
 int gsmvi_gsm_update(const float* X, long long ldx, const float* G, long long ldg, const float* mu,
-                     const float* Sigma, long long lds, float* mu_out, float* Sigma_out, long long ldso, int B, int D,
-                     int B_total, int mode, void* workspace, int npass, void* stream) {
-  return gsm_update(S(stream), X, ldx, G, ldg, mu, Sigma, lds, mu_out, Sigma_out, ldso, B, D, B_total, mode,
+                     const float* Sigma, const float* Sigma_hi, const float* Sigma_lo, long long lds, float* mu_out,
+                     float* Sigma_out, long long ldso, int B, int D, int B_total, int mode, void* workspace, int npass,
+                     void* stream) {
+  return gsm_update(S(stream), X, ldx, G, ldg, mu, Sigma, Sigma_hi, Sigma_lo, lds, mu_out, Sigma_out, ldso, B, D, B_total, mode,
                     static_cast<float*>(workspace), npass);
 }
 

@@ -26,19 +26,50 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// hi = tf32_rn(v), lo = tf32_rn(v - hi): the covariance GEMM consumes T pre-split (no in-kernel conversion).
+__device__ __forceinline__ void store_split1(float* hi, float* lo, float v) {
+  const float h = ptx::to_tf32(v);
+  *hi = h;
+  *lo = ptx::to_tf32(v - h);
+}
+__device__ __forceinline__ void store_split4(float* hi, float* lo, const float4 v) {
+  float4 h, l;
+  h.x = ptx::to_tf32(v.x); l.x = ptx::to_tf32(v.x - h.x);
+  h.y = ptx::to_tf32(v.y); l.y = ptx::to_tf32(v.y - h.y);
+  h.z = ptx::to_tf32(v.z); l.z = ptx::to_tf32(v.z - h.z);
+  h.w = ptx::to_tf32(v.w); l.w = ptx::to_tf32(v.w - h.w);
+  *reinterpret_cast<float4*>(hi) = h;
+  *reinterpret_cast<float4*>(lo) = l;
+}
+
+// hi = tf32_rn(a), lo = tf32_rn(a - hi): the round-to-nearest 3xTF32 split of a reused GEMM operand, done once
+__global__ void tf32_split_kernel(const float* __restrict__ A, long long lda, float* __restrict__ Hi, float* __restrict__ Lo,
+                                  long long ldo, int rows, int cols) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const long long i = blockIdx.y;
+  if (j >= cols) return;
+  if (j + 3 < cols && ((lda | ldo) & 3) == 0 &&
+      (((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Hi) | reinterpret_cast<uintptr_t>(Lo)) & 15) == 0)) {
+    store_split4(Hi + i * ldo + j, Lo + i * ldo + j, *reinterpret_cast<const float4*>(A + i * lda + j));
+  } else {
+    for (int t = 0; t < 4 && j + t < cols; ++t) store_split1(Hi + i * ldo + j + t, Lo + i * ldo + j + t, A[i * lda + j + t]);
+  }
+}
+
 // One CTA handles RP_ROWS consecutive samples.  Pass 1 (a warp per row): the two dot products and the per-sample
 // scalars.  Pass 2 (a thread per 4 columns): rows e, u, d of T = [E; U; D] and the column sums of u.
 __global__ void __launch_bounds__(RP_THREADS) gsm_rowpass_kernel(const float* __restrict__ X, long long ldx,
                                                                  const float* __restrict__ G, long long ldg,
                                                                  const float* __restrict__ W, long long ldw,
                                                                  const float* __restrict__ mu, float* __restrict__ T,
-                                                                 long long ldt, float* __restrict__ usum, int B, int D) {
+                                                                 float* __restrict__ Tlo, long long ldt,
+                                                                 float* __restrict__ usum, int B, int D) {
   __shared__ float s_alpha[RP_ROWS], s_beta[RP_ROWS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * RP_ROWS;
   const bool vec = ((D & 3) == 0) && ((ldx & 3) == 0) && ((ldg & 3) == 0) && ((ldw & 3) == 0) && ((ldt & 3) == 0) &&
                    (((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(W) |
-                      reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(mu)) & 15) == 0);
+                      reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(Tlo) | reinterpret_cast<uintptr_t>(mu)) & 15) == 0);
   for (int r = warp; r < RP_ROWS; r += RP_THREADS / 32) {
     const int b = row0 + r;
     if (b >= B) break;
@@ -87,9 +118,9 @@ __global__ void __launch_bounds__(RP_THREADS) gsm_rowpass_kernel(const float* __
         u.x = al * wv.x + be * d.x; u.y = al * wv.y + be * d.y; u.z = al * wv.z + be * d.z; u.w = al * wv.w + be * d.w;
         e.x = d.x + u.x; e.y = d.y + u.y; e.z = d.z + u.z; e.w = d.w + u.w;
         acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
-        *reinterpret_cast<float4*>(T + b * ldt + j) = e;
-        *reinterpret_cast<float4*>(T + (b + B) * ldt + j) = u;
-        *reinterpret_cast<float4*>(T + (b + 2LL * B) * ldt + j) = d;
+        store_split4(T + b * ldt + j, Tlo + b * ldt + j, e);
+        store_split4(T + (b + B) * ldt + j, Tlo + (b + B) * ldt + j, u);
+        store_split4(T + (b + 2LL * B) * ldt + j, Tlo + (b + 2LL * B) * ldt + j, d);
       }
       atomicAdd(usum + j + 0, acc.x);
       atomicAdd(usum + j + 1, acc.y);
@@ -105,9 +136,9 @@ __global__ void __launch_bounds__(RP_THREADS) gsm_rowpass_kernel(const float* __
         const float d = m - X[b * ldx + j];
         const float u = s_alpha[r] * W[b * ldw + j] + s_beta[r] * d;
         acc += u;
-        T[b * ldt + j] = d + u;
-        T[(b + B) * ldt + j] = u;
-        T[(b + 2LL * B) * ldt + j] = d;
+        store_split1(T + b * ldt + j, Tlo + b * ldt + j, d + u);
+        store_split1(T + (b + B) * ldt + j, Tlo + (b + B) * ldt + j, u);
+        store_split1(T + (b + 2LL * B) * ldt + j, Tlo + (b + 2LL * B) * ldt + j, d);
       }
       atomicAdd(usum + j, acc);
     }
@@ -184,55 +215,65 @@ int philox_normal(cudaStream_t stream, float* Z, long long ldz, int B, int D, un
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
 }
 
-int sample_mvn(cudaStream_t stream, const float* mu, const float* L, long long ldl, const float* Z, long long ldz,
-               float* X, long long ldx, int B, int D, int npass) {
+int tf32_split(cudaStream_t stream, const float* A, long long lda, float* Hi, float* Lo, long long ldo, int rows, int cols) {
+  if (!A || !Hi || !Lo || rows <= 0 || cols <= 0) return GSMVI_EINVAL;
+  tf32_split_kernel<<<dim3((cols / 4 + 256) / 256, rows), 256, 0, stream>>>(A, lda, Hi, Lo, ldo, rows, cols);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
+}
+
+int sample_mvn(cudaStream_t stream, const float* mu, const float* L, const float* L_lo, long long ldl, const float* Z,
+               long long ldz, float* X, long long ldx, int B, int D, int npass) {
   // X[b,i] = mu[i] + sum_{k<=i} Z[b,k] L[i,k]
   GemmOpts o;
   o.npass = npass;
   o.bias_n = mu;
   o.krange = KR_B_LOWER;
-  MatView vz{Z, B, D, ldz}, vl{L, D, D, ldl};
+  MatView vz{Z, B, D, ldz}, vl{L, D, D, ldl, L_lo};
   return launch_gemm_tf32(stream, B, D, D, vz, vl, X, ldx, o);
 }
 
-int gauss_score(cudaStream_t stream, const float* X, long long ldx, const float* P, long long ldp, const float* c,
-                float* G, long long ldg, int B, int D, int npass) {
+int gauss_score(cudaStream_t stream, const float* X, long long ldx, const float* P, const float* P_lo, long long ldp,
+                const float* c, float* G, long long ldg, int B, int D, int npass) {
   // G = -(X - m) P = -X P + c,  c = P m   (P symmetric: P[n,k] read K-major as-is)
   GemmOpts o;
   o.npass = npass;
   o.alpha = -1.0f;
   o.bias_n = c;
-  MatView vx{X, B, D, ldx}, vp{P, D, D, ldp};
+  MatView vx{X, B, D, ldx}, vp{P, D, D, ldp, P_lo};
   return launch_gemm_tf32(stream, B, D, D, vx, vp, G, ldg, o);
 }
 
 size_t gsm_update_workspace_bytes(int B, int D) {
   const long long ldw = round_up(D, 32);
-  // W [B x ldw] + T = [E; U; D] [3B x ldw] + usum [ldw]
-  return static_cast<size_t>((4LL * B + 1) * ldw) * sizeof(float);
+  // W [B x ldw] + T_hi, T_lo = split [E; U; D] [2 x 3B x ldw] + usum [ldw]
+  return static_cast<size_t>((7LL * B + 1) * ldw) * sizeof(float);
 }
 
 int gsm_update(cudaStream_t stream, const float* X, long long ldx, const float* G, long long ldg, const float* mu,
-               const float* Sigma, long long lds, float* mu_out, float* Sigma_out, long long ldso, int B, int D,
-               int B_total, int mode, float* workspace, int npass) {
+               const float* Sigma, const float* Sigma_hi, const float* Sigma_lo, long long lds, float* mu_out,
+               float* Sigma_out, long long ldso, int B, int D, int B_total, int mode, float* workspace, int npass) {
   if (!X || !G || !mu || !Sigma || !mu_out || !Sigma_out || !workspace || B <= 0 || D <= 0 || B_total < B)
     return GSMVI_EINVAL;
   const long long ldw = round_up(D, 32);
   float* W = workspace;
   float* T = W + static_cast<long long>(B) * ldw;
-  float* usum = T + 3LL * B * ldw;
+  float* Tlo = T + 3LL * B * ldw;
+  float* usum = Tlo + 3LL * B * ldw;
   cudaError_t e = cudaMemsetAsync(usum, 0, ldw * sizeof(float), stream);
   if (e != cudaSuccess) return static_cast<int>(e);
   // (i) W = G Sigma0   (Sigma0 symmetric)
   {
     GemmOpts o;
     o.npass = npass;
-    MatView vg{G, B, D, ldg}, vs{Sigma, D, D, lds};
+    // pre-split pair (hi, lo) if given, else the raw matrix split in-kernel
+    const bool pre = Sigma_hi != nullptr && Sigma_lo != nullptr;
+    MatView vg{G, B, D, ldg}, vs{pre ? Sigma_hi : Sigma, D, D, lds, pre ? Sigma_lo : nullptr};
     int rc = launch_gemm_tf32(stream, B, D, D, vg, vs, W, ldw, o);
     if (rc != GSMVI_OK) return rc;
   }
   // (ii) row pass
-  gsm_rowpass_kernel<<<(B + RP_ROWS - 1) / RP_ROWS, RP_THREADS, 0, stream>>>(X, ldx, G, ldg, W, ldw, mu, T, ldw, usum, B, D);
+  gsm_rowpass_kernel<<<(B + RP_ROWS - 1) / RP_ROWS, RP_THREADS, 0, stream>>>(X, ldx, G, ldg, W, ldw, mu, T, Tlo, ldw, usum, B, D);
   e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   // (iii) Sigma_out = [Sigma0] - (E^T U + U^T D) / B_total : rows of T are K, so both operands are MN-major views
@@ -248,7 +289,8 @@ int gsm_update(cudaStream_t stream, const float* X, long long ldx, const float* 
       o.Cin = Sigma;
       o.ldcin = lds;
     }
-    MatView va{T, 2LL * B, D, ldw}, vb{T + static_cast<long long>(B) * ldw, 2LL * B, D, ldw};
+    // both operands arrive pre-split (T_hi, T_lo from the row pass): no in-kernel conversion for 3-pass modes
+    MatView va{T, 2LL * B, D, ldw, Tlo}, vb{T + static_cast<long long>(B) * ldw, 2LL * B, D, ldw, Tlo + static_cast<long long>(B) * ldw};
     int rc = launch_gemm_tf32(stream, D, D, 2 * B, va, vb, Sigma_out, ldso, o);
     if (rc != GSMVI_OK) return rc;
   }

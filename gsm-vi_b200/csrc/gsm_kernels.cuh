@@ -6,13 +6,15 @@ namespace gsmvi {
 
 int philox_normal(cudaStream_t stream, float* Z, long long ldz, int B, int D, unsigned long long seed,
                   unsigned long long offset);
-int sample_mvn(cudaStream_t stream, const float* mu, const float* L, long long ldl, const float* Z, long long ldz,
-               float* X, long long ldx, int B, int D, int npass);
-int gauss_score(cudaStream_t stream, const float* X, long long ldx, const float* P, long long ldp, const float* c,
-                float* G, long long ldg, int B, int D, int npass);
+// hi = tf32_rn(a), lo = tf32_rn(a - hi).  Passing (hi, lo) as (X, X_lo) below lets the GEMM skip converting that operand.
+int tf32_split(cudaStream_t stream, const float* A, long long lda, float* Hi, float* Lo, long long ldo, int rows, int cols);
+int sample_mvn(cudaStream_t stream, const float* mu, const float* L, const float* L_lo, long long ldl, const float* Z,
+               long long ldz, float* X, long long ldx, int B, int D, int npass);
+int gauss_score(cudaStream_t stream, const float* X, long long ldx, const float* P, const float* P_lo, long long ldp,
+                const float* c, float* G, long long ldg, int B, int D, int npass);
 size_t gsm_update_workspace_bytes(int B, int D);
 int gsm_update(cudaStream_t stream, const float* X, long long ldx, const float* G, long long ldg, const float* mu,
-               const float* Sigma, long long lds, float* mu_out, float* Sigma_out, long long ldso, int B, int D,
+               const float* Sigma, const float* Sigma_hi, const float* Sigma_lo, long long lds, float* mu_out, float* Sigma_out, long long ldso, int B, int D,
                int B_total, int mode, float* workspace, int npass);
 int gsm_apply_stats(cudaStream_t stream, const float* Sigma, long long lds, const float* dSigma, long long ldd,
                     const float* mu, const float* dmu, float* Sigma_out, long long ldso, float* mu_out, int D);

@@ -31,6 +31,10 @@ __global__ void tril_copy_kernel(const float* __restrict__ A, long long lda, flo
 //   (1) warp 0 factors the 32x32 diagonal block, one row per lane in registers, pivots broadcast with shuffles;
 //   (2) a thread per row below solves its 32 panel entries against that block by forward substitution (registers);
 //   (3) all threads apply the rank-32 update to the trailing lower triangle in 4x4 register tiles.
+__device__ long long g_pt[24];
+#define PT(i) do { if (threadIdx.x == 0 && gridDim.x > 8) g_pt[i] = clock64(); } while (0)
+constexpr int RPC = 32;          // rows of the panel per TRSM CTA (eight threads per row)
+constexpr int TPR = 256 / RPC;
 constexpr int DS = NB + 4;  // shared-memory leading dimension: rows stay 16-byte aligned, quarter-warps hit distinct banks
 
 // acc[r][c] += sum_k Arows[r * lda_][k] * Brows[c * ldb_][k]   (both row-major over k; kbeg, kend multiples of 4).
@@ -128,10 +132,11 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
 // Panel kernel: one launch factors the 128-wide panel starting at column j0 of the n x n matrix L (in place).
 //   CTA 0            : Cholesky of the nb x nb diagonal block (shared memory / registers), written back with explicit
 //                      zeros above the diagonal, then publishes `epoch` through *ready (release).
-//   CTA t = 1, 2, ...: TRSM of rows r0 = j0 + nb + 128 (t-1) ...: prefetches its 128 x 128 tile of A21 into shared memory
-//                      while CTA 0 works, acquires the flag, loads L11, and solves X L11^T = A21 one row per thread in
-//                      registers (fp32 FMAs: no explicit inverse, no tensor-core rounding), 32 columns at a time.
-// All CTAs are co-resident (at most 1 + 31 CTAs of one per SM), so the spin-wait cannot deadlock.
+//   CTA t = 1, 2, ...: TRSM of rows r0 = j0 + nb + 32 (t-1) ...: prefetches its 32 x 128 tile of A21 into shared memory
+//                      while CTA 0 works, acquires the flag, loads L11, and solves X L11^T = A21 with eight threads per
+//                      row in registers (fp32 FMAs: no explicit inverse, no tensor-core rounding), 32 columns at a time.
+// All CTAs must be co-resident for the spin-wait (1 + rest/32 CTAs of one per SM: n <= 4700; larger n would need a
+// larger RPC).
 // A non-positive or non-finite pivot sets *flag (bit 0); the panel is then garbage and the caller discards L.
 __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(float* __restrict__ Lm, long long ld, int n, int j0, int nb,
                                                              int* __restrict__ flag, unsigned* __restrict__ ready,
@@ -147,6 +152,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(float* __restrict__
   if (tid == 0) bad = 0;
 
   if (blockIdx.x == 0) {
+    PT(0);
     // ---------------- diagonal block
     if (vec_ok) {
       float4 v[16];  // 4096 float4: 16 loads per thread issued back to back, then stored
@@ -171,7 +177,9 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(float* __restrict__
       }
     }
     __syncthreads();
+    PT(1);
     const bool isbad = factor_block_smem(s, dinv, &bad);
+    PT(2);
     if (vec_ok) {
 #pragma unroll 4
       for (int e = 0; e < 16; ++e) {
@@ -190,14 +198,16 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(float* __restrict__
       if (isbad) atomicOr(flag, 1);
       st_release_u32(ready, epoch);
     }
+    PT(3);
     return;
   }
 
   // ---------------- TRSM rows (nb == NB whenever rows below exist)
-  const int r0 = j0 + nb + (blockIdx.x - 1) * NB;
-  const int rows = min(NB, n - r0);
+  if (blockIdx.x == 1) PT(8);
+  const int r0 = j0 + nb + (blockIdx.x - 1) * RPC;
+  const int rows = min(RPC, n - r0);
   float* a21 = Lm + static_cast<long long>(r0) * ld + j0;
-  for (int q = tid; q < NB * 32; q += 256) {  // prefetch this CTA's rows while CTA 0 factors
+  for (int q = tid; q < RPC * 32; q += 256) {  // prefetch this CTA's rows while CTA 0 factors
     const int i = q >> 5, j4 = (q & 31) * 4;
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < rows) {
@@ -207,6 +217,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(float* __restrict__
     }
     *reinterpret_cast<float4*>(at + i * DS + j4) = t;
   }
+  if (blockIdx.x == 1) PT(9);
   if (tid == 0) {
     const long long t0 = clock64();
     while (ld_acquire_u32(ready) != epoch) {
@@ -215,6 +226,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(float* __restrict__
     }
   }
   __syncthreads();
+  if (blockIdx.x == 1) PT(10);
   for (int q = tid; q < NB * 32; q += 256) {  // L11 (just published; lower triangle + explicit zeros)
     const int i = q >> 5, j4 = (q & 31) * 4;
     float4 t;
@@ -226,55 +238,73 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(float* __restrict__
   __syncthreads();
   if (tid < NB) dinv[tid] = 1.0f / s[tid * DS + tid];
   __syncthreads();
-  if (tid < rows) {
-    float* myrow = at + tid * DS;
+  if (blockIdx.x == 1) PT(11);
+  {
+    // TPR threads per row: thread (row, part) applies the block updates to 32/TPR of the 32 columns of block J, then
+    // the part-0 threads run the in-block forward substitution.  L rows are read as broadcast float4.
+    constexpr int CPT = 32 / TPR;  // columns per thread in the update phase
+    const int row = tid % RPC, part = tid / RPC;
+    float* myrow = at + row * DS;
 #pragma unroll 1
     for (int J = 0; J < NB / 32; ++J) {
-      float v[32];
-#pragma unroll
-      for (int k = 0; k < 32; k += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(myrow + 32 * J + k);
-        v[k] = t.x; v[k + 1] = t.y; v[k + 2] = t.z; v[k + 3] = t.w;
-      }
+      if (J > 0) {
+        float v[CPT];
+        {
+          const float4 t = *reinterpret_cast<const float4*>(myrow + 32 * J + CPT * part);
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        }
 #pragma unroll 1
-      for (int I = 0; I < J; ++I) {  // v -= X_I L11[J][I]^T
-        float xp[32];
+        for (int I = 0; I < J; ++I) {  // v -= X_I L11[J][I]^T
+          float4 xp[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) xp[k] = *reinterpret_cast<const float4*>(myrow + 32 * I + 4 * k);
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) {
+            const float4* lr = reinterpret_cast<const float4*>(s + (32 * J + CPT * part + j) * DS + 32 * I);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float4 l = lr[k];
+              a0 += xp[k].x * l.x;
+              a1 += xp[k].y * l.y;
+              a2 += xp[k].z * l.z;
+              a3 += xp[k].w * l.w;
+            }
+            v[j] -= (a0 + a1) + (a2 + a3);
+          }
+        }
+        *reinterpret_cast<float4*>(myrow + 32 * J + CPT * part) = make_float4(v[0], v[1], v[2], v[3]);
+        __syncthreads();
+      }
+      if (part == 0) {  // in-block forward substitution (sequential in j)
+        float v[32];
 #pragma unroll
         for (int k = 0; k < 32; k += 4) {
-          const float4 t = *reinterpret_cast<const float4*>(myrow + 32 * I + k);
-          xp[k] = t.x; xp[k + 1] = t.y; xp[k + 2] = t.z; xp[k + 3] = t.w;
+          const float4 t = *reinterpret_cast<const float4*>(myrow + 32 * J + k);
+          v[k] = t.x; v[k + 1] = t.y; v[k + 2] = t.z; v[k + 3] = t.w;
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float* lr = s + (32 * J + j) * DS + 32 * I;  // broadcast reads
-          float a0 = 0.f, a1 = 0.f;
+          float acc0 = v[j], acc1 = 0.0f;
+          const float* lrow = s + (32 * J + j) * DS + 32 * J;
 #pragma unroll
-          for (int k = 0; k < 32; k += 2) {
-            a0 += xp[k] * lr[k];
-            a1 += xp[k + 1] * lr[k + 1];
+          for (int k = 0; k + 1 < j; k += 2) {
+            acc0 -= v[k] * lrow[k];
+            acc1 -= v[k + 1] * lrow[k + 1];
           }
-          v[j] -= a0 + a1;
+          if (j & 1) acc0 -= v[j - 1] * lrow[j - 1];
+          v[j] = (acc0 + acc1) * dinv[32 * J + j];
         }
+#pragma unroll
+        for (int k = 0; k < 32; k += 4)
+          *reinterpret_cast<float4*>(myrow + 32 * J + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
       }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {  // in-block forward substitution
-        float acc0 = v[j], acc1 = 0.0f;
-        const float* lrow = s + (32 * J + j) * DS + 32 * J;
-#pragma unroll
-        for (int k = 0; k + 1 < j; k += 2) {
-          acc0 -= v[k] * lrow[k];
-          acc1 -= v[k + 1] * lrow[k + 1];
-        }
-        if (j & 1) acc0 -= v[j - 1] * lrow[j - 1];
-        v[j] = (acc0 + acc1) * dinv[32 * J + j];
-      }
-#pragma unroll
-      for (int k = 0; k < 32; k += 4)
-        *reinterpret_cast<float4*>(myrow + 32 * J + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+      __syncthreads();
     }
   }
   __syncthreads();
-  for (int q = tid; q < NB * 32; q += 256) {
+  if (blockIdx.x == 1) PT(12);
+  for (int q = tid; q < RPC * 32; q += 256) {
     const int i = q >> 5, j4 = (q & 31) * 4;
     if (i < rows) {
       const float4 t = *reinterpret_cast<const float4*>(at + i * DS + j4);
@@ -283,6 +313,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(float* __restrict__
              a21[static_cast<long long>(i) * ld + j4 + 2] = t.z; a21[static_cast<long long>(i) * ld + j4 + 3] = t.w; }
     }
   }
+  if (blockIdx.x == 1) PT(13);
 }
 
 size_t potrf_workspace_bytes(int n) {
@@ -311,7 +342,7 @@ int potrf_lower(cudaStream_t stream, const float* A, long long lda, float* L, lo
     const int nb = min(NB, n - j0);
     const int rest = n - j0 - nb;
     // panel: diagonal block (CTA 0) + TRSM of the rows below (one CTA per 128 rows)
-    potrf_panel_kernel<<<1 + (rest + NB - 1) / NB, 256, smem, stream>>>(L, ldl, n, j0, nb, flag, ready, ++epoch);
+    potrf_panel_kernel<<<1 + (rest + RPC - 1) / RPC, 256, smem, stream>>>(L, ldl, n, j0, nb, flag, ready, ++epoch);
     if (rest > 0) {
       float* a21 = L + static_cast<long long>(j0 + nb) * ldl + j0;
       float* a22 = L + static_cast<long long>(j0 + nb) * ldl + j0 + nb;
@@ -327,6 +358,13 @@ int potrf_lower(cudaStream_t stream, const float* A, long long lda, float* L, lo
       int rc = launch_gemm_tf32(stream, rest, rest, nb, vl, vl, a22, ldl, s);
       if (rc != GSMVI_OK) return rc;
     }
+  }
+  if (getenv("GSMVI_POTRF_TIMING")) {
+    long long h[24];
+    cudaStreamSynchronize(stream);
+    cudaMemcpyFromSymbol(h, g_pt, sizeof(h));
+    fprintf(stderr, "[potrf panel timing] CTA0: load %lld factor %lld store+publish %lld | CTA1: prefetch %lld wait %lld loadL11 %lld solve %lld store %lld | CTA1 end - CTA0 start %lld\n",
+            h[1] - h[0], h[2] - h[1], h[3] - h[2], h[9] - h[8], h[10] - h[9], h[11] - h[10], h[12] - h[11], h[13] - h[12], h[13] - h[0]);
   }
   e = cudaGetLastError();
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);

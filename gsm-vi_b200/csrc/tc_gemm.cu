@@ -34,17 +34,18 @@ int make_tmap_2d(CUtensorMap* out, const MatView& v, int box_cols, int box_rows,
   return r == CUDA_SUCCESS ? GSMVI_OK : GSMVI_EDRIVER;
 }
 
-template <int NPASS, bool SPLIT_RN, bool A_MN, bool B_MN>
-static int launch_one(cudaStream_t stream, const GemmArgs& args, const CUtensorMap& ta, const CUtensorMap& tb, int grid) {
+template <int NPASS, bool SPLIT_RN, bool A_MN, bool B_MN, int PRE>
+static int launch_one(cudaStream_t stream, const GemmArgs& args, const CUtensorMap& ta, const CUtensorMap& tb,
+                      const CUtensorMap& tal, const CUtensorMap& tbl, int grid) {
   using Cfg = GemmCfg<NPASS>;
   static bool attr_set = false;
-  auto kern = gemm_tf32_kernel<NPASS, SPLIT_RN, A_MN, B_MN>;
+  auto kern = gemm_tf32_kernel<NPASS, SPLIT_RN, A_MN, B_MN, PRE>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(args, ta, tb);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(args, ta, tb, tal, tbl);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
 }
@@ -69,28 +70,48 @@ int launch_gemm_tf32(cudaStream_t stream, int M, int N, int K, const MatView& A,
   if (o.beta != 0.0f && !o.Cin) return GSMVI_EINVAL;
   const int grid = o.tri ? a.tiles_m * (a.tiles_m + 1) / 2 : a.tiles_m * a.tiles_n;
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tal, tbl;
   int rc;
+  // pre-split operands only matter for the 3-pass modes; B alone or both (A alone is not instantiated)
+  const bool b_pre = (o.npass != 1) && B.lo != nullptr;
+  const bool a_pre = b_pre && A.lo != nullptr;
   if (K == 0) {
     // no operand is touched; still need valid maps for the kernel signature: point them at C (never loaded)
     MatView dummy{C, 1, 4, 4};
     if ((rc = make_tmap_2d(&ta, dummy, 4, 1, false)) != GSMVI_OK) return rc;
-    tb = ta;
+    tb = tal = tbl = ta;
   } else {
     rc = o.a_mn ? make_tmap_2d(&ta, A, 32, BK, true) : make_tmap_2d(&ta, A, BK, BM, false);
     if (rc != GSMVI_OK) return rc;
     rc = o.b_mn ? make_tmap_2d(&tb, B, 32, BK, true) : make_tmap_2d(&tb, B, BK, BN, false);
     if (rc != GSMVI_OK) return rc;
+    tal = ta;
+    tbl = tb;
+    if (a_pre) {
+      MatView al{A.lo, A.rows, A.cols, A.ld};
+      rc = o.a_mn ? make_tmap_2d(&tal, al, 32, BK, true) : make_tmap_2d(&tal, al, BK, BM, false);
+      if (rc != GSMVI_OK) return rc;
+    }
+    if (b_pre) {
+      MatView bl{B.lo, B.rows, B.cols, B.ld};
+      rc = o.b_mn ? make_tmap_2d(&tbl, bl, 32, BK, true) : make_tmap_2d(&tbl, bl, BK, BN, false);
+      if (rc != GSMVI_OK) return rc;
+    }
   }
 
-#define GSMVI_DISPATCH(NP, RN)                                                              \
-  if (!o.a_mn && !o.b_mn) return launch_one<NP, RN, false, false>(stream, a, ta, tb, grid); \
-  if (o.a_mn && !o.b_mn) return launch_one<NP, RN, true, false>(stream, a, ta, tb, grid);   \
-  if (!o.a_mn && o.b_mn) return launch_one<NP, RN, false, true>(stream, a, ta, tb, grid);   \
-  return launch_one<NP, RN, true, true>(stream, a, ta, tb, grid);
+#define GSMVI_DISPATCH_MN(NP, RN, PRE)                                                                    \
+  if (!o.a_mn && !o.b_mn) return launch_one<NP, RN, false, false, PRE>(stream, a, ta, tb, tal, tbl, grid); \
+  if (o.a_mn && !o.b_mn) return launch_one<NP, RN, true, false, PRE>(stream, a, ta, tb, tal, tbl, grid);   \
+  if (!o.a_mn && o.b_mn) return launch_one<NP, RN, false, true, PRE>(stream, a, ta, tb, tal, tbl, grid);   \
+  return launch_one<NP, RN, true, true, PRE>(stream, a, ta, tb, tal, tbl, grid);
+#define GSMVI_DISPATCH(NP, RN)                   \
+  if (a_pre) { GSMVI_DISPATCH_MN(NP, RN, 3) }    \
+  if (b_pre) { GSMVI_DISPATCH_MN(NP, RN, 2) }    \
+  GSMVI_DISPATCH_MN(NP, RN, 0)
   if (o.npass == 3) { GSMVI_DISPATCH(3, true) }
   if (o.npass == 2) { GSMVI_DISPATCH(3, false) }
-  GSMVI_DISPATCH(1, false)
+  GSMVI_DISPATCH_MN(1, false, 0)
+#undef GSMVI_DISPATCH_MN
 #undef GSMVI_DISPATCH
 }
 

@@ -16,6 +16,11 @@
 //    the small terms go to their own; the epilogue adds the four in fp32 round-to-nearest.
 //    The default (precision 3) rounds hi to nearest instead and stores it too: ~8x more accurate products
 //    (fp32-grade) for ~10% more shared-memory traffic.  1xTF32 mode skips the split (one accumulator).
+//  * pre-split operands: ncu shows the converters' LDS/STS traffic saturating the shared-memory pipe (tensor pipe
+//    ~48% active).  An operand may therefore come with a precomputed `lo` array (PRE bit): TMA then loads hi and lo
+//    tiles directly and the converters skip it.  Reused operands (Sigma, P, L) carry lo = tf32_rn(a - trunc(a)) next
+//    to the raw array (the tensor core truncates the raw value itself); when both operands are pre-split
+//    (covariance update: the row pass writes T_hi / T_lo) the kernel runs with no conversion at all.
 //  * warp-specialised: warp0 = TMA producer, warp1 = MMA issuer + TMEM owner, warps 2..9 = converters,
 //    and the same eight warps drain TMEM in the epilogue (tcgen05.ld 32x32b) with a fused
 //    alpha/beta/bias update, optional lower-triangle-only tiles and mirrored (symmetric) stores.
@@ -98,9 +103,12 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(bool a_mn, bool b_mn, boo
          ((b_mn ? 1u : 0u) << 16) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
 }
 
-template <int NPASS, bool SPLIT_RN, bool A_MN, bool B_MN>
+template <int NPASS, bool SPLIT_RN, bool A_MN, bool B_MN, int PRE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tf32_kernel(const GemmArgs args, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
+gemm_tf32_kernel(const GemmArgs args, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo) {
+  constexpr bool A_PRE = (PRE & 1) != 0, B_PRE = (PRE & 2) != 0;  // operand arrives pre-split (hi via tmA/tmB, lo via tmAlo/tmBlo)
+  constexpr bool NEED_CONV = (NPASS == 3) && !(A_PRE && B_PRE);
   using Cfg = GemmCfg<NPASS>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -179,7 +187,7 @@ gemm_tf32_kernel(const GemmArgs args, const __grid_constant__ CUtensorMap tmA, c
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-        ptx::mbar_arrive_expect_tx(full_bar(s), 2 * TILE_BYTES);
+        ptx::mbar_arrive_expect_tx(full_bar(s), (2 + (A_PRE ? 1 : 0) + (B_PRE ? 1 : 0)) * TILE_BYTES);
         const int k0 = (kb_begin + it) * BK;
         const uint32_t sA = stage_base + s * Cfg::STAGE_BYTES;
         const uint32_t sB = sA + TILE_BYTES;
@@ -194,6 +202,24 @@ gemm_tf32_kernel(const GemmArgs args, const __grid_constant__ CUtensorMap tmA, c
         } else {
 #pragma unroll
           for (int c = 0; c < BN / 32; ++c) ptx::tma_load_2d(sB + c * (BK * 128), &tmB, full_bar(s), n0 + 32 * c, k0);
+        }
+        if (A_PRE) {
+          if (!A_MN) {
+            ptx::tma_load_2d(sA + 2 * TILE_BYTES, &tmAlo, full_bar(s), k0, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 32; ++c)
+              ptx::tma_load_2d(sA + 2 * TILE_BYTES + c * (BK * 128), &tmAlo, full_bar(s), m0 + 32 * c, k0);
+          }
+        }
+        if (B_PRE) {
+          if (!B_MN) {
+            ptx::tma_load_2d(sB + 2 * TILE_BYTES, &tmBlo, full_bar(s), k0, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c)
+              ptx::tma_load_2d(sB + 2 * TILE_BYTES + c * (BK * 128), &tmBlo, full_bar(s), n0 + 32 * c, k0);
+          }
         }
       }
     }
@@ -212,7 +238,7 @@ gemm_tf32_kernel(const GemmArgs args, const __grid_constant__ CUtensorMap tmA, c
       for (int it = 0; it < num_kb; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
-        ptx::mbar_wait(NPASS == 3 ? ready_bar(s) : full_bar(s), ph);
+        ptx::mbar_wait(NEED_CONV ? ready_bar(s) : full_bar(s), ph);
         ptx::tc_fence_after_sync();
         const uint32_t sA = stage_base + s * Cfg::STAGE_BYTES;
         const uint32_t sB = sA + TILE_BYTES;
@@ -240,16 +266,18 @@ gemm_tf32_kernel(const GemmArgs args, const __grid_constant__ CUtensorMap tmA, c
   } else {
     // ===================== converter warps, then epilogue =====================
     const int ct = threadIdx.x - 64;  // 0..255
-    if (NPASS == 3) {
+    if (NEED_CONV) {
       for (int it = 0; it < num_kb; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         ptx::mbar_wait(full_bar(s), ph);
         uint8_t* st = smem + BAR_BYTES + s * Cfg::STAGE_BYTES;
-        constexpr int CHUNKS = 2 * TILE_BYTES / 16;  // 16-byte chunks in [A|B]
+        // 16-byte chunks of the operands that still need splitting: [A|B], or only A / only B when the other is pre-split
+        constexpr int CHUNK0 = A_PRE ? TILE_BYTES / 16 : 0;
+        constexpr int CHUNKS = (A_PRE || B_PRE) ? TILE_BYTES / 16 : 2 * TILE_BYTES / 16;
 #pragma unroll
         for (int j = 0; j < CHUNKS / (32 * NUM_CONV_WARPS); ++j) {
-          const int c = ct + j * 32 * NUM_CONV_WARPS;
+          const int c = CHUNK0 + ct + j * 32 * NUM_CONV_WARPS;
           const float4 v = *reinterpret_cast<const float4*>(st + c * 16);
           float4 lo;
           if (SPLIT_RN) {
@@ -371,6 +399,7 @@ gemm_tf32_kernel(const GemmArgs args, const __grid_constant__ CUtensorMap tmA, c
 struct MatView {
   const float* ptr;
   long long rows, cols, ld;
+  const float* lo = nullptr;  // optional pre-split low part (same shape / ld): ptr is then the hi part (raw or pre-rounded)
 };
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

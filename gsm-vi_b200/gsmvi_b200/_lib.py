@@ -37,7 +37,7 @@ def _declare(L):
     L.gsmvi_abi_version.restype = c_i
     L.gsmvi_gemm_tf32.restype = c_i
     L.gsmvi_gemm_tf32.argtypes = [c_p, c_ll, c_ll, c_ll, c_i, c_p, c_ll, c_ll, c_ll, c_i, c_p, c_ll, c_i, c_i, c_i,
-                                  c_f, c_f, c_p, c_ll, c_p, c_i, c_i, c_i, c_i, c_i, c_p]
+                                  c_f, c_f, c_p, c_ll, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]
 
 
 def check(rc, what):
@@ -58,14 +58,14 @@ KR_FULL, KR_A_LOWER, KR_B_LOWER, KR_A_UPPER, KR_B_UPPER = 0, 1, 2, 4, 8
 
 
 def gemm_tf32(A, B, C, M, N, K, a_mn=False, b_mn=False, alpha=1.0, beta=0.0, Cin=None, bias_n=None, npass=3,
-              tri=False, mirror=False, krange=0, neg_from=0x7fffffff):
+              tri=False, mirror=False, krange=0, neg_from=0x7fffffff, A_lo=None, B_lo=None):
     """C[M,N] = alpha * op(A) op(B)^T + beta*Cin + bias_n. A, B, C are 2-D fp32 CUDA tensors (row-major views with
     stride(1) == 1). K-major operand: [rows, K]; MN-major (a_mn/b_mn): [K, rows]."""
     assert A.stride(1) == 1 and B.stride(1) == 1 and C.stride(1) == 1
     rc = lib().gsmvi_gemm_tf32(ptr(A), A.shape[0], A.shape[1], A.stride(0), int(a_mn), ptr(B), B.shape[0], B.shape[1],
                                B.stride(0), int(b_mn), ptr(C), C.stride(0), M, N, K, alpha, beta, ptr(Cin),
                                Cin.stride(0) if Cin is not None else 0, ptr(bias_n), npass, int(tri), int(mirror),
-                               krange, neg_from, stream_ptr())
+                               krange, neg_from, ptr(A_lo), ptr(B_lo), stream_ptr())
     check(rc, "gsmvi_gemm_tf32")
     return C
 
@@ -83,11 +83,14 @@ def _declare_gsm(L):
     L.gsmvi_philox_normal.restype = c_i
     L.gsmvi_philox_normal.argtypes = [c_p, c_ll, c_i, c_i, c_ull, c_ull, c_p]
     L.gsmvi_sample.restype = c_i
-    L.gsmvi_sample.argtypes = [c_p, c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p]
+    L.gsmvi_sample.argtypes = [c_p, c_p, c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p]
+    L.gsmvi_tf32_split.restype = c_i
+    L.gsmvi_tf32_split.argtypes = [c_p, c_ll, c_p, c_p, c_ll, c_i, c_i, c_p]
     L.gsmvi_gauss_score.restype = c_i
-    L.gsmvi_gauss_score.argtypes = [c_p, c_ll, c_p, c_ll, c_p, c_p, c_ll, c_i, c_i, c_i, c_p]
+    L.gsmvi_gauss_score.argtypes = [c_p, c_ll, c_p, c_p, c_ll, c_p, c_p, c_ll, c_i, c_i, c_i, c_p]
     L.gsmvi_gsm_update.restype = c_i
-    L.gsmvi_gsm_update.argtypes = [c_p, c_ll, c_p, c_ll, c_p, c_p, c_ll, c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_p, c_i, c_p]
+    L.gsmvi_gsm_update.argtypes = [c_p, c_ll, c_p, c_ll, c_p, c_p, c_p, c_p, c_ll, c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_p,
+                                   c_i, c_p]
     L.gsmvi_gsm_apply_stats.restype = c_i
     L.gsmvi_gsm_apply_stats.argtypes = [c_p, c_ll, c_p, c_ll, c_p, c_p, c_p, c_ll, c_p, c_i, c_p]
 
@@ -118,20 +121,27 @@ def philox_normal(Z, B, D, seed, offset):
           "gsmvi_philox_normal")
 
 
-def sample(mu, L_, Z, X, B, D, npass=3):
-    check(lib().gsmvi_sample(ptr(mu), ptr(L_), L_.stride(0), ptr(Z), Z.stride(0), ptr(X), X.stride(0), B, D, npass,
-                             stream_ptr()), "gsmvi_sample")
+def tf32_split(A, A_hi, A_lo, rows, cols):
+    """A_hi <- tf32_rn(A), A_lo <- tf32_rn(A - A_hi): pre-split form of a reused GEMM operand (pass hi as the operand)."""
+    assert A_hi.stride(0) == A_lo.stride(0)
+    check(lib().gsmvi_tf32_split(ptr(A), A.stride(0), ptr(A_hi), ptr(A_lo), A_lo.stride(0), rows, cols, stream_ptr()),
+          "gsmvi_tf32_split")
 
 
-def gauss_score(X, P, c, G, B, D, npass=3):
-    check(lib().gsmvi_gauss_score(ptr(X), X.stride(0), ptr(P), P.stride(0), ptr(c), ptr(G), G.stride(0), B, D, npass,
-                                  stream_ptr()), "gsmvi_gauss_score")
+def sample(mu, L_, Z, X, B, D, npass=3, L_lo=None):
+    check(lib().gsmvi_sample(ptr(mu), ptr(L_), ptr(L_lo), L_.stride(0), ptr(Z), Z.stride(0), ptr(X), X.stride(0), B, D,
+                             npass, stream_ptr()), "gsmvi_sample")
 
 
-def gsm_update_raw(X, G, mu, Sigma, mu_out, Sigma_out, B, D, B_total, mode, ws, npass=3):
-    check(lib().gsmvi_gsm_update(ptr(X), X.stride(0), ptr(G), G.stride(0), ptr(mu), ptr(Sigma), Sigma.stride(0),
-                                 ptr(mu_out), ptr(Sigma_out), Sigma_out.stride(0), B, D, B_total, mode, ptr(ws), npass,
-                                 stream_ptr()), "gsmvi_gsm_update")
+def gauss_score(X, P, c, G, B, D, npass=3, P_lo=None):
+    check(lib().gsmvi_gauss_score(ptr(X), X.stride(0), ptr(P), ptr(P_lo), P.stride(0), ptr(c), ptr(G), G.stride(0), B, D,
+                                  npass, stream_ptr()), "gsmvi_gauss_score")
+
+
+def gsm_update_raw(X, G, mu, Sigma, mu_out, Sigma_out, B, D, B_total, mode, ws, npass=3, Sigma_hi=None, Sigma_lo=None):
+    check(lib().gsmvi_gsm_update(ptr(X), X.stride(0), ptr(G), G.stride(0), ptr(mu), ptr(Sigma), ptr(Sigma_hi), ptr(Sigma_lo),
+                                 Sigma.stride(0), ptr(mu_out), ptr(Sigma_out), Sigma_out.stride(0), B, D, B_total, mode,
+                                 ptr(ws), npass, stream_ptr()), "gsmvi_gsm_update")
 
 
 def gsm_apply_stats(Sigma, dSigma, mu, dmu, Sigma_out, mu_out, D):

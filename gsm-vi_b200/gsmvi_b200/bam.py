@@ -119,7 +119,7 @@ class BaMEngine:
         self.draws += 1
         L.sample(self.mu, self.Lb, self.Zb, self.Xb, B, D, npass)
         if self.target is not None:
-            L.gauss_score(self.Xb, self.target.Pb, self.target.c, self.Gb, B, D, npass)
+            L.gauss_score(self.Xb, self.target.Phib, self.target.c, self.Gb, B, D, npass, P_lo=self.target.Plob)
         elif self.score_input == "numpy":
             self.G.copy_(to_dev(self.lp_g(self.X.cpu().numpy()), self.dev))
         else:

@@ -56,6 +56,11 @@ class GSMEngine:
         self.Snb, self.Sn = new_mat(D, D, dev)
         self.Lb, _ = new_mat(D, D, dev)
         self.Lnb, _ = new_mat(D, D, dev)
+        # pre-split low parts of the reused GEMM operands (Sigma for W = G Sigma, L for the sampler), kept per buffer
+        self.Shi, self.Slo = new_mat(D, D, dev)[0], new_mat(D, D, dev)[0]
+        self.Snhi, self.Snlo = new_mat(D, D, dev)[0], new_mat(D, D, dev)[0]
+        self.Lhi, self.Llo = new_mat(D, D, dev)[0], new_mat(D, D, dev)[0]
+        self.Lnhi, self.Lnlo = new_mat(D, D, dev)[0], new_mat(D, D, dev)[0]
         self.mu, self.mun = new_vec(D, dev), new_vec(D, dev)
         if mean is not None:
             self.mu[:D].copy_(to_dev(mean, dev))  # gsm.py:100-101 (default zeros)
@@ -82,12 +87,14 @@ class GSMEngine:
         L.potrf_check(self.Sb, self.Lb, D, self.bad, self.ws_p, npass)
         if int(self.bad.item()) != 0:
             raise ValueError("initial covariance is not positive definite")
+        L.tf32_split(self.Sb, self.Shi, self.Slo, D, D)
+        L.tf32_split(self.Lb, self.Lhi, self.Llo, D, D)
 
     def launches_per_step(self):
         """Kernels of libgsmvi_b200.so launched by one step (bench.py reports it as gpu_launches)."""
         panels = (self.D + 127) // 128
         potrf = 1 + panels + (panels - 1)  # tril copy, panel kernels, SYRK GEMMs
-        upd = 4
+        upd = 4 + 2  # W GEMM, row pass, covariance GEMM, axpy + the two tf32_split launches (Sigma_new, L_new)
         return (0 if self.z_tape is not None else 1) + 1 + (1 if self.target is not None else 0) + upd + potrf + \
             (2 if self.world > 1 else 0)
 
@@ -98,29 +105,34 @@ class GSMEngine:
             self.Z.copy_(self.z_tape[i, self.rank * B:(self.rank + 1) * B], non_blocking=True)
         else:
             L.philox_normal(self.Zb, B, D, self.seed, i * self.world + self.rank)
-        L.sample(self.mu, self.Lb, self.Zb, self.Xb, B, D, npass)
+        L.sample(self.mu, self.Lhi, self.Zb, self.Xb, B, D, npass, L_lo=self.Llo)
         # ---- score (gsm.py:121)
         if self.target is not None:
-            L.gauss_score(self.Xb, self.target.Pb, self.target.c, self.Gb, B, D, npass)
+            L.gauss_score(self.Xb, self.target.Phib, self.target.c, self.Gb, B, D, npass, P_lo=self.target.Plob)
         elif self.score_input == "numpy":
             self.G.copy_(to_dev(self.lp_g(self.X.cpu().numpy()), self.dev))
         else:
             self.G.copy_(to_dev(self.lp_g(self.X), self.dev))
         # ---- update (gsm.py:122)
         if self.world == 1:
-            L.gsm_update_raw(self.Xb, self.Gb, self.mu, self.Sb, self.mun, self.Snb, B, D, B, 0, self.ws_u, npass)
+            L.gsm_update_raw(self.Xb, self.Gb, self.mu, self.Sb, self.mun, self.Snb, B, D, B, 0, self.ws_u, npass,
+                             Sigma_hi=self.Shi, Sigma_lo=self.Slo)
         else:
             L.gsm_update_raw(self.Xb, self.Gb, self.mu, self.Sb, self.dmu, self.dSb, B, D, self.batch_size, 1,
-                             self.ws_u, npass)
+                             self.ws_u, npass, Sigma_hi=self.Shi, Sigma_lo=self.Slo)
             self.dist.all_reduce(self.dSb, group=self.group)
             self.dist.all_reduce(self.dmu, group=self.group)
             L.gsm_apply_stats(self.Sb, self.dSb, self.mu, self.dmu, self.Snb, self.mun, D)
         # ---- goodness check = Cholesky of the new covariance, reused as the next sampling factor (gsm.py:125)
         L.potrf_check(self.Snb, self.Lnb, D, self.bad, self.ws_p, npass)
+        L.tf32_split(self.Snb, self.Snhi, self.Snlo, D, D)  # queued before the flag is read: overlap the host round trip
+        L.tf32_split(self.Lnb, self.Lnhi, self.Lnlo, D, D)
         ok = int(self.bad.item()) == 0  # the step's only device->host read (4 bytes)
         if ok:  # gsm.py:126-127
             self.Sb, self.Snb, self.S, self.Sn = self.Snb, self.Sb, self.Sn, self.S
             self.Lb, self.Lnb = self.Lnb, self.Lb
+            self.Shi, self.Snhi, self.Slo, self.Snlo = self.Snhi, self.Shi, self.Snlo, self.Slo
+            self.Lhi, self.Lnhi, self.Llo, self.Lnlo = self.Lnhi, self.Lhi, self.Lnlo, self.Llo
             self.mu, self.mun = self.mun, self.mu
         else:
             self.n_reverts += 1

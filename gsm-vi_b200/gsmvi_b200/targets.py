@@ -22,6 +22,9 @@ class DenseGaussianTarget:
         self.mean64, self.cov64, self.P64 = mean, cov, P
         self.Pb, self.P = new_mat(self.D, self.D, dev)
         self.P.copy_(torch.as_tensor(P, dtype=torch.float32))
+        self.Phib, _ = new_mat(self.D, self.D, dev)  # pre-split (hi, lo) form of P for the score GEMM
+        self.Plob, _ = new_mat(self.D, self.D, dev)
+        L.tf32_split(self.Pb, self.Phib, self.Plob, self.D, self.D)
         self.c = new_vec(self.D, dev)
         self.c[: self.D].copy_(torch.as_tensor(P @ mean, dtype=torch.float32))
         self.m = torch.as_tensor(mean, dtype=torch.float32, device=dev)
@@ -33,7 +36,7 @@ class DenseGaussianTarget:
         Xb, X = new_mat(B, self.D, x.device)
         X.copy_(x)
         Gb, G = new_mat(B, self.D, x.device)
-        L.gauss_score(Xb, self.Pb, self.c, Gb, B, self.D)
+        L.gauss_score(Xb, self.Phib, self.c, Gb, B, self.D, P_lo=self.Plob)
         return G
 
     def lp(self, x):

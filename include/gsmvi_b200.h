@@ -37,11 +37,12 @@ int gsmvi_abi_version(void);
 long long gsmvi_workspace_bytes(int kind, int B, int D);
 
 /* General tensor-core contraction C[M,N] = alpha * op(A) op(B)^T + beta * Cin + bias_n (diagnostics and tests; the
- * engine under every call below).  a_mn/b_mn: operand stored [K, rows] instead of [rows, K]. */
+ * engine under every call below).  a_mn/b_mn: operand stored [K, rows] instead of [rows, K].  A_lo / B_lo: optional
+ * pre-split low parts (see gsmvi_tf32_split; B_lo alone, or both; the operand itself is then the hi part). */
 int gsmvi_gemm_tf32(const float* A, long long a_rows, long long a_cols, long long lda, int a_mn, const float* B,
                     long long b_rows, long long b_cols, long long ldb, int b_mn, float* C, long long ldc, int M, int N,
                     int K, float alpha, float beta, const float* Cin, long long ldcin, const float* bias_n, int npass,
-                    int tri, int mirror, int krange, int neg_from, void* stream);
+                    int tri, int mirror, int krange, int neg_from, const float* A_lo, const float* B_lo, void* stream);
 
 /* L <- chol(Sigma) (lower, upper triangle zeroed), *bad_flag <- 0 if Sigma is positive definite else 1.
  * Replaces GSM._check_goodness / BaM._check_goodness (gsmvi/gsm.py:136-150, gsmvi/bam.py:219-233: host
@@ -54,24 +55,32 @@ int gsmvi_potrf_check(const float* Sigma, long long lds, float* L, long long ldl
 int gsmvi_philox_normal(float* Z, long long ldz, int B, int D, unsigned long long seed, unsigned long long offset,
                         void* stream);
 
+/* A_hi = tf32_rn(A), A_lo = tf32_rn(A - A_hi): the round-to-nearest 3xTF32 split of a reused operand, done once.
+ * The calls below take an optional X_lo beside an operand X (same shape and leading dimension, NULL = none): when it is
+ * given, X must be the matching hi part and TMA loads hi and lo tiles directly instead of splitting inside the GEMM. */
+int gsmvi_tf32_split(const float* A, long long lda, float* A_hi, float* A_lo, long long ldo, int rows, int cols,
+                     void* stream);
+
 /* X[B,D] = mu + Z L^T : samples of N(mu, L L^T).  Replaces np.random.multivariate_normal (gsmvi/gsm.py:119,
  * gsmvi/bam.py:193, gsmvi/monitors.py:106). */
-int gsmvi_sample(const float* mu, const float* L, long long ldl, const float* Z, long long ldz, float* X,
-                 long long ldx, int B, int D, int npass, void* stream);
+int gsmvi_sample(const float* mu, const float* L, const float* L_lo, long long ldl, const float* Z, long long ldz,
+                 float* X, long long ldx, int B, int D, int npass, void* stream);
 
 /* G[B,D] = -(X - m) P = -X P + c with c = P m: batched score of a dense Gaussian target.  Replaces lp_g of the
  * benchmark targets (examples/example_gsm_numpy.py:24-29, examples/example_gsm.py:34-35). */
-int gsmvi_gauss_score(const float* X, long long ldx, const float* P, long long ldp, const float* c, float* G,
-                      long long ldg, int B, int D, int npass, void* stream);
+int gsmvi_gauss_score(const float* X, long long ldx, const float* P, const float* P_lo, long long ldp, const float* c,
+                      float* G, long long ldg, int B, int D, int npass, void* stream);
 
 /* Fused GSM batch update.  Replaces gsm_update (gsmvi/gsm.py:31-58; _gsm_update_single gsmvi/gsm.py:8-28).
  * mode 0: mu_out = mu + mean_b u_b, Sigma_out = Sigma + (D^T D - E^T E)/B_total (B_total == B).
  * mode 1: partial statistics of a batch shard: mu_out = sum_b u_b / B_total, Sigma_out = (D^T D - E^T E)/B_total,
  *         to be summed over shards (all-reduce) and applied with gsmvi_gsm_apply_stats.
+ * Sigma_hi / Sigma_lo: optional gsmvi_tf32_split of Sigma (both or neither; same leading dimension) for W = G Sigma.
  * workspace: gsmvi_workspace_bytes(GSMVI_WS_GSM_UPDATE, B, D). Sigma_out must not alias Sigma. */
 int gsmvi_gsm_update(const float* X, long long ldx, const float* G, long long ldg, const float* mu,
-                     const float* Sigma, long long lds, float* mu_out, float* Sigma_out, long long ldso, int B, int D,
-                     int B_total, int mode, void* workspace, int npass, void* stream);
+                     const float* Sigma, const float* Sigma_hi, const float* Sigma_lo, long long lds, float* mu_out,
+                     float* Sigma_out, long long ldso, int B, int D, int B_total, int mode, void* workspace, int npass,
+                     void* stream);
 
 /* Sigma_out = Sigma + dSigma, mu_out = mu + dmu (after the all-reduce of mode-1 statistics). */
 int gsmvi_gsm_apply_stats(const float* Sigma, long long lds, const float* dSigma, long long ldd, const float* mu,

@@ -31,7 +31,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.gsmvi_abi_version() == 1
     # pure host queries are safe without a GPU
     assert lib.gsmvi_workspace_bytes(_lib.WS_POTRF, 0, 4096) == 128 * 128 * 4
-    assert lib.gsmvi_workspace_bytes(_lib.WS_GSM_UPDATE, 4096, 4096) == (4 * 4096 + 1) * 4096 * 4
+    assert lib.gsmvi_workspace_bytes(_lib.WS_GSM_UPDATE, 4096, 4096) == (7 * 4096 + 1) * 4096 * 4
     assert lib.gsmvi_workspace_bytes(99, 1, 1) == -1
 
 
@@ -39,7 +39,8 @@ def test_header_cites_reference_for_each_hot_path_entry():
     with open(os.path.join(ROOT, "include", "gsmvi_b200.h")) as f:
         src = f.read()
     for name in ("gsmvi_potrf_check", "gsmvi_sample", "gsmvi_gauss_score", "gsmvi_gsm_update", "gsmvi_bam_stats",
-                 "gsmvi_bam_solve", "gsmvi_bam_solve_lowrank", "gsmvi_gauss_logq_reduce", "gsmvi_philox_normal"):
+                 "gsmvi_bam_solve", "gsmvi_bam_solve_lowrank", "gsmvi_gauss_logq_reduce", "gsmvi_philox_normal",
+                 "gsmvi_gsm_ensemble_fit"):
         decl = src.index("int " + name + "(")
         comment = src[src.rindex("/*", 0, decl):decl]
         assert re.search(r"(gsmvi/(gsm|bam|monitors)|examples/example_\w+)\.py:\d+", comment), name

@@ -148,6 +148,39 @@ elif group == "epi":
     out["subview_upper_untouched"] = float((torch.triu(Cv - before, 1)).abs().max())
     for k, v in out.items():
         print("%-28s %s" % (k, v), flush=True)
+elif group == "presplit":
+    from gsmvi_b200._util import new_mat
+    M, N, K = 384, 512, 1024
+    g = torch.Generator().manual_seed(7)
+    A = torch.randn(M, K, generator=g).to(dev); B = torch.randn(N, K, generator=g).to(dev)
+    ref = A.double() @ B.double().t()
+    C = torch.empty(M, N, device=dev)
+    Bhi = torch.empty_like(B); Blo = torch.empty_like(B); L.tf32_split(B, Bhi, Blo, N, K)
+    L.gemm_tf32(A, Bhi, C, M, N, K, B_lo=Blo)
+    out["presplit_B"] = relerr(C, ref)
+    L.gemm_tf32(A, B, C, M, N, K)
+    out["no_presplit"] = relerr(C, ref)
+    # both pre-split with the round-to-nearest split (as the row pass writes T_hi / T_lo), MN-major
+    At, Bt = A.t().contiguous(), B.t().contiguous()
+    def rn_split(x):
+        hi = (x.view(torch.int32) + 0x1000 & ~0x1FFF).view(torch.float32)
+        lo = x - hi
+        lo = ((lo.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+        return hi.contiguous(), lo.contiguous()
+    Ahi, Alo = rn_split(At); Bhi, Blo2 = rn_split(Bt)
+    L.gemm_tf32(Ahi, Bhi, C, M, N, K, a_mn=True, b_mn=True, A_lo=Alo, B_lo=Blo2)
+    out["presplit_both_mn"] = relerr(C, ref)
+    for k, v in out.items():
+        print("%-20s %.3e" % (k, v), flush=True)
+    n = 4096
+    A = torch.randn(n, n, device=dev); B = torch.randn(n, n, device=dev); C = torch.empty(n, n, device=dev)
+    Bhi = torch.empty_like(B); Blo = torch.empty_like(B); L.tf32_split(B, Bhi, Blo, n, n)
+    Ahi = torch.empty_like(A); Alo = torch.empty_like(A); L.tf32_split(A, Ahi, Alo, n, n)
+    fl = 2.0 * n**3
+    for name, (a_, b_, kw) in [("none", (A, B, {})), ("B", (A, Bhi, {"B_lo": Blo})), ("both", (Ahi, Bhi, {"A_lo": Alo, "B_lo": Blo}))]:
+        ms = timeit(lambda: L.gemm_tf32(a_, b_, C, n, n, n, **kw))
+        out["perf_presplit_%s_4096" % name] = {"ms": ms, "tflops_alg": fl / ms / 1e9}
+        print("presplit=%s 4096^3: %.3f ms %.1f TF/s algorithmic (%.1f executed)" % (name, ms, fl / ms / 1e9, 3 * fl / ms / 1e9), flush=True)
 elif group == "perf":
     for n in (2048, 4096, 8192):
         A = torch.randn(n, n, device=dev)

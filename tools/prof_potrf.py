@@ -3,7 +3,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "gsm-vi_b200"))
 import torch
 from gsmvi_b200 import _lib as L
-D = 1024
+D = 4096
 g = torch.Generator().manual_seed(0)
 A = torch.randn(D, D, generator=g).cuda(); S = A @ A.t() / D + 0.1 * torch.eye(D, device="cuda")
 Lo = torch.empty(D, D, device="cuda"); bad = torch.zeros(1, dtype=torch.int32, device="cuda")

@@ -5,6 +5,7 @@
 #include "dgemm.cuh"
 #include "gsm_ensemble.cuh"
 #include "gsm_kernels.cuh"
+#include "h3_gemm.cuh"
 #include "monitor.cuh"
 #include "potrf.cuh"
 #include "tc_gemm.cuh"
@@ -21,6 +22,7 @@ long long gsmvi_workspace_bytes(int kind, int B, int D) {
   switch (kind) {
     case GSMVI_WS_POTRF: return static_cast<long long>(potrf_workspace_bytes(D));
     case GSMVI_WS_GSM_UPDATE: return static_cast<long long>(gsm_update_workspace_bytes(B, D));
+    case GSMVI_WS_GSM_UPDATE_H3: return static_cast<long long>(gsm_update_h3_workspace_bytes(B, D));
     case GSMVI_WS_BAM_STATS: return static_cast<long long>(bam_stats_workspace_bytes(B, D));
     case GSMVI_WS_BAM_SOLVE: return static_cast<long long>(bam_solve_workspace_bytes(B, D, 0));
     case GSMVI_WS_BAM_SOLVE_LOWRANK: return static_cast<long long>(bam_solve_workspace_bytes(B, D, 1));
@@ -47,6 +49,67 @@ int gsmvi_gemm_tf32(const float* A, long long a_rows, long long a_cols, long lon
   o.neg_from = neg_from;
   MatView a{A, a_rows, a_cols, lda, A_lo}, b{B, b_rows, b_cols, ldb, B_lo};
   return launch_gemm_tf32(S(stream), M, N, K, a, b, C, ldc, o);
+}
+
+int gsmvi_gemm_h3(const void* A_hi, const void* A_lo, const float* scale_a, long long a_rows, long long a_cols, long long lda,
+                  int a_mn, const void* B_hi, const void* B_lo, const float* scale_b, long long b_rows, long long b_cols,
+                  long long ldb, int b_mn, float* C, long long ldc, int M, int N, int K, float alpha, float beta,
+                  const float* Cin, long long ldcin, const float* bias_n, int tri, int mirror, int krange,
+                  unsigned* absmax_out, int splits, long long split_stride, void* stream) {
+  H3Opts o;
+  o.a_mn = a_mn != 0;
+  o.b_mn = b_mn != 0;
+  o.alpha = alpha;
+  o.beta = beta;
+  o.Cin = Cin;
+  o.ldcin = ldcin;
+  o.bias_n = bias_n;
+  o.tri = tri != 0;
+  o.mirror = mirror != 0;
+  o.krange = krange;
+  o.absmax_out = absmax_out;
+  o.splits = splits;
+  o.split_stride = split_stride;
+  HView a{static_cast<const __half*>(A_hi), static_cast<const __half*>(A_lo), a_rows, a_cols, lda, scale_a};
+  HView b{static_cast<const __half*>(B_hi), static_cast<const __half*>(B_lo), b_rows, b_cols, ldb, scale_b};
+  return launch_gemm_h3(S(stream), M, N, K, a, b, C, ldc, o);
+}
+
+int gsmvi_h3_absmax(const float* A, long long lda, int rows, int cols, unsigned* absmax, void* stream) {
+  return h3_absmax(S(stream), A, lda, rows, cols, absmax);
+}
+
+int gsmvi_h3_split(const float* A, long long lda, int rows, int cols, const unsigned* absmax, int sqrt_mode,
+                   float* scale_out, void* A_hi, void* A_lo, long long ldo, void* stream) {
+  return h3_split(S(stream), A, lda, rows, cols, absmax, sqrt_mode, scale_out, static_cast<__half*>(A_hi),
+                  static_cast<__half*>(A_lo), ldo);
+}
+
+int gsmvi_philox_normal_h3(const gsmvi_h3_operand* Z, int B, int D, unsigned long long seed, unsigned long long offset,
+                           void* stream) {
+  if (!Z) return GSMVI_EINVAL;
+  return philox_normal_h3(S(stream), *Z, B, D, seed, offset);
+}
+
+int gsmvi_sample_h3(const float* mu, const gsmvi_h3_operand* L, const gsmvi_h3_operand* Z, float* X, long long ldx,
+                    unsigned* absmax_x, int B, int D, void* stream) {
+  if (!mu || !L || !Z || !X || B <= 0 || D <= 0) return GSMVI_EINVAL;
+  return sample_mvn_h3(S(stream), mu, *L, *Z, X, ldx, absmax_x, B, D);
+}
+
+int gsmvi_gauss_score_h3(const gsmvi_h3_operand* X, const gsmvi_h3_operand* P, const float* c, float* G, long long ldg,
+                         unsigned* absmax_g, int B, int D, void* stream) {
+  if (!X || !P || !c || !G || B <= 0 || D <= 0) return GSMVI_EINVAL;
+  return gauss_score_h3(S(stream), *X, *P, c, G, ldg, absmax_g, B, D);
+}
+
+int gsmvi_gsm_update_h3(const float* X, long long ldx, const float* G, long long ldg, const gsmvi_h3_operand* G_split,
+                        const float* mu, const float* Sigma, long long lds, const gsmvi_h3_operand* Sigma_split,
+                        float* mu_out, float* Sigma_out, long long ldso, unsigned* absmax_sout, int B, int D, int B_total,
+                        int mode, void* workspace, void* stream) {
+  if (!G_split || !Sigma_split) return GSMVI_EINVAL;
+  return gsm_update_h3(S(stream), X, ldx, G, ldg, *G_split, mu, Sigma, lds, *Sigma_split, mu_out, Sigma_out, ldso,
+                       absmax_sout, B, D, B_total, mode, workspace);
 }
 
 int gsmvi_potrf_check(const float* Sigma, long long lds, float* L, long long ldl, int D, int* bad_flag,

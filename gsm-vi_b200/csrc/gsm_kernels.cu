@@ -12,6 +12,7 @@
 // Three launches: W = G Sigma0 (tensor-core GEMM), the row pass below (HBM-bound, 24 B D bytes), and that GEMM
 // with the "+ Sigma0" and -1/B fused in its epilogue (lower tiles only, mirrored stores).
 #include "gsm_kernels.cuh"
+#include "h3_gemm.cuh"
 
 #include <math.h>
 
@@ -42,6 +43,11 @@ __device__ __forceinline__ void store_split4(float* hi, float* lo, const float4 
   *reinterpret_cast<float4*>(lo) = l;
 }
 
+__device__ __forceinline__ unsigned max4_bits(const float4 v) {
+  return max(max(__float_as_uint(fabsf(v.x)), __float_as_uint(fabsf(v.y))),
+             max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w))));
+}
+
 // hi = tf32_rn(a), lo = tf32_rn(a - hi): the round-to-nearest 3xTF32 split of a reused GEMM operand, done once
 __global__ void tf32_split_kernel(const float* __restrict__ A, long long lda, float* __restrict__ Hi, float* __restrict__ Lo,
                                   long long ldo, int rows, int cols) {
@@ -58,18 +64,22 @@ __global__ void tf32_split_kernel(const float* __restrict__ A, long long lda, fl
 
 // One CTA handles RP_ROWS consecutive samples.  Pass 1 (a warp per row): the two dot products and the per-sample
 // scalars.  Pass 2 (a thread per 4 columns): rows e, u, d of T = [E; U; D] and the column sums of u.
+template <int MODE>
 __global__ void __launch_bounds__(RP_THREADS) gsm_rowpass_kernel(const float* __restrict__ X, long long ldx,
                                                                  const float* __restrict__ G, long long ldg,
                                                                  const float* __restrict__ W, long long ldw,
                                                                  const float* __restrict__ mu, float* __restrict__ T,
                                                                  float* __restrict__ Tlo, long long ldt,
-                                                                 float* __restrict__ usum, int B, int D) {
+                                                                 float* __restrict__ usum, int B, int D,
+                                                                 unsigned* __restrict__ absmax) {
   __shared__ float s_alpha[RP_ROWS], s_beta[RP_ROWS];
+  unsigned amax = 0u;  // MODE 1: bit pattern of max |e|, |u|, |d| (as unsigned, NaN > Inf > finite)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * RP_ROWS;
   const bool vec = ((D & 3) == 0) && ((ldx & 3) == 0) && ((ldg & 3) == 0) && ((ldw & 3) == 0) && ((ldt & 3) == 0) &&
                    (((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(W) |
-                      reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(Tlo) | reinterpret_cast<uintptr_t>(mu)) & 15) == 0);
+                      reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(mu)) & 15) == 0) &&
+                   (MODE == 1 || (reinterpret_cast<uintptr_t>(Tlo) & 15) == 0);
   for (int r = warp; r < RP_ROWS; r += RP_THREADS / 32) {
     const int b = row0 + r;
     if (b >= B) break;
@@ -118,9 +128,18 @@ __global__ void __launch_bounds__(RP_THREADS) gsm_rowpass_kernel(const float* __
         u.x = al * wv.x + be * d.x; u.y = al * wv.y + be * d.y; u.z = al * wv.z + be * d.z; u.w = al * wv.w + be * d.w;
         e.x = d.x + u.x; e.y = d.y + u.y; e.z = d.z + u.z; e.w = d.w + u.w;
         acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
-        store_split4(T + b * ldt + j, Tlo + b * ldt + j, e);
-        store_split4(T + (b + B) * ldt + j, Tlo + (b + B) * ldt + j, u);
-        store_split4(T + (b + 2LL * B) * ldt + j, Tlo + (b + 2LL * B) * ldt + j, d);
+        if (MODE == 0) {
+          store_split4(T + b * ldt + j, Tlo + b * ldt + j, e);
+          store_split4(T + (b + B) * ldt + j, Tlo + (b + B) * ldt + j, u);
+          store_split4(T + (b + 2LL * B) * ldt + j, Tlo + (b + 2LL * B) * ldt + j, d);
+        } else {
+          *reinterpret_cast<float4*>(T + b * ldt + j) = e;
+          *reinterpret_cast<float4*>(T + (b + B) * ldt + j) = u;
+          *reinterpret_cast<float4*>(T + (b + 2LL * B) * ldt + j) = d;
+          amax = max(amax, max4_bits(e));
+          amax = max(amax, max4_bits(u));
+          amax = max(amax, max4_bits(d));
+        }
       }
       atomicAdd(usum + j + 0, acc.x);
       atomicAdd(usum + j + 1, acc.y);
@@ -136,12 +155,23 @@ __global__ void __launch_bounds__(RP_THREADS) gsm_rowpass_kernel(const float* __
         const float d = m - X[b * ldx + j];
         const float u = s_alpha[r] * W[b * ldw + j] + s_beta[r] * d;
         acc += u;
-        store_split1(T + b * ldt + j, Tlo + b * ldt + j, d + u);
-        store_split1(T + (b + B) * ldt + j, Tlo + (b + B) * ldt + j, u);
-        store_split1(T + (b + 2LL * B) * ldt + j, Tlo + (b + 2LL * B) * ldt + j, d);
+        if (MODE == 0) {
+          store_split1(T + b * ldt + j, Tlo + b * ldt + j, d + u);
+          store_split1(T + (b + B) * ldt + j, Tlo + (b + B) * ldt + j, u);
+          store_split1(T + (b + 2LL * B) * ldt + j, Tlo + (b + 2LL * B) * ldt + j, d);
+        } else {
+          T[b * ldt + j] = d + u;
+          T[(b + B) * ldt + j] = u;
+          T[(b + 2LL * B) * ldt + j] = d;
+          amax = max(amax, max(__float_as_uint(fabsf(d + u)), max(__float_as_uint(fabsf(u)), __float_as_uint(fabsf(d)))));
+        }
       }
       atomicAdd(usum + j, acc);
     }
+  }
+  if (MODE == 1) {
+    amax = __reduce_max_sync(0xffffffffu, amax);
+    if (lane == 0 && amax != 0u) atomicMax(absmax, amax);
   }
 }
 
@@ -273,7 +303,7 @@ int gsm_update(cudaStream_t stream, const float* X, long long ldx, const float* 
     if (rc != GSMVI_OK) return rc;
   }
   // (ii) row pass
-  gsm_rowpass_kernel<<<(B + RP_ROWS - 1) / RP_ROWS, RP_THREADS, 0, stream>>>(X, ldx, G, ldg, W, ldw, mu, T, Tlo, ldw, usum, B, D);
+  gsm_rowpass_kernel<0><<<(B + RP_ROWS - 1) / RP_ROWS, RP_THREADS, 0, stream>>>(X, ldx, G, ldg, W, ldw, mu, T, Tlo, ldw, usum, B, D, nullptr);
   e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   // (iii) Sigma_out = [Sigma0] - (E^T U + U^T D) / B_total : rows of T are K, so both operands are MN-major views
@@ -306,6 +336,142 @@ int gsm_apply_stats(cudaStream_t stream, const float* Sigma, long long lds, cons
   mat_add_kernel<<<dim3((D + 255) / 256, D), 256, 0, stream>>>(Sigma, lds, dSigma, ldd, Sigma_out, ldso, D);
   vec_axpy_kernel<<<(D + 255) / 256, 256, 0, stream>>>(mu, dmu, 1.0f, mu_out, D);
   cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
+}
+
+
+// ================================================================================================ scaled 3xFP16 path
+// The same iteration on the h3 engine (h3_gemm.cuh): every GEMM operand is an fp16 (hi, lo) pair with a power-of-two
+// scale.  Producers record max |value| through their epilogue (one atomicMax per warp) and a split pass turns the fp32
+// result into the next GEMM's operand; Philox draws are written split directly (|z| < 2^3 by construction).
+
+// Philox4x32-10 normals written as the fp16 pair with the fixed scale 2^11 (|z| <= sqrt(-2 ln 2^-25) = 5.9 < 2^3).
+constexpr float Z_H3_SCALE = 2048.0f;
+__global__ void philox_normal_h3_kernel(__half* __restrict__ Zhi, __half* __restrict__ Zlo, long long ldz, int B, int D,
+                                        unsigned long long seed, unsigned long long offset, float* __restrict__ scale_out) {
+  const int groups_per_row = (D + 3) / 4;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid == 0) *scale_out = Z_H3_SCALE;
+  if (gid >= static_cast<long long>(B) * groups_per_row) return;
+  const int b = static_cast<int>(gid / groups_per_row);
+  const int j = static_cast<int>(gid % groups_per_row) * 4;
+  uint32_t c[4] = {static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), static_cast<uint32_t>(offset),
+                   static_cast<uint32_t>(offset >> 32)};
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const float u0 = (static_cast<float>(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u1 = (static_cast<float>(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = (static_cast<float>(c[2] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u3 = (static_cast<float>(c[3] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+  float s0, c0, s1, c1;
+  sincospif(2.0f * u1, &s0, &c0);
+  sincospif(2.0f * u3, &s1, &c1);
+  const float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+  __half h[4], l[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) h3_split1(z[t], Z_H3_SCALE, h[t], l[t]);
+  __half* hrow = Zhi + static_cast<long long>(b) * ldz;
+  __half* lrow = Zlo + static_cast<long long>(b) * ldz;
+  if (j + 3 < D && (ldz & 3) == 0) {
+    *reinterpret_cast<uint2*>(hrow + j) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(lrow + j) = *reinterpret_cast<const uint2*>(l);
+  } else {
+    for (int t = 0; t < 4 && j + t < D; ++t) { hrow[j + t] = h[t]; lrow[j + t] = l[t]; }
+  }
+}
+
+int philox_normal_h3(cudaStream_t stream, const H3Operand& Z, int B, int D, unsigned long long seed,
+                     unsigned long long offset) {
+  if (!Z.hi || !Z.lo || !Z.scale || B <= 0 || D <= 0 || Z.ld < D) return GSMVI_EINVAL;
+  const long long n = static_cast<long long>(B) * ((D + 3) / 4);
+  philox_normal_h3_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+      static_cast<__half*>(Z.hi), static_cast<__half*>(Z.lo), Z.ld, B, D, seed, offset, Z.scale);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
+}
+
+static inline HView hview(const H3Operand& o, long long rows, long long cols) {
+  return HView{static_cast<const __half*>(o.hi), static_cast<const __half*>(o.lo), rows, cols, o.ld, o.scale};
+}
+
+int sample_mvn_h3(cudaStream_t stream, const float* mu, const H3Operand& L, const H3Operand& Z, float* X, long long ldx,
+                  unsigned* absmax_x, int B, int D) {
+  // X[b,i] = mu[i] + sum_{k<=i} Z[b,k] L[i,k]
+  H3Opts o;
+  o.bias_n = mu;
+  o.krange = KR_B_LOWER;
+  o.absmax_out = absmax_x;
+  return launch_gemm_h3(stream, B, D, D, hview(Z, B, D), hview(L, D, D), X, ldx, o);
+}
+
+int gauss_score_h3(cudaStream_t stream, const H3Operand& X, const H3Operand& P, const float* c, float* G, long long ldg,
+                   unsigned* absmax_g, int B, int D) {
+  // G = -X P + c,  c = P m   (P symmetric: P[n,k] read K-major as-is)
+  H3Opts o;
+  o.alpha = -1.0f;
+  o.bias_n = c;
+  o.absmax_out = absmax_g;
+  return launch_gemm_h3(stream, B, D, D, hview(X, B, D), hview(P, D, D), G, ldg, o);
+}
+
+size_t gsm_update_h3_workspace_bytes(int B, int D) {
+  const long long ldw = round_up(D, 32);
+  // W [B x ldw] fp32 + T = [E; U; D] [3B x ldw] fp32 + usum [ldw] fp32 + 32 floats of scalars + T_hi, T_lo [3B x ldw] fp16
+  return static_cast<size_t>((4LL * B + 1) * ldw + 32) * sizeof(float) + static_cast<size_t>(6LL * B * ldw) * sizeof(__half);
+}
+
+int gsm_update_h3(cudaStream_t stream, const float* X, long long ldx, const float* G, long long ldg, const H3Operand& Gh,
+                  const float* mu, const float* Sigma, long long lds, const H3Operand& Sh, float* mu_out, float* Sigma_out,
+                  long long ldso, unsigned* absmax_sout, int B, int D, int B_total, int mode, void* workspace) {
+  if (!X || !G || !mu || !Sigma || !mu_out || !Sigma_out || !workspace || B <= 0 || D <= 0 || B_total < B)
+    return GSMVI_EINVAL;
+  const long long ldw = round_up(D, 32);
+  float* W = static_cast<float*>(workspace);
+  float* T = W + static_cast<long long>(B) * ldw;
+  float* usum = T + 3LL * B * ldw;
+  float* scal = usum + ldw;  // [0] = |T| max (bit pattern), [1] = T scale
+  __half* Thi = reinterpret_cast<__half*>(scal + 32);
+  __half* Tlo = Thi + 3LL * B * ldw;
+  cudaError_t e = cudaMemsetAsync(usum, 0, (ldw + 32) * sizeof(float), stream);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  int rc;
+  // (i) W = G Sigma0   (Sigma0 symmetric)
+  {
+    H3Opts o;
+    if ((rc = launch_gemm_h3(stream, B, D, D, hview(Gh, B, D), hview(Sh, D, D), W, ldw, o)) != GSMVI_OK) return rc;
+  }
+  // (ii) row pass -> T = [E; U; D] (fp32), |T| max, column sums of U; then the fp16 split of T
+  gsm_rowpass_kernel<1><<<(B + RP_ROWS - 1) / RP_ROWS, RP_THREADS, 0, stream>>>(X, ldx, G, ldg, W, ldw, mu, T, nullptr, ldw,
+                                                                                usum, B, D, reinterpret_cast<unsigned*>(scal));
+  if ((e = cudaGetLastError()) != cudaSuccess) return static_cast<int>(e);
+  if ((rc = h3_split(stream, T, ldw, 3 * B, D, reinterpret_cast<const unsigned*>(scal), 0, scal + 1, Thi, Tlo, ldw)) != GSMVI_OK)
+    return rc;
+  // (iii) Sigma_out = [Sigma0] - (E^T U + U^T D) / B_total : rows of T are K, so both operands are MN-major views
+  {
+    H3Opts o;
+    o.a_mn = o.b_mn = true;
+    o.alpha = -1.0f / static_cast<float>(B_total);
+    o.tri = true;
+    o.mirror = true;
+    o.absmax_out = absmax_sout;
+    if (mode == 0) {
+      o.beta = 1.0f;
+      o.Cin = Sigma;
+      o.ldcin = lds;
+    }
+    HView va{Thi, Tlo, 2LL * B, D, ldw, scal + 1};
+    HView vb{Thi + static_cast<long long>(B) * ldw, Tlo + static_cast<long long>(B) * ldw, 2LL * B, D, ldw, scal + 1};
+    if ((rc = launch_gemm_h3(stream, D, D, 2 * B, va, vb, Sigma_out, ldso, o)) != GSMVI_OK) return rc;
+  }
+  vec_axpy_kernel<<<(D + 255) / 256, 256, 0, stream>>>(mode == 0 ? mu : nullptr, usum, 1.0f / static_cast<float>(B_total),
+                                                      mu_out, D);
+  e = cudaGetLastError();
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
 }
 

@@ -1,0 +1,159 @@
+// Host side of the scaled 3xFP16 GEMM (h3_gemm.cuh): fp16 tensor maps, dispatch, and the operand split kernels.
+#include "h3_gemm.cuh"
+
+namespace gsmvi {
+
+static int make_tmap_h(CUtensorMap* out, const __half* ptr, long long rows, long long cols, long long ld, int box_cols,
+                       int box_rows) {
+  static PFN_tmapEncodeTiled enc = nullptr;
+  if (!enc) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return GSMVI_EDRIVER;
+    enc = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  if (rows <= 0 || cols <= 0) return GSMVI_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld & 7) != 0 || ld < cols) return GSMVI_EALIGN;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(__half)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? GSMVI_OK : GSMVI_EDRIVER;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_h3_one(cudaStream_t stream, const H3Args& args, const CUtensorMap& tah, const CUtensorMap& tbh,
+                         const CUtensorMap& tal, const CUtensorMap& tbl, dim3 grid) {
+  static bool attr_set = false;
+  auto kern = gemm_h3_kernel<A_MN, B_MN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  kern<<<grid, H3_THREADS, H3_SMEM_BYTES, stream>>>(args, tah, tbh, tal, tbl);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
+}
+
+int launch_gemm_h3(cudaStream_t stream, int M, int N, int K, const HView& A, const HView& B, float* C, long long ldc,
+                   const H3Opts& o) {
+  if (M <= 0 || N <= 0 || K <= 0 || !C || !A.hi || !A.lo || !B.hi || !B.lo || !A.scale || !B.scale) return GSMVI_EINVAL;
+  if (o.tri && M != N) return GSMVI_EINVAL;
+  if (o.beta != 0.0f && !o.Cin) return GSMVI_EINVAL;
+  if (o.splits < 1 || (o.splits > 1 && (o.beta != 0.0f || o.bias_n || o.mirror))) return GSMVI_EINVAL;
+  H3Args a;
+  a.M = M; a.N = N; a.K = K;
+  a.alpha = o.alpha; a.beta = o.beta;
+  a.Cin = o.Cin; a.ldcin = o.ldcin;
+  a.C = C; a.ldc = ldc;
+  a.bias_n = o.bias_n;
+  a.scale_a = A.scale; a.scale_b = B.scale;
+  a.absmax_out = o.absmax_out;
+  a.tri = o.tri ? 1 : 0;
+  a.mirror = o.mirror ? 1 : 0;
+  a.krange = o.krange;
+  a.tiles_m = (M + H3_BM - 1) / H3_BM;
+  a.tiles_n = (N + H3_BN - 1) / H3_BN;
+  a.splits = o.splits;
+  a.split_stride = o.split_stride;
+  const int tiles = o.tri ? a.tiles_m * (a.tiles_m + 1) / 2 : a.tiles_m * a.tiles_n;
+  const dim3 grid(tiles, o.splits);
+
+  CUtensorMap tah, tbh, tal, tbl;
+  int rc;
+  // K-major: box = 64 K-elements (128 B) x 128 rows.  MN-major: box = 64 MN-elements (128 B) x 64 K-rows, two per tile.
+  const int abc = 64, abr = o.a_mn ? H3_BK : H3_BM, bbr = o.b_mn ? H3_BK : H3_BN;
+  if ((rc = make_tmap_h(&tah, A.hi, A.rows, A.cols, A.ld, abc, abr)) != GSMVI_OK) return rc;
+  if ((rc = make_tmap_h(&tal, A.lo, A.rows, A.cols, A.ld, abc, abr)) != GSMVI_OK) return rc;
+  if ((rc = make_tmap_h(&tbh, B.hi, B.rows, B.cols, B.ld, abc, bbr)) != GSMVI_OK) return rc;
+  if ((rc = make_tmap_h(&tbl, B.lo, B.rows, B.cols, B.ld, abc, bbr)) != GSMVI_OK) return rc;
+
+  if (!o.a_mn && !o.b_mn) return launch_h3_one<false, false>(stream, a, tah, tbh, tal, tbl, grid);
+  if (o.a_mn && !o.b_mn) return launch_h3_one<true, false>(stream, a, tah, tbh, tal, tbl, grid);
+  if (!o.a_mn && o.b_mn) return launch_h3_one<false, true>(stream, a, tah, tbh, tal, tbl, grid);
+  return launch_h3_one<true, true>(stream, a, tah, tbh, tal, tbl, grid);
+}
+
+// ------------------------------------------------------------------------------------------------ operand split
+
+__global__ void __launch_bounds__(256) h3_absmax_kernel(const float* __restrict__ A, long long lda, int rows, int cols,
+                                                        unsigned* __restrict__ out) {
+  unsigned m = 0u;
+  const bool vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  for (long long i = blockIdx.y; i < rows; i += gridDim.y) {
+    const float* row = A + i * lda;
+    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4; j < cols; j += gridDim.x * blockDim.x * 4) {
+      if (vec && j + 3 < cols) {
+        const float4 v = *reinterpret_cast<const float4*>(row + j);
+        m = max(max(m, __float_as_uint(fabsf(v.x))), max(__float_as_uint(fabsf(v.y)), max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
+      } else {
+        for (int t = 0; t < 4 && j + t < cols; ++t) m = max(m, __float_as_uint(fabsf(row[j + t])));
+      }
+    }
+  }
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(out, m);
+}
+
+__global__ void __launch_bounds__(256) h3_split_kernel(const float* __restrict__ A, long long lda, int rows, int cols,
+                                                       const unsigned* __restrict__ absmax, int sqrt_mode,
+                                                       float* __restrict__ scale_out, __half* __restrict__ Hi,
+                                                       __half* __restrict__ Lo, long long ldo) {
+  const float s = h3_scale_from_absmax(*absmax, sqrt_mode);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *scale_out = s;
+  const bool vec = ((lda & 3) == 0) && ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+                   (((reinterpret_cast<uintptr_t>(Hi) | reinterpret_cast<uintptr_t>(Lo)) & 7) == 0);
+  for (long long i = blockIdx.y; i < rows; i += gridDim.y) {
+    const float* row = A + i * lda;
+    __half* hrow = Hi + i * ldo;
+    __half* lrow = Lo + i * ldo;
+    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4; j < cols; j += gridDim.x * blockDim.x * 4) {
+      if (vec && j + 3 < cols) {
+        const float4 v = *reinterpret_cast<const float4*>(row + j);
+        __half h[4], l[4];
+        h3_split1(v.x, s, h[0], l[0]);
+        h3_split1(v.y, s, h[1], l[1]);
+        h3_split1(v.z, s, h[2], l[2]);
+        h3_split1(v.w, s, h[3], l[3]);
+        *reinterpret_cast<uint2*>(hrow + j) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(lrow + j) = *reinterpret_cast<const uint2*>(l);
+      } else {
+        for (int t = 0; t < 4 && j + t < cols; ++t) h3_split1(row[j + t], s, hrow[j + t], lrow[j + t]);
+      }
+    }
+  }
+}
+
+static inline dim3 rowwise_grid(int rows, int cols) {
+  const int gx = (cols / 4 + 255) / 256 > 0 ? (cols / 4 + 255) / 256 : 1;
+  int gy = rows;
+  if (gy > 65535) gy = 65535;
+  return dim3(gx, gy);
+}
+
+int h3_absmax(cudaStream_t stream, const float* A, long long lda, int rows, int cols, unsigned* out) {
+  if (!A || !out || rows <= 0 || cols <= 0) return GSMVI_EINVAL;
+  // a few rows per CTA keeps the atomic count low
+  dim3 g = rowwise_grid(rows, cols);
+  g.y = (rows + 7) / 8;
+  if (g.y > 65535) g.y = 65535;
+  h3_absmax_kernel<<<g, 256, 0, stream>>>(A, lda, rows, cols, out);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
+}
+
+int h3_split(cudaStream_t stream, const float* A, long long lda, int rows, int cols, const unsigned* absmax, int sqrt_mode,
+             float* scale_out, __half* Hi, __half* Lo, long long ldo) {
+  if (!A || !absmax || !scale_out || !Hi || !Lo || rows <= 0 || cols <= 0) return GSMVI_EINVAL;
+  h3_split_kernel<<<rowwise_grid(rows, cols), 256, 0, stream>>>(A, lda, rows, cols, absmax, sqrt_mode, scale_out, Hi, Lo, ldo);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
+}
+
+}  // namespace gsmvi

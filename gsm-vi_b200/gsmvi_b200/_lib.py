@@ -242,3 +242,109 @@ def _declare(L):  # noqa: F811
 def gsm_ensemble_fit_raw(P, c, mu, Sigma, F, D, B, niter, seed, z_tape, reverts):
     check(lib().gsmvi_gsm_ensemble_fit(ptr(P), ptr(c), ptr(mu), ptr(Sigma), F, D, B, niter, seed & (2**64 - 1), ptr(z_tape),
                                        ptr(reverts), stream_ptr()), "gsmvi_gsm_ensemble_fit")
+
+
+# ------------------------------------------------------------------------------------------------ scaled 3xFP16 engine
+c_u = ctypes.c_uint
+
+
+class H3OperandC(ctypes.Structure):
+    """gsmvi_h3_operand of include/gsmvi_b200.h"""
+    _fields_ = [("hi", c_p), ("lo", c_p), ("scale", c_p), ("ld", c_ll)]
+
+
+WS_GSM_UPDATE_H3 = 6
+
+
+def _declare_h3(L):
+    L.gsmvi_gemm_h3.restype = c_i
+    L.gsmvi_gemm_h3.argtypes = [c_p, c_p, c_p, c_ll, c_ll, c_ll, c_i, c_p, c_p, c_p, c_ll, c_ll, c_ll, c_i, c_p, c_ll,
+                                c_i, c_i, c_i, c_f, c_f, c_p, c_ll, c_p, c_i, c_i, c_i, c_p, c_i, c_ll, c_p]
+    L.gsmvi_h3_absmax.restype = c_i
+    L.gsmvi_h3_absmax.argtypes = [c_p, c_ll, c_i, c_i, c_p, c_p]
+    L.gsmvi_h3_split.restype = c_i
+    L.gsmvi_h3_split.argtypes = [c_p, c_ll, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_ll, c_p]
+    hp = ctypes.POINTER(H3OperandC)
+    L.gsmvi_philox_normal_h3.restype = c_i
+    L.gsmvi_philox_normal_h3.argtypes = [hp, c_i, c_i, c_ull, c_ull, c_p]
+    L.gsmvi_sample_h3.restype = c_i
+    L.gsmvi_sample_h3.argtypes = [c_p, hp, hp, c_p, c_ll, c_p, c_i, c_i, c_p]
+    L.gsmvi_gauss_score_h3.restype = c_i
+    L.gsmvi_gauss_score_h3.argtypes = [hp, hp, c_p, c_p, c_ll, c_p, c_i, c_i, c_p]
+    L.gsmvi_gsm_update_h3.restype = c_i
+    L.gsmvi_gsm_update_h3.argtypes = [c_p, c_ll, c_p, c_ll, hp, c_p, c_p, c_ll, hp, c_p, c_p, c_ll, c_p, c_i, c_i, c_i,
+                                      c_i, c_p, c_p]
+
+
+_declare_ens_level = _declare
+
+
+def _declare(L):  # noqa: F811
+    _declare_ens_level(L)
+    _declare_h3(L)
+
+
+class HOperand:
+    """fp16 (hi, lo) pair + device scale of one GEMM operand (gsmvi_h3_split)."""
+
+    def __init__(self, rows, cols, dev, ld=None):
+        import torch
+        self.rows, self.cols = rows, cols
+        self.ld = ld if ld is not None else (cols + 31) // 32 * 32
+        self.hi = torch.zeros(rows, self.ld, dtype=torch.float16, device=dev)
+        self.lo = torch.zeros(rows, self.ld, dtype=torch.float16, device=dev)
+        self.scale = torch.ones(1, dtype=torch.float32, device=dev)
+        self.absmax = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.c = H3OperandC(self.hi.data_ptr(), self.lo.data_ptr(), self.scale.data_ptr(), self.ld)
+        self.ref = ctypes.byref(self.c)
+
+    def split_from(self, A, sqrt_mode=False, absmax=None):
+        """Split the fp32 matrix A ([rows, cols] view) into this operand; absmax: device word already holding the bit
+        pattern of max |A| (else it is reduced here)."""
+        if absmax is None:
+            self.absmax.zero_()
+            check(lib().gsmvi_h3_absmax(ptr(A), A.stride(0), self.rows, self.cols, ptr(self.absmax), stream_ptr()),
+                  "gsmvi_h3_absmax")
+            absmax = self.absmax
+        check(lib().gsmvi_h3_split(ptr(A), A.stride(0), self.rows, self.cols, ptr(absmax), int(sqrt_mode),
+                                   ptr(self.scale), ptr(self.hi), ptr(self.lo), self.ld, stream_ptr()), "gsmvi_h3_split")
+        return self
+
+    def dequant(self):
+        return (self.hi[:, :self.cols].float() + self.lo[:, :self.cols].float() / 2048.0) / self.scale
+
+
+def gemm_h3(A, B, C, M, N, K, a_mn=False, b_mn=False, alpha=1.0, beta=0.0, Cin=None, bias_n=None, tri=False,
+            mirror=False, krange=0, absmax_out=None, splits=1, split_stride=0):
+    """C[M,N] = alpha * op(A) op(B)^T + beta*Cin + bias_n with A, B HOperand (K-major [rows, K] or MN-major [K, rows])."""
+    rc = lib().gsmvi_gemm_h3(ptr(A.hi), ptr(A.lo), ptr(A.scale), A.rows, A.cols, A.ld, int(a_mn), ptr(B.hi), ptr(B.lo),
+                             ptr(B.scale), B.rows, B.cols, B.ld, int(b_mn), ptr(C), C.stride(0), M, N, K, alpha, beta,
+                             ptr(Cin), Cin.stride(0) if Cin is not None else 0, ptr(bias_n), int(tri), int(mirror),
+                             krange, ptr(absmax_out), splits, split_stride, stream_ptr())
+    check(rc, "gsmvi_gemm_h3")
+    return C
+
+
+def philox_normal_h3(Zh, B, D, seed, offset):
+    check(lib().gsmvi_philox_normal_h3(Zh.ref, B, D, seed & (2**64 - 1), offset & (2**64 - 1), stream_ptr()),
+          "gsmvi_philox_normal_h3")
+
+
+def sample_h3(mu, Lh, Zh, X, absmax_x, B, D):
+    check(lib().gsmvi_sample_h3(ptr(mu), Lh.ref, Zh.ref, ptr(X), X.stride(0), ptr(absmax_x), B, D, stream_ptr()),
+          "gsmvi_sample_h3")
+
+
+def gauss_score_h3(Xh, Ph, c, G, absmax_g, B, D):
+    check(lib().gsmvi_gauss_score_h3(Xh.ref, Ph.ref, ptr(c), ptr(G), G.stride(0), ptr(absmax_g), B, D, stream_ptr()),
+          "gsmvi_gauss_score_h3")
+
+
+def gsm_update_h3(X, G, Gh, mu, Sigma, Sh, mu_out, Sigma_out, absmax_sout, B, D, B_total, mode, ws):
+    check(lib().gsmvi_gsm_update_h3(ptr(X), X.stride(0), ptr(G), G.stride(0), Gh.ref, ptr(mu), ptr(Sigma), Sigma.stride(0),
+                                    Sh.ref, ptr(mu_out), ptr(Sigma_out), Sigma_out.stride(0), ptr(absmax_sout), B, D,
+                                    B_total, mode, ptr(ws), stream_ptr()), "gsmvi_gsm_update_h3")
+
+
+def h3_absmax(A, rows, cols, absmax):
+    check(lib().gsmvi_h3_absmax(ptr(A), A.stride(0), rows, cols, ptr(absmax), stream_ptr()), "gsmvi_h3_absmax")

@@ -37,7 +37,7 @@ class GSMEngine:
     """Device-resident state and workspaces of one GSM fit; `step(i)` is one loop body of gsmvi/gsm.py:107-129
     (sample -> score -> update -> goodness check -> accept/revert).  GSM.fit drives it; bench.py times it."""
 
-    def __init__(self, D, batch_size, lp_g, key, mean=None, cov=None, z_tape=None, npass=3, process_group=None,
+    def __init__(self, D, batch_size, lp_g, key, mean=None, cov=None, z_tape=None, npass=4, process_group=None,
                  score_input="torch"):
         dev = self.dev = device()
         self.D, self.batch_size, self.lp_g, self.npass = D, batch_size, lp_g, npass
@@ -84,11 +84,23 @@ class GSMEngine:
         self.z_tape = z_tape
         self.target = getattr(getattr(lp_g, "__self__", None), "_gsmvi_builtin_target", None)
         self.n_reverts = 0
-        L.potrf_check(self.Sb, self.Lb, D, self.bad, self.ws_p, npass)
+        self.h3 = npass == 4
+        self.np_gemm = 3 if self.h3 else npass  # precision of the Cholesky's tensor-core updates
+        L.potrf_check(self.Sb, self.Lb, D, self.bad, self.ws_p, self.np_gemm)
         if int(self.bad.item()) != 0:
             raise ValueError("initial covariance is not positive definite")
-        L.tf32_split(self.Sb, self.Shi, self.Slo, D, D)
-        L.tf32_split(self.Lb, self.Lhi, self.Llo, D, D)
+        if self.h3:
+            # scaled 3xFP16 engine: every GEMM operand lives as an fp16 (hi, lo) pair + power-of-two scale
+            H = L.HOperand
+            self.Sh, self.Snh, self.Lh, self.Lnh = H(D, D, dev), H(D, D, dev), H(D, D, dev), H(D, D, dev)
+            self.Zh, self.Xh, self.Gh = H(B, D, dev), H(B, D, dev), H(B, D, dev)
+            self.slots = torch.zeros(8, dtype=torch.int32, device=dev)  # |X|, |G|, |Sigma_new| maxima (bit patterns)
+            self.ws_u = torch.empty(L.workspace_bytes(L.WS_GSM_UPDATE_H3, B, D) // 4, dtype=torch.float32, device=dev)
+            self.Sh.split_from(self.S)
+            self.Lh.split_from(self.Lb[:, :D], sqrt_mode=True, absmax=self.Sh.absmax)
+        else:
+            L.tf32_split(self.Sb, self.Shi, self.Slo, D, D)
+            L.tf32_split(self.Lb, self.Lhi, self.Llo, D, D)
 
     def launches_per_step(self):
         """Kernels of libgsmvi_b200.so launched by one step (bench.py reports it as gpu_launches)."""
@@ -98,7 +110,57 @@ class GSMEngine:
         return (0 if self.z_tape is not None else 1) + 1 + (1 if self.target is not None else 0) + upd + potrf + \
             (2 if self.world > 1 else 0)
 
+    def step_h3(self, i):
+        """One iteration on the scaled 3xFP16 engine (same sequence as `step`)."""
+        D, B = self.D, self.B
+        sl = self.slots
+        sl.zero_()
+        # ---- sample (gsm.py:117-119)
+        if self.z_tape is not None:
+            self.Z.copy_(self.z_tape[i, self.rank * B:(self.rank + 1) * B], non_blocking=True)
+            self.Zh.split_from(self.Z)
+        else:
+            L.philox_normal_h3(self.Zh, B, D, self.seed, i * self.world + self.rank)
+        L.sample_h3(self.mu, self.Lh, self.Zh, self.Xb, sl[0:1], B, D)
+        # ---- score (gsm.py:121)
+        if self.target is not None:
+            self.Xh.split_from(self.X, absmax=sl[0:1])
+            L.gauss_score_h3(self.Xh, self.target.Ph, self.target.c, self.Gb, sl[1:2], B, D)
+            self.Gh.split_from(self.G, absmax=sl[1:2])
+        else:
+            if self.score_input == "numpy":
+                self.G.copy_(to_dev(self.lp_g(self.X.cpu().numpy()), self.dev))
+            else:
+                self.G.copy_(to_dev(self.lp_g(self.X), self.dev))
+            self.Gh.split_from(self.G)
+        # ---- update (gsm.py:122)
+        if self.world == 1:
+            L.gsm_update_h3(self.Xb, self.Gb, self.Gh, self.mu, self.Sb, self.Sh, self.mun, self.Snb, sl[2:3], B, D, B, 0,
+                            self.ws_u)
+        else:
+            L.gsm_update_h3(self.Xb, self.Gb, self.Gh, self.mu, self.Sb, self.Sh, self.dmu, self.dSb, None, B, D,
+                            self.batch_size, 1, self.ws_u)
+            self.dist.all_reduce(self.dSb, group=self.group)
+            self.dist.all_reduce(self.dmu, group=self.group)
+            L.gsm_apply_stats(self.Sb, self.dSb, self.mu, self.dmu, self.Snb, self.mun, D)
+            L.h3_absmax(self.Sn, D, D, sl[2:3])
+        # ---- goodness check = Cholesky of the new covariance, reused as the next sampling factor (gsm.py:125)
+        L.potrf_check(self.Snb, self.Lnb, D, self.bad, self.ws_p, self.np_gemm)
+        self.Snh.split_from(self.Sn, absmax=sl[2:3])  # queued before the flag is read: overlap the host round trip
+        self.Lnh.split_from(self.Lnb[:, :D], sqrt_mode=True, absmax=sl[2:3])  # |L_ij| <= sqrt(max Sigma_ii)
+        ok = int(self.bad.item()) == 0  # the step's only device->host read (4 bytes)
+        if ok:  # gsm.py:126-127
+            self.Sb, self.Snb, self.S, self.Sn = self.Snb, self.Sb, self.Sn, self.S
+            self.Lb, self.Lnb = self.Lnb, self.Lb
+            self.Sh, self.Snh, self.Lh, self.Lnh = self.Snh, self.Sh, self.Lnh, self.Lh
+            self.mu, self.mun = self.mun, self.mu
+        else:
+            self.n_reverts += 1
+        return ok
+
     def step(self, i):
+        if self.h3:
+            return self.step_h3(i)
         D, B, npass = self.D, self.B, self.npass
         # ---- sample (gsm.py:117-119)
         if self.z_tape is not None:
@@ -157,7 +219,7 @@ class GSM:
         self.lp_g = lp_g
 
     def fit(self, key, mean=None, cov=None, batch_size=2, niter=5000, nprint=10, verbose=True, check_goodness=True,
-            monitor=None, *, z_tape=None, npass=3, process_group=None, score_input="torch"):
+            monitor=None, *, z_tape=None, npass=4, process_group=None, score_input="torch"):
         """Main function to fit a multivariate Gaussian to the target (gsmvi/gsm.py:79-133).
 
         Reference arguments keep their meaning (check_goodness is accepted and, as in the reference, the covariance
@@ -165,7 +227,8 @@ class GSM:
         arguments:
           z_tape: optional [niter+1, batch_size, D] standard-normal draws used instead of the Philox stream
                   (parity runs: the same tape is fed to the oracle)
-          npass: 3 = 3xTF32 tensor-core passes (fp32-grade), 1 = single TF32 pass
+          npass: tensor-core precision: 4 = scaled 3xFP16 split (default; 22-bit significands like 3xTF32 at twice the
+                  pipe rate), 3 = 3xTF32 round-to-nearest split, 2 = 3xTF32 truncation split, 1 = single TF32 pass
           process_group: torch.distributed group; the batch is sharded across its ranks and the D x D statistics are
                   all-reduced (one process per GPU)
           score_input: "torch" passes CUDA tensors to lp_g; "numpy" passes host arrays (reference-style callables)

@@ -25,6 +25,7 @@ class DenseGaussianTarget:
         self.Phib, _ = new_mat(self.D, self.D, dev)  # pre-split (hi, lo) form of P for the score GEMM
         self.Plob, _ = new_mat(self.D, self.D, dev)
         L.tf32_split(self.Pb, self.Phib, self.Plob, self.D, self.D)
+        self.Ph = L.HOperand(self.D, self.D, dev).split_from(self.P)  # fp16 (hi, lo) form for the scaled 3xFP16 engine
         self.c = new_vec(self.D, dev)
         self.c[: self.D].copy_(torch.as_tensor(P @ mean, dtype=torch.float32))
         self.m = torch.as_tensor(mean, dtype=torch.float32, device=dev)

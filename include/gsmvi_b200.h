@@ -30,6 +30,16 @@ extern "C" {
 #define GSMVI_WS_BAM_STATS 3
 #define GSMVI_WS_BAM_SOLVE 4
 #define GSMVI_WS_BAM_SOLVE_LOWRANK 5
+#define GSMVI_WS_GSM_UPDATE_H3 6
+
+/* One operand of the scaled 3xFP16 engine: fp16 arrays hi / lo (row-major, leading dimension ld in elements, a multiple
+ * of 8) and the device float holding the power-of-two scale they were stored with (see gsmvi_h3_split). */
+typedef struct gsmvi_h3_operand {
+  void* hi;
+  void* lo;
+  float* scale;
+  long long ld;
+} gsmvi_h3_operand;
 
 int gsmvi_abi_version(void);
 
@@ -43,6 +53,44 @@ int gsmvi_gemm_tf32(const float* A, long long a_rows, long long a_cols, long lon
                     long long b_rows, long long b_cols, long long ldb, int b_mn, float* C, long long ldc, int M, int N,
                     int K, float alpha, float beta, const float* Cin, long long ldcin, const float* bias_n, int npass,
                     int tri, int mirror, int krange, int neg_from, const float* A_lo, const float* B_lo, void* stream);
+
+/* Scaled 3xFP16 contraction (same contract as gsmvi_gemm_tf32 at twice the tensor-pipe rate): operands arrive pre-split
+ * as fp16 pairs A_hi = rn_f16(A s), A_lo = rn_f16((A s - A_hi) 2^11) with a power-of-two scale s held in a device float
+ * (gsmvi_h3_split); fp16 products are exact in the fp32 accumulator, so hi*hi + hi*lo + lo*hi carries 22 significand
+ * bits like 3xTF32.  Leading dimensions of the fp16 arrays are in elements, multiples of 8.
+ * absmax_out: optional device word, atomicMax of the bit patterns of |C| (feeds the next gsmvi_h3_split; zero it first).
+ * splits > 1: split-K, split s writes its raw partial product to C + s * split_stride (beta, bias, mirror not allowed). */
+int gsmvi_gemm_h3(const void* A_hi, const void* A_lo, const float* scale_a, long long a_rows, long long a_cols, long long lda,
+                  int a_mn, const void* B_hi, const void* B_lo, const float* scale_b, long long b_rows, long long b_cols,
+                  long long ldb, int b_mn, float* C, long long ldc, int M, int N, int K, float alpha, float beta,
+                  const float* Cin, long long ldcin, const float* bias_n, int tri, int mirror, int krange,
+                  unsigned* absmax_out, int splits, long long split_stride, void* stream);
+
+/* *absmax <- max(*absmax, max |A|) as a float bit pattern (device word; zero it first). */
+int gsmvi_h3_absmax(const float* A, long long lda, int rows, int cols, unsigned* absmax, void* stream);
+
+/* The fp16 split of an operand: *scale_out <- 2^(14 - e) where *absmax = f 2^e (sqrt_mode: of sqrt(*absmax), the bound
+ * on a Cholesky factor's entries given max Sigma_ii), A_hi / A_lo as above. */
+int gsmvi_h3_split(const float* A, long long lda, int rows, int cols, const unsigned* absmax, int sqrt_mode,
+                   float* scale_out, void* A_hi, void* A_lo, long long ldo, void* stream);
+
+/* The GSM iteration on the scaled 3xFP16 engine (same reference lines as the fp32-operand calls below).
+ * gsmvi_philox_normal_h3: Z written directly as the fp16 pair (fixed scale 2^11).
+ * gsmvi_sample_h3 / gsmvi_gauss_score_h3: as gsmvi_sample / gsmvi_gauss_score with pre-split operands; *absmax_x /
+ *   *absmax_g (device words, zeroed by the caller) receive the bit pattern of max |X| / max |G| for the next split.
+ * gsmvi_gsm_update_h3: as gsmvi_gsm_update; G is given both as fp32 (row pass) and split (W = G Sigma), Sigma both as
+ *   fp32 (epilogue) and split; *absmax_sout receives max |Sigma_out| (lower tiles; Sigma_out is symmetric).
+ *   workspace: gsmvi_workspace_bytes(GSMVI_WS_GSM_UPDATE_H3, B, D). */
+int gsmvi_philox_normal_h3(const gsmvi_h3_operand* Z, int B, int D, unsigned long long seed, unsigned long long offset,
+                           void* stream);
+int gsmvi_sample_h3(const float* mu, const gsmvi_h3_operand* L, const gsmvi_h3_operand* Z, float* X, long long ldx,
+                    unsigned* absmax_x, int B, int D, void* stream);
+int gsmvi_gauss_score_h3(const gsmvi_h3_operand* X, const gsmvi_h3_operand* P, const float* c, float* G, long long ldg,
+                         unsigned* absmax_g, int B, int D, void* stream);
+int gsmvi_gsm_update_h3(const float* X, long long ldx, const float* G, long long ldg, const gsmvi_h3_operand* G_split,
+                        const float* mu, const float* Sigma, long long lds, const gsmvi_h3_operand* Sigma_split,
+                        float* mu_out, float* Sigma_out, long long ldso, unsigned* absmax_sout, int B, int D, int B_total,
+                        int mode, void* workspace, void* stream);
 
 /* L <- chol(Sigma) (lower, upper triangle zeroed), *bad_flag <- 0 if Sigma is positive definite else 1.
  * Replaces GSM._check_goodness / BaM._check_goodness (gsmvi/gsm.py:136-150, gsmvi/bam.py:219-233: host

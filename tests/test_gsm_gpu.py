@@ -159,8 +159,9 @@ FIT_CASES = [
 ]
 
 
+@pytest.mark.parametrize("npass", [4, 3])  # 4: scaled 3xFP16 engine (default), 3: 3xTF32 engine
 @pytest.mark.parametrize("D,B,niter,kind", FIT_CASES)
-def test_gsm_fit_trajectory_parity(lib, D, B, niter, kind):
+def test_gsm_fit_trajectory_parity(lib, D, B, niter, kind, npass):
     """Identical z-tape and target fed to the device loop and the fp64 oracle loop (SURVEY.md section 8c protocol):
     fitted (mu, Sigma) within 1e-4 relative (Frobenius) of the oracle - BASELINE.json north_star tolerance."""
     from gsmvi_b200.gsm import GSM
@@ -181,10 +182,10 @@ def test_gsm_fit_trajectory_parity(lib, D, B, niter, kind):
     o = orc.GSM(D, None, lp_g)
     m_o, c_o = o.fit(99, niter=niter, batch_size=B, sampler=orc.CholeskyTapeSampler(Z.astype(np.float64)))
     g = GSM(D, tgt.lp, tgt.lp_g)
-    m_d, c_d = g.fit(99, niter=niter, batch_size=B, z_tape=Z, verbose=False)
+    m_d, c_d = g.fit(99, niter=niter, batch_size=B, z_tape=Z, verbose=False, npass=npass)
     e_c = relF(c_d, c_o)
     e_m = np.linalg.norm(m_d.cpu().double().numpy() - m_o) / np.linalg.norm(m_o)
-    record("gsm_fit_parity", dict(D=D, B=B, niter=niter, target=kind, relF_cov=e_c, rel_mean=e_m,
+    record("gsm_fit_parity", dict(D=D, B=B, niter=niter, target=kind, npass=npass, relF_cov=e_c, rel_mean=e_m,
                                   reverts_dev=g.n_reverts, reverts_oracle=o.n_reverts))
     assert g.n_reverts == o.n_reverts
     # BASELINE north_star tolerance: 1e-4 relative (Frobenius).  The reference example target (LL^T + 1e-3 I at

@@ -209,6 +209,127 @@ elif group == "perf":
             out["cublas_fp64_%d" % n] = {"ms": ms, "tflops": fl / ms / 1e9}
             print("cublas fp64 n=%d: %.3f ms %.1f TF/s" % (n, ms, fl / ms / 1e9), flush=True)
             del Ad, Bd, Cd
+elif group in ("h3", "h3mn", "h3perf"):
+    def hop(X):
+        return L.HOperand(X.shape[0], X.shape[1], dev, ld=(X.shape[1] + 31) // 32 * 32).split_from(X)
+
+    def h3_case(name, M, N, K, a_mn=False, b_mn=False, scale_a=1.0, scale_b=1.0, **kw):
+        g = torch.Generator(device="cpu").manual_seed(abs(hash(name)) % (2**31))
+        A = (torch.randn(M, K, generator=g, dtype=torch.float32) * scale_a).to(dev)
+        B = (torch.randn(N, K, generator=g, dtype=torch.float32) * scale_b).to(dev)
+        Aop = hop(A.t().contiguous() if a_mn else A)
+        Bop = hop(B.t().contiguous() if b_mn else B)
+        C = torch.full((M, N + 4), float("nan"), device=dev)[:, :N]
+        L.gemm_h3(Aop, Bop, C, M, N, K, a_mn=a_mn, b_mn=b_mn, **kw)
+        torch.cuda.synchronize()
+        e = relerr(C, A.double() @ B.double().t())
+        out[name] = e
+        print("%-40s M=%d N=%d K=%d  relerr=%.3e" % (name, M, N, K, e), flush=True)
+        return e
+
+    if group == "h3":
+        # the split itself: hi + lo/2^11 reproduces the fp32 value to 2^-22
+        X = torch.randn(300, 200, device=dev) * 37.0
+        o = hop(X)
+        out["split_roundtrip"] = float(((o.dequant() - X).abs() / X.abs().clamp_min(1e-30)).max())
+        out["split_scale"] = float(o.scale)
+        print(out, flush=True)
+        h3_case("kk_128x128x64", 128, 128, 64)
+        h3_case("kk_128x128x256", 128, 128, 256)
+        h3_case("kk_256x384x512", 256, 384, 512)
+        h3_case("kk_ragged", 300, 200, 100)
+        h3_case("kk_tiny", 10, 10, 12)
+        h3_case("kk_1024", 1024, 1024, 1024)
+        h3_case("kk_K4096", 512, 512, 4096)
+        h3_case("kk_K8192", 512, 512, 8192)
+        h3_case("kk_scales", 256, 256, 512, scale_a=3.0e-7, scale_b=8.0e5)
+        # same-sign sums: worst case for the truncating TMEM accumulate
+        A = torch.rand(512, 8192, device=dev) + 0.5
+        C = torch.empty(512, 512, device=dev)
+        Ao = hop(A)
+        L.gemm_h3(Ao, Ao, C, 512, 512, 8192)
+        out["positive_K8192"] = relerr(C, A.double() @ A.double().t())
+        L.gemm_tf32(A, A, C, 512, 512, 8192)
+        out["positive_K8192_tf32x3"] = relerr(C, A.double() @ A.double().t())
+        # wide dynamic range inside one tensor (rows scaled by 2^-20 .. 1)
+        g = torch.Generator().manual_seed(3)
+        A = torch.randn(256, 512, generator=g).to(dev) * torch.logspace(-6, 0, 256, device=dev)[:, None]
+        B = torch.randn(256, 512, generator=g).to(dev)
+        C = torch.empty(256, 256, device=dev)
+        L.gemm_h3(hop(A), hop(B), C, 256, 256, 512)
+        ref = A.double() @ B.double().t()
+        out["dynrange_rowwise_relerr_max"] = float(((C.double() - ref).norm(dim=1) / ref.norm(dim=1)).max())
+        # epilogue: alpha/beta/bias, absmax, tri+mirror, krange, split-K
+        M, N, K = 384, 384, 256
+        A = torch.randn(M, K, generator=g).to(dev)
+        Cin = torch.randn(M, N, generator=g).to(dev)
+        bias = torch.randn(N, generator=g).to(dev)
+        Ao = hop(A)
+        C = torch.empty(M, N, device=dev)
+        am = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.gemm_h3(Ao, Ao, C, M, N, K, alpha=0.5, beta=-2.0, Cin=Cin, bias_n=bias, absmax_out=am)
+        ref = 0.5 * (A.double() @ A.double().t()) - 2.0 * Cin.double() + bias.double()
+        out["alpha_beta_bias"] = relerr(C, ref)
+        out["absmax_matches"] = float(am.view(torch.float32)) - float(C.abs().max())
+        C2 = (Cin + Cin.t()) / 2
+        sym = C2.clone()
+        L.gemm_h3(Ao, Ao, C2, M, N, K, alpha=1.0 / K, beta=1.0, Cin=C2, tri=True, mirror=True)
+        out["tri_mirror_inplace"] = relerr(C2, sym.double() + (A.double() @ A.double().t()) / K)
+        out["tri_mirror_asym"] = float((C2 - C2.t()).abs().max())
+        Lm = torch.tril(torch.randn(N, N, generator=g)).to(dev)
+        Z = torch.randn(M, N, generator=g).to(dev)
+        C4 = torch.empty(M, N, device=dev)
+        L.gemm_h3(hop(Z), hop(Lm), C4, M, N, N, krange=L.KR_B_LOWER, bias_n=bias)
+        out["krange_b_lower"] = relerr(C4, Z.double() @ Lm.double().t() + bias.double())
+        S = 3
+        Cs = torch.zeros(S, M, N, device=dev)
+        L.gemm_h3(Ao, Ao, Cs.view(S * M, N), M, N, K, splits=S, split_stride=M * N)
+        out["splitk3"] = relerr(Cs.sum(0), A.double() @ A.double().t())
+        Cs = torch.zeros(7, M, N, device=dev)
+        L.gemm_h3(Ao, Ao, Cs.view(7 * M, N), M, N, K, splits=7, split_stride=M * N)
+        out["splitk7_more_than_blocks"] = relerr(Cs.sum(0), A.double() @ A.double().t())
+        for k, v in out.items():
+            print("%-32s %s" % (k, v), flush=True)
+    elif group == "h3mn":
+        h3_case("mnA", 256, 256, 128, a_mn=True)
+        h3_case("mnB", 256, 256, 128, b_mn=True)
+        h3_case("mnAB", 256, 256, 128, a_mn=True, b_mn=True)
+        h3_case("mnAB_big", 256, 384, 1024, a_mn=True, b_mn=True)
+        h3_case("mnAB_ragged", 300, 200, 100, a_mn=True, b_mn=True)
+        h3_case("mnAB_tri_mirror", 384, 384, 192, a_mn=True, b_mn=True)
+    else:
+        for n in (2048, 4096, 8192):
+            A = torch.randn(n, n, device=dev)
+            B = torch.randn(n, n, device=dev)
+            C = torch.empty(n, n, device=dev)
+            Ao, Bo = hop(A), hop(B)
+            fl = 2.0 * n**3
+            ms = timeit(lambda: L.gemm_h3(Ao, Bo, C, n, n, n))
+            out["h3_%d" % n] = {"ms": ms, "tflops_alg": fl / ms / 1e9, "tflops_exec": 3 * fl / ms / 1e9}
+            print("h3 n=%d: %.3f ms  %.1f TF/s algorithmic (%.1f executed)" % (n, ms, fl / ms / 1e9, 3 * fl / ms / 1e9), flush=True)
+            ms = timeit(lambda: L.gemm_h3(Ao, Ao, C, n, n, n, tri=True, mirror=True, a_mn=True, b_mn=True))
+            out["h3_syrk_mn_%d" % n] = {"ms": ms, "tflops_alg_dense": fl / ms / 1e9}
+            print("h3 syrk mn n=%d: %.3f ms  %.1f TF/s dense-counted" % (n, ms, fl / ms / 1e9), flush=True)
+            ms = timeit(lambda: L.gemm_h3(Ao, Bo, C, n, n, n, krange=L.KR_B_LOWER))
+            out["h3_trmm_%d" % n] = {"ms": ms}
+            print("h3 B-lower n=%d: %.3f ms" % (n, ms), flush=True)
+            ms = timeit(lambda: Ao.split_from(A))
+            out["split_%d" % n] = {"ms": ms, "GBps": (12.0 * n * n) / ms / 1e6}
+            print("absmax+split n=%d: %.3f ms" % (n, ms), flush=True)
+            Ah, Bh = A.half(), B.half()
+            Ch = torch.empty(n, n, device=dev, dtype=torch.float16)
+            ms = timeit(lambda: torch.matmul(Ah, Bh.t(), out=Ch))
+            out["cublas_f16_%d" % n] = {"ms": ms, "tflops": fl / ms / 1e9}
+            print("cublas f16 n=%d: %.3f ms %.1f TF/s" % (n, ms, fl / ms / 1e9), flush=True)
+        # left-looking Cholesky panel update shape: M x 128 output, long K, split-K
+        n = 4096
+        A = torch.randn(n, n, device=dev)
+        Ao = hop(A)
+        for (M, K, S) in [(2048, 2048, 9), (1024, 3072, 18), (3968, 128, 1), (3072, 1024, 6)]:
+            Cs = torch.empty(S * M, 128, device=dev)
+            ms = timeit(lambda: L.gemm_h3(Ao, Ao, Cs, M, 128, K, splits=S, split_stride=M * 128), iters=20)
+            out["panel_update_M%d_K%d_S%d" % (M, K, S)] = {"ms": ms}
+            print("panel update M=%d K=%d splits=%d: %.4f ms" % (M, K, S, ms), flush=True)
 else:
     raise SystemExit("unknown group")
 

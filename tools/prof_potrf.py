@@ -11,3 +11,9 @@ ws = torch.empty(L.workspace_bytes(L.WS_POTRF, 0, D) // 4, device="cuda")
 for _ in range(3):
     L.potrf_check(S, Lo, D, bad, ws)
 torch.cuda.synchronize(); print("ok", int(bad.item()))
+s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+s.record()
+for _ in range(10):
+    L.potrf_check(S, Lo, D, bad, ws)
+e.record(); torch.cuda.synchronize()
+print("potrf D=%d: %.3f ms per factorisation" % (D, s.elapsed_time(e) / 10))

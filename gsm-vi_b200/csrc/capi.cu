@@ -22,6 +22,7 @@ long long gsmvi_workspace_bytes(int kind, int B, int D) {
   switch (kind) {
     case GSMVI_WS_POTRF: return static_cast<long long>(potrf_workspace_bytes(D));
     case GSMVI_WS_GSM_UPDATE: return static_cast<long long>(gsm_update_workspace_bytes(B, D));
+    case GSMVI_WS_POTRF_H3: return static_cast<long long>(potrf_h3_workspace_bytes(D));
     case GSMVI_WS_GSM_UPDATE_H3: return static_cast<long long>(gsm_update_h3_workspace_bytes(B, D));
     case GSMVI_WS_BAM_STATS: return static_cast<long long>(bam_stats_workspace_bytes(B, D));
     case GSMVI_WS_BAM_SOLVE: return static_cast<long long>(bam_solve_workspace_bytes(B, D, 0));
@@ -115,6 +116,12 @@ int gsmvi_gsm_update_h3(const float* X, long long ldx, const float* G, long long
 int gsmvi_potrf_check(const float* Sigma, long long lds, float* L, long long ldl, int D, int* bad_flag,
                       void* workspace, int npass, void* stream) {
   return potrf_lower(S(stream), Sigma, lds, L, ldl, D, bad_flag, static_cast<float*>(workspace), npass);
+}
+
+int gsmvi_potrf_h3(const float* Sigma, long long lds, float* L, long long ldl, const gsmvi_h3_operand* L_split, int D,
+                   int* bad_flag, void* workspace, int zero_upper, void* stream) {
+  if (!L_split) return GSMVI_EINVAL;
+  return potrf_h3(S(stream), Sigma, lds, L, ldl, *L_split, D, bad_flag, workspace, zero_upper);
 }
 
 int gsmvi_philox_normal(float* Z, long long ldz, int B, int D, unsigned long long seed, unsigned long long offset,

@@ -26,4 +26,58 @@ __device__ __forceinline__ void chol32_step(float (&row)[32], int lane, float* d
   }
 }
 
+// Blocked variant of the same warp-level 32x32 Cholesky: four 8-column steps.  Each step gathers the 8x8 diagonal
+// block into EVERY lane (36 shuffles, issued back to back), factors it redundantly in registers - so the eight
+// dependent pivots (rsqrt + one Newton step each) have no cross-lane traffic between them - then every row solves its
+// eight entries against that block locally and the remaining columns take a rank-8 update (8 shuffles per column).
+// The per-column dependent chain drops from shuffle + rsqrt + shuffle (~110 cycles) to rsqrt + a few FMAs (~60).
+// On return lane i holds row i of L in row[0..i]; row[k] for k > i is undefined (callers mask it to zero).
+__device__ __forceinline__ void chol32_b8(float (&row)[32], int lane, float* dinv_out, int& isbad) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int c0 = 8 * q;
+    float d[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c <= r; ++c) d[r][c] = __shfl_sync(0xffffffffu, row[c0 + c], c0 + r);
+    float rinv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dj = d[j][j];
+      if (!(dj > 0.0f) || isinf(dj)) isbad = 1;
+      float r = rsqrtf(dj);
+      r = r * (1.5f - 0.5f * dj * r * r);
+      rinv[j] = r;
+#pragma unroll
+      for (int i = j + 1; i < 8; ++i) d[i][j] *= r;
+#pragma unroll
+      for (int i = j + 1; i < 8; ++i)
+#pragma unroll
+        for (int k = j + 1; k <= i; ++k) d[i][k] -= d[i][j] * d[k][j];
+    }
+    // x L8^T = a for this lane's row (rows inside the block reproduce their own row of L8 for j <= r)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float x = row[c0 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) x -= row[c0 + k] * d[j][k];
+      // the diagonal entry itself: l_jj = d_jj * rinv_j, computed from the un-scaled pivot for full accuracy
+      row[c0 + j] = (lane == c0 + j) ? d[j][j] * rinv[j] : x * rinv[j];
+      if (lane == c0 + j) dinv_out[c0 + j] = rinv[j];
+    }
+    // rank-8 update of the remaining columns: row_i[k] -= sum_c l_ic l_kc
+#pragma unroll
+    for (int k = c0 + 8; k < 32; ++k) {
+      float acc0 = row[k], acc1 = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        acc0 -= row[c0 + c] * __shfl_sync(0xffffffffu, row[c0 + c], k);
+        acc1 -= row[c0 + c + 1] * __shfl_sync(0xffffffffu, row[c0 + c + 1], k);
+      }
+      row[k] = acc0 + acc1;
+    }
+  }
+}
+
 }  // namespace gsmvi

@@ -12,4 +12,11 @@ size_t potrf_workspace_bytes(int n);
 int potrf_lower(cudaStream_t stream, const float* A, long long lda, float* L, long long ldl, int n, int* flag,
                 float* workspace, int npass);
 
+// Left-looking variant on the scaled 3xFP16 engine (potrf_h3.cu): also writes L as the fp16 (hi, lo) pair `Lh` with the
+// scale derived from max |A_ii|.  zero_upper = 0 skips clearing the blocks above the diagonal (they are never written,
+// so a buffer that was zero once stays valid).  workspace: potrf_h3_workspace_bytes(n) bytes, 16-byte aligned.
+size_t potrf_h3_workspace_bytes(int n);
+int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long long ldl, const gsmvi_h3_operand& Lh, int n,
+             int* flag, void* workspace, int zero_upper);
+
 }  // namespace gsmvi

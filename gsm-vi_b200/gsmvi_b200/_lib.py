@@ -254,6 +254,7 @@ class H3OperandC(ctypes.Structure):
 
 
 WS_GSM_UPDATE_H3 = 6
+WS_POTRF_H3 = 7
 
 
 def _declare_h3(L):
@@ -271,6 +272,8 @@ def _declare_h3(L):
     L.gsmvi_sample_h3.argtypes = [c_p, hp, hp, c_p, c_ll, c_p, c_i, c_i, c_p]
     L.gsmvi_gauss_score_h3.restype = c_i
     L.gsmvi_gauss_score_h3.argtypes = [hp, hp, c_p, c_p, c_ll, c_p, c_i, c_i, c_p]
+    L.gsmvi_potrf_h3.restype = c_i
+    L.gsmvi_potrf_h3.argtypes = [c_p, c_ll, c_p, c_ll, hp, c_i, c_p, c_p, c_i, c_p]
     L.gsmvi_gsm_update_h3.restype = c_i
     L.gsmvi_gsm_update_h3.argtypes = [c_p, c_ll, c_p, c_ll, hp, c_p, c_p, c_ll, hp, c_p, c_p, c_ll, c_p, c_i, c_i, c_i,
                                       c_i, c_p, c_p]
@@ -297,6 +300,16 @@ class HOperand:
         self.absmax = torch.zeros(1, dtype=torch.int32, device=dev)
         self.c = H3OperandC(self.hi.data_ptr(), self.lo.data_ptr(), self.scale.data_ptr(), self.ld)
         self.ref = ctypes.byref(self.c)
+
+    @classmethod
+    def from_tensors(cls, hi, lo, scale, rows, cols):
+        """Operand over existing storage (2-D fp16 views with the same row stride, 1-element fp32 scale tensor)."""
+        o = cls.__new__(cls)
+        o.rows, o.cols, o.ld = rows, cols, hi.stride(0)
+        o.hi, o.lo, o.scale, o.absmax = hi, lo, scale, None
+        o.c = H3OperandC(hi.data_ptr(), lo.data_ptr(), scale.data_ptr(), o.ld)
+        o.ref = ctypes.byref(o.c)
+        return o
 
     def split_from(self, A, sqrt_mode=False, absmax=None):
         """Split the fp32 matrix A ([rows, cols] view) into this operand; absmax: device word already holding the bit
@@ -348,3 +361,9 @@ def gsm_update_h3(X, G, Gh, mu, Sigma, Sh, mu_out, Sigma_out, absmax_sout, B, D,
 
 def h3_absmax(A, rows, cols, absmax):
     check(lib().gsmvi_h3_absmax(ptr(A), A.stride(0), rows, cols, ptr(absmax), stream_ptr()), "gsmvi_h3_absmax")
+
+
+def potrf_h3(Sigma, L_out, Lh, D, bad_flag, ws, zero_upper=True):
+    """L_out <- chol(Sigma[:D,:D]) (fp32) and Lh <- its fp16 split; bad_flag <- 0 if PD else 1.  No sync."""
+    check(lib().gsmvi_potrf_h3(ptr(Sigma), Sigma.stride(0), ptr(L_out), L_out.stride(0), Lh.ref, D, ptr(bad_flag), ptr(ws),
+                               int(zero_upper), stream_ptr()), "gsmvi_potrf_h3")

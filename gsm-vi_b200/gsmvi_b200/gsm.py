@@ -56,11 +56,13 @@ class GSMEngine:
         self.Snb, self.Sn = new_mat(D, D, dev)
         self.Lb, _ = new_mat(D, D, dev)
         self.Lnb, _ = new_mat(D, D, dev)
-        # pre-split low parts of the reused GEMM operands (Sigma for W = G Sigma, L for the sampler), kept per buffer
-        self.Shi, self.Slo = new_mat(D, D, dev)[0], new_mat(D, D, dev)[0]
-        self.Snhi, self.Snlo = new_mat(D, D, dev)[0], new_mat(D, D, dev)[0]
-        self.Lhi, self.Llo = new_mat(D, D, dev)[0], new_mat(D, D, dev)[0]
-        self.Lnhi, self.Lnlo = new_mat(D, D, dev)[0], new_mat(D, D, dev)[0]
+        self.h3 = npass == 4
+        if not self.h3:
+            # pre-split low parts of the reused GEMM operands (Sigma for W = G Sigma, L for the sampler), kept per buffer
+            self.Shi, self.Slo = new_mat(D, D, dev)[0], new_mat(D, D, dev)[0]
+            self.Snhi, self.Snlo = new_mat(D, D, dev)[0], new_mat(D, D, dev)[0]
+            self.Lhi, self.Llo = new_mat(D, D, dev)[0], new_mat(D, D, dev)[0]
+            self.Lnhi, self.Lnlo = new_mat(D, D, dev)[0], new_mat(D, D, dev)[0]
         self.mu, self.mun = new_vec(D, dev), new_vec(D, dev)
         if mean is not None:
             self.mu[:D].copy_(to_dev(mean, dev))  # gsm.py:100-101 (default zeros)
@@ -71,8 +73,9 @@ class GSMEngine:
         self.Zb, self.Z = new_mat(B, D, dev)
         self.Xb, self.X = new_mat(B, D, dev)
         self.Gb, self.G = new_mat(B, D, dev)
-        self.ws_p = torch.empty(L.workspace_bytes(L.WS_POTRF, B, D) // 4, dtype=torch.float32, device=dev)
-        self.ws_u = torch.empty(L.workspace_bytes(L.WS_GSM_UPDATE, B, D) // 4, dtype=torch.float32, device=dev)
+        if not self.h3:
+            self.ws_p = torch.empty(L.workspace_bytes(L.WS_POTRF, B, D) // 4, dtype=torch.float32, device=dev)
+            self.ws_u = torch.empty(L.workspace_bytes(L.WS_GSM_UPDATE, B, D) // 4, dtype=torch.float32, device=dev)
         self.bad = torch.zeros(1, dtype=torch.int32, device=dev)
         if self.world > 1:
             self.dSb, _ = new_mat(D, D, dev)
@@ -84,11 +87,6 @@ class GSMEngine:
         self.z_tape = z_tape
         self.target = getattr(getattr(lp_g, "__self__", None), "_gsmvi_builtin_target", None)
         self.n_reverts = 0
-        self.h3 = npass == 4
-        self.np_gemm = 3 if self.h3 else npass  # precision of the Cholesky's tensor-core updates
-        L.potrf_check(self.Sb, self.Lb, D, self.bad, self.ws_p, self.np_gemm)
-        if int(self.bad.item()) != 0:
-            raise ValueError("initial covariance is not positive definite")
         if self.h3:
             # scaled 3xFP16 engine: every GEMM operand lives as an fp16 (hi, lo) pair + power-of-two scale
             H = L.HOperand
@@ -96,19 +94,64 @@ class GSMEngine:
             self.Zh, self.Xh, self.Gh = H(B, D, dev), H(B, D, dev), H(B, D, dev)
             self.slots = torch.zeros(8, dtype=torch.int32, device=dev)  # |X|, |G|, |Sigma_new| maxima (bit patterns)
             self.ws_u = torch.empty(L.workspace_bytes(L.WS_GSM_UPDATE_H3, B, D) // 4, dtype=torch.float32, device=dev)
+            self.ws_p = torch.empty(L.workspace_bytes(L.WS_POTRF_H3, B, D) // 4, dtype=torch.float32, device=dev)
+            L.potrf_h3(self.Sb, self.Lb, self.Lh, D, self.bad, self.ws_p, zero_upper=False)  # buffers start zeroed
             self.Sh.split_from(self.S)
-            self.Lh.split_from(self.Lb[:, :D], sqrt_mode=True, absmax=self.Sh.absmax)
         else:
+            L.potrf_check(self.Sb, self.Lb, D, self.bad, self.ws_p, npass)
             L.tf32_split(self.Sb, self.Shi, self.Slo, D, D)
             L.tf32_split(self.Lb, self.Lhi, self.Llo, D, D)
+        if int(self.bad.item()) != 0:
+            raise ValueError("initial covariance is not positive definite")
 
     def launches_per_step(self):
         """Kernels of libgsmvi_b200.so launched by one step (bench.py reports it as gpu_launches)."""
         panels = (self.D + 127) // 128
+        if self.h3:
+            potrf = 1 + panels + (panels - 1)  # prepare, panel kernels, left-looking update GEMMs
+            draw = 2 if self.z_tape is not None else 1  # |Z| max + split of a tape slice, or Philox written split
+            score = 3 if self.target is not None else 2  # split X, score GEMM, split G | |G| max + split G
+            upd = 5 + 1  # W GEMM, row pass, split T, covariance GEMM, axpy + split Sigma_new
+            return draw + 1 + score + upd + potrf + (3 if self.world > 1 else 0)
         potrf = 1 + panels + (panels - 1)  # tril copy, panel kernels, SYRK GEMMs
         upd = 4 + 2  # W GEMM, row pass, covariance GEMM, axpy + the two tf32_split launches (Sigma_new, L_new)
         return (0 if self.z_tape is not None else 1) + 1 + (1 if self.target is not None else 0) + upd + potrf + \
             (2 if self.world > 1 else 0)
+
+    def gemm_calls(self):
+        """The four batch-sized tensor-core launches of one step (sampler, score, W = G Sigma, covariance update) as
+        callables on the engine's current buffers; bench.py brackets each with CUDA events for the roofline figure."""
+        D, B, npass = self.D, self.B, self.npass
+        ldw = ld_of(D)
+        ws = self.ws_u
+        tgt = self.target
+        if self.h3:
+            off = (4 * B + 1) * ldw + 32
+            th = ws[off:].view(torch.float16)
+            Thi = th[: 3 * B * ldw].view(3 * B, ldw)
+            Tlo = th[3 * B * ldw: 6 * B * ldw].view(3 * B, ldw)
+            tscale = ws[(4 * B + 1) * ldw + 1: (4 * B + 1) * ldw + 2]
+            W = ws[: B * ldw].view(B, ldw)
+            Ta = L.HOperand.from_tensors(Thi[: 2 * B], Tlo[: 2 * B], tscale, 2 * B, D)
+            Tb = L.HOperand.from_tensors(Thi[B:], Tlo[B:], tscale, 2 * B, D)
+            return [
+                lambda: L.sample_h3(self.mu, self.Lh, self.Zh, self.Xb, None, B, D),
+                lambda: L.gauss_score_h3(self.Xh, tgt.Ph, tgt.c, self.Gb, None, B, D),
+                lambda: L.gemm_h3(self.Gh, self.Sh, W, B, D, D),
+                lambda: L.gemm_h3(Ta, Tb, self.Snb, D, D, 2 * B, a_mn=True, b_mn=True, alpha=-1.0 / self.batch_size,
+                                  beta=1.0, Cin=self.Sb, tri=True, mirror=True),
+            ]
+        W = ws[: B * ldw].view(B, ldw)
+        T = ws[B * ldw: 4 * B * ldw].view(3 * B, ldw)
+        Tlo = ws[4 * B * ldw: 7 * B * ldw].view(3 * B, ldw)
+        return [
+            lambda: L.sample(self.mu, self.Lhi, self.Zb, self.Xb, B, D, npass, L_lo=self.Llo),
+            lambda: L.gauss_score(self.Xb, tgt.Phib, tgt.c, self.Gb, B, D, npass, P_lo=tgt.Plob),
+            lambda: L.gemm_tf32(self.Gb[:, :D], self.Shi[:, :D], W[:, :D], B, D, D, npass=npass, B_lo=self.Slo[:, :D]),
+            lambda: L.gemm_tf32(T[: 2 * B, :D], T[B:, :D], self.Snb[:, :D], D, D, 2 * B, a_mn=True, b_mn=True,
+                                alpha=-1.0 / self.batch_size, beta=1.0, Cin=self.Sb[:, :D], tri=True, mirror=True,
+                                npass=npass, A_lo=Tlo[: 2 * B, :D], B_lo=Tlo[B:, :D]),
+        ]
 
     def step_h3(self, i):
         """One iteration on the scaled 3xFP16 engine (same sequence as `step`)."""
@@ -145,9 +188,8 @@ class GSMEngine:
             L.gsm_apply_stats(self.Sb, self.dSb, self.mu, self.dmu, self.Snb, self.mun, D)
             L.h3_absmax(self.Sn, D, D, sl[2:3])
         # ---- goodness check = Cholesky of the new covariance, reused as the next sampling factor (gsm.py:125)
-        L.potrf_check(self.Snb, self.Lnb, D, self.bad, self.ws_p, self.np_gemm)
+        L.potrf_h3(self.Snb, self.Lnb, self.Lnh, D, self.bad, self.ws_p, zero_upper=False)
         self.Snh.split_from(self.Sn, absmax=sl[2:3])  # queued before the flag is read: overlap the host round trip
-        self.Lnh.split_from(self.Lnb[:, :D], sqrt_mode=True, absmax=sl[2:3])  # |L_ij| <= sqrt(max Sigma_ii)
         ok = int(self.bad.item()) == 0  # the step's only device->host read (4 bytes)
         if ok:  # gsm.py:126-127
             self.Sb, self.Snb, self.S, self.Sn = self.Snb, self.Sb, self.Sn, self.S

@@ -31,6 +31,7 @@ extern "C" {
 #define GSMVI_WS_BAM_SOLVE 4
 #define GSMVI_WS_BAM_SOLVE_LOWRANK 5
 #define GSMVI_WS_GSM_UPDATE_H3 6
+#define GSMVI_WS_POTRF_H3 7
 
 /* One operand of the scaled 3xFP16 engine: fp16 arrays hi / lo (row-major, leading dimension ld in elements, a multiple
  * of 8) and the device float holding the power-of-two scale they were stored with (see gsmvi_h3_split). */
@@ -97,6 +98,13 @@ int gsmvi_gsm_update_h3(const float* X, long long ldx, const float* G, long long
  * np.linalg.cholesky) and the factorisation inside the sampler (gsmvi/gsm.py:119, gsmvi/bam.py:193). */
 int gsmvi_potrf_check(const float* Sigma, long long lds, float* L, long long ldl, int D, int* bad_flag,
                       void* workspace, int npass, void* stream);
+
+/* Same contract as gsmvi_potrf_check on the scaled 3xFP16 engine: left-looking panels (one long-K split-K update GEMM +
+ * one panel kernel each), L also written as the fp16 pair *L_split (scale from max |Sigma_ii|) for the sampler's and the
+ * later panels' TMA loads.  zero_upper = 0: the blocks above the diagonal are left untouched (valid for a buffer that
+ * was zeroed once).  workspace: gsmvi_workspace_bytes(GSMVI_WS_POTRF_H3, 0, D). */
+int gsmvi_potrf_h3(const float* Sigma, long long lds, float* L, long long ldl, const gsmvi_h3_operand* L_split, int D,
+                   int* bad_flag, void* workspace, int zero_upper, void* stream);
 
 /* Z[B,D] <- N(0,1), Philox4x32-10 keyed by seed, counter (element, offset).  Replaces the host RNG of
  * np.random.seed / np.random.multivariate_normal (gsmvi/gsm.py:117-119). */

@@ -86,6 +86,53 @@ def test_potrf_flags_bad_matrices(lib, D, kind):
     assert int(bad.item()) == 1
 
 
+@pytest.mark.parametrize("D", [1, 5, 10, 64, 128, 129, 200, 512, 1000, 2048, 4096])
+def test_potrf_h3_matches_cholesky(lib, D):
+    """Left-looking Cholesky on the scaled 3xFP16 engine: fp32 factor, its fp16 (hi, lo) split, zeroed upper blocks."""
+    rng = np.random.RandomState(D)
+    A = rng.normal(size=(D, D))
+    S = A @ A.T / D + 0.05 * np.eye(D)
+    Sb, Sv = padded(S)
+    Lb, Lv = padded(np.full((D, D), np.nan))
+    Lh = lib.HOperand(D, D, "cuda")
+    Lh.hi.fill_(float("nan")); Lh.lo.fill_(float("nan"))
+    bad = torch.ones(1, dtype=torch.int32, device="cuda")
+    ws = torch.empty(lib.workspace_bytes(lib.WS_POTRF_H3, 0, D) // 4, device="cuda")
+    for _ in range(2):  # second pass: epoch word and flag are reset by the call itself
+        lib.potrf_h3(Sb, Lb, Lh, D, bad, ws, zero_upper=True)
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
+    Lref = np.linalg.cholesky(Sv.cpu().double().numpy())
+    assert relF(Lv, Lref) < 2e-5
+    assert float(torch.triu(Lv, 1).abs().max()) == 0.0 if D > 1 else True
+    rec = Lv.cpu().double().numpy()
+    assert np.linalg.norm(rec @ rec.T - Sv.cpu().double().numpy()) / np.linalg.norm(S) < 5e-6
+    # the split reproduces L to 2^-22 of the row scale
+    deq = Lh.dequant()
+    assert float((deq - Lv).abs().max()) <= 2.0 ** -21 * float(Lv.abs().max())
+    record("potrf_h3", dict(D=D, relF_L=relF(Lv, Lref)))
+
+
+@pytest.mark.parametrize("D,kind", [(64, "indef"), (300, "indef"), (300, "nan"), (130, "late")])
+def test_potrf_h3_flags_bad_matrices(lib, D, kind):
+    rng = np.random.RandomState(1)
+    A = rng.normal(size=(D, D))
+    S = A @ A.T / D + 0.05 * np.eye(D)
+    if kind == "indef":
+        S = S - 2.0 * np.eye(D)
+    elif kind == "nan":
+        S[D // 2, D // 3] = S[D // 3, D // 2] = np.nan
+    else:  # negative pivot only in the last panel
+        S[D - 1, D - 1] = -1.0
+    Sb, _ = padded(S)
+    Lb, _ = padded(np.zeros((D, D)))
+    Lh = lib.HOperand(D, D, "cuda")
+    bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ws = torch.empty(lib.workspace_bytes(lib.WS_POTRF_H3, 0, D) // 4, device="cuda")
+    lib.potrf_h3(Sb, Lb, Lh, D, bad, ws)
+    assert int(bad.item()) == 1
+
+
 def test_philox_normal_moments_and_determinism(lib):
     B, D = 512, 1000
     Zb, Z = padded(np.zeros((B, D)))

@@ -17,3 +17,15 @@ for _ in range(10):
     L.potrf_check(S, Lo, D, bad, ws)
 e.record(); torch.cuda.synchronize()
 print("potrf D=%d: %.3f ms per factorisation" % (D, s.elapsed_time(e) / 10))
+
+Lh = L.HOperand(D, D, "cuda")
+ws3 = torch.empty(L.workspace_bytes(L.WS_POTRF_H3, 0, D) // 4, device="cuda")
+Lo3 = torch.zeros(D, D, device="cuda")
+for _ in range(3):
+    L.potrf_h3(S, Lo3, Lh, D, bad, ws3, zero_upper=False)
+torch.cuda.synchronize(); print("h3 ok", int(bad.item()), float((Lo3 - Lo).abs().max()))
+s.record()
+for _ in range(10):
+    L.potrf_h3(S, Lo3, Lh, D, bad, ws3, zero_upper=False)
+e.record(); torch.cuda.synchronize()
+print("potrf_h3 D=%d: %.3f ms per factorisation" % (D, s.elapsed_time(e) / 10))

@@ -1,0 +1,22 @@
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gsm-vi_b200"))
+import torch
+from gsmvi_b200 import _lib as L
+D = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+g = torch.Generator().manual_seed(0)
+A = torch.randn(D, D, generator=g).cuda(); S = A @ A.t() / D + 0.1 * torch.eye(D, device="cuda")
+bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+Lh = L.HOperand(D, D, "cuda")
+ws3 = torch.empty(L.workspace_bytes(L.WS_POTRF_H3, 0, D) // 4, device="cuda")
+Lo3 = torch.zeros(D, D, device="cuda")
+for _ in range(2):
+    L.potrf_h3(S, Lo3, Lh, D, bad, ws3, zero_upper=False)
+torch.cuda.synchronize(); print("h3 ok", int(bad.item()))
+s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+s.record()
+for _ in range(reps):
+    L.potrf_h3(S, Lo3, Lh, D, bad, ws3, zero_upper=False)
+e.record(); torch.cuda.synchronize()
+print("potrf_h3 D=%d: %.3f ms per factorisation" % (D, s.elapsed_time(e) / reps))

@@ -60,22 +60,65 @@ __device__ __forceinline__ void tile4x4_mac(const float* __restrict__ Arows, int
 
 // Forward substitution of one row against a 32 x 32 lower-triangular block, right-looking so that the dependent chain
 // per column is one multiply and one FMA:  x_j = v_j / l_jj;  v_k -= x_j l_kj (k > j).  dT holds the block TRANSPOSED
-// (dT[j * DT + k] = l_kj) so the column below the pivot is read as broadcast float4s.
-__device__ __forceinline__ void row_solve32(float (&v)[32], const float* __restrict__ dT, const float* __restrict__ dinv) {
+// (dT[j * DT + k] = l_kj) so the column below the pivot is read as broadcast float4s.  Fully unrolled (a rolled variant
+// with rotated registers measured 40% slower); the solved row is written to out_row[0..31].
+// Warp Cholesky of the 32 x 32 block whose row `lane` starts at myrow (shared memory).
+__device__ __forceinline__ void chol32_smem(float* __restrict__ myrow, int lane, float* __restrict__ dT,
+                                         float* __restrict__ dinv_out, int* __restrict__ bad) {
+  float row[32];
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(myrow + k);
+    row[k] = t.x; row[k + 1] = t.y; row[k + 2] = t.z; row[k + 3] = t.w;
+  }
+  int isbad = 0;
+  chol32_rolled(row, lane, myrow, dT, DT, dinv_out, isbad);
+  if (isbad && lane == 0) *bad = 1;
+}
+
+// Inlined on purpose: every CTA runs this code once per launch from a cold instruction cache, and fall-through code is
+// prefetched while the first call of an out-of-line copy measured 11-12k cycles (one full miss per 128-byte line).
+template <int COPY>
+__device__ __forceinline__ void row_solve32(float* __restrict__ row_io, const float* __restrict__ dT,
+                                         const float* __restrict__ dinv) {
+  float v[32];
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(row_io + k);
+    v[k] = t.x; v[k + 1] = t.y; v[k + 2] = t.z; v[k + 3] = t.w;
+  }
+  float* out_row = row_io;
+  // software-pipelined: the pivot column j+1 (and its 1/l) is loaded while column j is applied, so the in-order warp
+  // never waits on a shared-memory load inside the dependent chain
+  float4 lc[8];
+  float di = dinv[0];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) lc[g] = *reinterpret_cast<const float4*>(dT + 4 * g);
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    const float x = v[j] * dinv[j];
-    v[j] = x;
-    const float* col = dT + j * DT;
+    float4 ln[8];
+    float dn = 0.0f;
+    if (j + 1 < 32) {
+      dn = dinv[j + 1];
 #pragma unroll
-    for (int k = (j + 1) & ~3; k < 32; k += 4) {
-      const float4 l = *reinterpret_cast<const float4*>(col + k);
-      if (k + 0 > j) v[k + 0] -= x * l.x;
-      if (k + 1 > j) v[k + 1] -= x * l.y;
-      if (k + 2 > j) v[k + 2] -= x * l.z;
-      if (k + 3 > j) v[k + 3] -= x * l.w;
+      for (int g = (j + 2) / 4; g < 8; ++g) ln[g] = *reinterpret_cast<const float4*>(dT + (j + 1) * DT + 4 * g);
     }
+    const float x = v[j] * di;
+    v[j] = x;
+#pragma unroll
+    for (int g = (j + 1) / 4; g < 8; ++g) {
+      const int k = 4 * g;
+      if (k + 0 > j) v[k + 0] -= x * lc[g].x;
+      if (k + 1 > j) v[k + 1] -= x * lc[g].y;
+      if (k + 2 > j) v[k + 2] -= x * lc[g].z;
+      if (k + 3 > j) v[k + 3] -= x * lc[g].w;
+    }
+    di = dn;
+#pragma unroll
+    for (int g = (j + 2) / 4; g < 8; ++g) lc[g] = ln[g];
   }
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(out_row + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
 }
 
 // one 16-byte group of a finished row of L: fp32 store + the fp16 pair
@@ -104,7 +147,8 @@ __global__ void __launch_bounds__(256) potrf_prepare_kernel(const float* __restr
   if (threadIdx.x == 0) {
     for (int w = 1; w < 8; ++w) m = max(m, smax[w]);
     *scale_l = h3_scale_from_absmax(m, 1);
-    *ready = 0u;
+    ready[0] = 0u;  // panel epochs
+    ready[1] = 0u;  // helper CTA count
     *flag = 0;
   }
 }
@@ -124,8 +168,8 @@ __global__ void potrf_zero_upper_kernel(float* __restrict__ L, long long ldl, __
 }
 
 // optional phase timing of one panel (GSMVI_POTRF_TIMING=1): clock64 stamps of CTA 0 / CTA 1, read back by the host
-__device__ long long g_pt3[32];
-#define PT3(i) do { if (a.timing && threadIdx.x == 0) g_pt3[i] = clock64(); } while (0)
+__device__ long long g_pt3[64];
+#define PT3(i) do { if (TIMING && threadIdx.x == 0) g_pt3[i] = clock64(); } while (0)
 
 struct PanelArgs {
   const float* A;
@@ -143,7 +187,13 @@ struct PanelArgs {
   int* flag;
   unsigned* ready;
   unsigned epoch_base;  // this panel publishes epoch_base + 1 .. epoch_base + 7
-  int timing;
+  // helpers: the first `helpers` TRSM CTAs (0 or 16) each reduce 8 rows of A11 - sum P into d0 [128][128] before their own
+  // rows and bump *helper_count; CTA 0 starts from d0 once the count reaches helper_target (16 CTAs' worth of loads in
+  // flight instead of one's)
+  float* d0;
+  unsigned* helper_count;
+  unsigned helper_target;
+  int helpers;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -165,99 +215,142 @@ __device__ __forceinline__ void wait_epoch(const unsigned* ready, unsigned targe
 // Epochs of one panel (relative to epoch_base): 2p+1 = diagonal block p factored and stored, 2p+2 = the rows below it in
 // block-column p solved and stored.  A TRSM CTA needs 2J for the block-update of its stage J and 2J+1 for the in-block
 // substitution, so only that last substitution trails CTA 0.
-__global__ void __launch_bounds__(256, 2) potrf_panel_h3_kernel(const PanelArgs a) {
-  extern __shared__ __align__(16) float sm[];
+// FULL: nb == 128 (every panel but a ragged last one, which has no rows below it and runs as a single CTA).
+// The straight-line parts are kept small on purpose: each CTA runs this code once per launch with a cold instruction
+// cache, and an earlier fully unrolled version (10.8k SASS instructions) spent more time fetching than computing.
+template <bool FULL, bool TIMING>
+__global__ void __launch_bounds__(256, 1) potrf_panel_h3_kernel(const PanelArgs a) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  // [1 KiB-aligned: tf32 hi | lo operand tiles of CTA 0's tensor-core update, 96 x 128 B each] then the fp32 arrays.  The
+  // MMA (M = 128) reads 32 rows past each 96-row tile: those land in the lo tile / in s (ignored accumulator rows).
+  const uint32_t pt_addr = (ptx::smem_u32(sm_raw) + 1023u) & ~1023u;
+  float* sm = reinterpret_cast<float*>(sm_raw + (pt_addr - ptx::smem_u32(sm_raw)) + 2 * 12288);
   float* s = sm;                   // [NB][DS]   diagonal block (CTA 0) / published block-rows of L11 (TRSM CTAs)
   float* at = sm + NB * DS;        // [RPC][DS]  TRSM CTAs: their rows of the panel
   float* dT = at + RPC * DS;       // [32][DT]   current 32 x 32 diagonal block, transposed
-  __shared__ float dinv[NB];
+  __shared__ float dinv[32];
   __shared__ int bad;
+  __shared__ __align__(8) unsigned long long mma_bar;
+  __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int j0 = a.j0, nb = a.nb, n = a.n;
   const float sl = *a.scale_l;
-  const bool full = (nb == NB);
   if (tid == 0) bad = 0;
 
   if (blockIdx.x == 0) {
     // ------------------------------------------------------------------ diagonal block
     PT3(0);
+    const uint32_t bar_addr = ptx::smem_u32(&mma_bar);
+    if (warp == 0) {  // tensor-core trailing update below: 128 TMEM columns and one mbarrier
+      ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), 128);
+      ptx::tmem_relinquish();
+      if (lane == 0) {
+        ptx::mbar_init(bar_addr, 1);
+        ptx::fence_mbar_init();
+      }
+    }
     const float* a11 = a.A + static_cast<long long>(j0) * a.lda + j0;
-    if (full) {
-      // A11 - sum of the update partials, lower-triangle 16-byte groups only: 2112 groups, compactly enumerated (row i has
-      // i/4 + 1 groups), eight per thread with all loads of a split issued before any is consumed
-      constexpr int NG = 2112;
-      float4 v[9];
-      int gi[9], gj[9];
+    if (FULL) {
+      // lower-triangle 16-byte groups only: 2112 groups, compactly enumerated (rows 4b .. 4b+3 hold b+1 groups each,
+      // 2 b (b+1) groups precede them), nine per thread
+      constexpr int NG = 2112, PER = 9;
+      float4 v[PER];
+      int off_s[PER];  // (row << 8) | first column; -1: no group
 #pragma unroll
-      for (int e = 0; e < 9; ++e) {
+      for (int e = 0; e < PER; ++e) {
         const int g = tid + e * 256;
-        // row i = 4 b + r holds groups [2 b (b+1) + r (b+1), ...): invert with b = floor((sqrt(1 + 2 g) - 1) / 2) then fix up
         int b = static_cast<int>((sqrtf(1.0f + 2.0f * g) - 1.0f) * 0.5f);
-        while (2 * (b + 1) * (b + 2) <= g) ++b;
-        while (2 * b * (b + 1) > g) --b;
+        b += (2 * (b + 1) * (b + 2) <= g) ? 1 : 0;
+        b -= (2 * b * (b + 1) > g) ? 1 : 0;
         const int rem = g - 2 * b * (b + 1);
-        gi[e] = 4 * b + rem / (b + 1);
-        gj[e] = 4 * (rem % (b + 1));
-        v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g < NG) v[e] = *reinterpret_cast<const float4*>(a11 + static_cast<long long>(gi[e]) * a.lda + gj[e]);
+        const int rr = (rem >= b + 1) + (rem >= 2 * (b + 1)) + (rem >= 3 * (b + 1));
+        const int gi = 4 * b + rr, gj = 4 * (rem - rr * (b + 1));
+        off_s[e] = (g < NG) ? ((gi << 8) | gj) : -1;
       }
-      for (int sp = 0; sp < a.splits; ++sp) {
-        const float* pb = a.partials + sp * a.split_stride;
-        float4 pv[9];
-#pragma unroll
-        for (int e = 0; e < 9; ++e) {
-          pv[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (tid + e * 256 < NG) pv[e] = *reinterpret_cast<const float4*>(pb + gi[e] * NB + gj[e]);
+      if (a.helpers > 0) {
+        // the helper CTAs have formed A11 - sum P in d0: wait for all of them, then one round of loads
+        if (tid == 0) {
+          const long long t0 = clock64();
+          while (static_cast<int>(ld_acquire_u32(a.helper_count) - a.helper_target) < 0) {
+            if (clock64() - t0 > 4000000000LL) { printf("gsmvi: potrf helper watchdog (j0=%d)\n", j0); __trap(); }
+          }
         }
+        __syncthreads();
 #pragma unroll
-        for (int e = 0; e < 9; ++e) { v[e].x -= pv[e].x; v[e].y -= pv[e].y; v[e].z -= pv[e].z; v[e].w -= pv[e].w; }
+        for (int e = 0; e < PER; ++e) {
+          v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (off_s[e] >= 0) v[e] = __ldcg(reinterpret_cast<const float4*>(a.d0 + (off_s[e] >> 8) * NB + (off_s[e] & 255)));
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+          v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (off_s[e] >= 0) v[e] = *reinterpret_cast<const float4*>(a11 + static_cast<long long>(off_s[e] >> 8) * a.lda + (off_s[e] & 255));
+        }
+#pragma unroll 1
+        for (int sp = 0; sp < a.splits; ++sp) {
+          const float* pb = a.partials + sp * a.split_stride;
+          float4 pv[PER];
+#pragma unroll
+          for (int e = 0; e < PER; ++e) {
+            pv[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (off_s[e] >= 0) pv[e] = *reinterpret_cast<const float4*>(pb + (off_s[e] >> 8) * NB + (off_s[e] & 255));
+          }
+#pragma unroll
+          for (int e = 0; e < PER; ++e) { v[e].x -= pv[e].x; v[e].y -= pv[e].y; v[e].z -= pv[e].z; v[e].w -= pv[e].w; }
+        }
       }
 #pragma unroll
-      for (int e = 0; e < 9; ++e)
-        if (tid + e * 256 < NG) {
+      for (int e = 0; e < PER; ++e)
+        if (off_s[e] >= 0) {
+          const int gi = off_s[e] >> 8, gj = off_s[e] & 255;
           float4 t = v[e];
-          if (gj[e] + 1 > gi[e]) t.y = 0.f;
-          if (gj[e] + 2 > gi[e]) t.z = 0.f;
-          if (gj[e] + 3 > gi[e]) t.w = 0.f;
-          *reinterpret_cast<float4*>(s + gi[e] * DS + gj[e]) = t;
+          if (gj + 1 > gi) t.y = 0.f;
+          if (gj + 2 > gi) t.z = 0.f;
+          if (gj + 3 > gi) t.w = 0.f;
+          *reinterpret_cast<float4*>(s + gi * DS + gj) = t;
         }
     } else {
+#pragma unroll 1
       for (int q = tid; q < NB * 32; q += 256) {
         const int i = q >> 5, j4 = (q & 31) * 4;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (i < nb && j4 <= i) {
-          for (int t = 0; t < 4; ++t)
-            if (j4 + t < nb) v[t] = a11[static_cast<long long>(i) * a.lda + j4 + t];
-          for (int sp = 0; sp < a.splits; ++sp) {
-            const float4 p = *reinterpret_cast<const float4*>(a.partials + sp * a.split_stride + static_cast<long long>(i) * NB + j4);
-            v[0] -= p.x; v[1] -= p.y; v[2] -= p.z; v[3] -= p.w;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int j = j4 + t;
+          if (i < nb && j <= i) {
+            float x = a11[static_cast<long long>(i) * a.lda + j];
+            for (int sp = 0; sp < a.splits; ++sp) x -= a.partials[sp * a.split_stride + static_cast<long long>(i) * NB + j];
+            v[t] = x;
+          } else if (i >= nb && j == i) {
+            v[t] = 1.0f;  // identity padding of the ragged last panel
           }
         }
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-          if (j4 + t > i) v[t] = 0.f;
-        if (i >= nb && j4 <= i && i < j4 + 4) v[i - j4] = 1.0f;  // identity padding of a ragged last panel
         *reinterpret_cast<float4*>(s + i * DS + j4) = make_float4(v[0], v[1], v[2], v[3]);
       }
     }
+    ptx::tc_fence_before_sync();
     __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
     PT3(1);
     float* l11 = a.L + static_cast<long long>(j0) * a.ldl + j0;
     __half* h11 = a.Lhi + static_cast<long long>(j0) * a.ldh + j0;
     __half* o11 = a.Llo + static_cast<long long>(j0) * a.ldh + j0;
-    // rows [i_lo, i_hi) x 16-byte column groups [g_lo, g_hi) of the block in smem -> L (fp32 + fp16 pair), by the 128 threads
-    // of warps 4..7; groups right of the diagonal block are written as zeros (upper triangle)
+    // rows [i_lo, i_hi) x 16-byte column groups [g_lo, g_hi) of the block in smem -> L (fp32 + fp16 pair), by the publisher
+    // warp; groups from column zero_from_col on are written as zeros (upper triangle)
     auto store_rect = [&](int i_lo, int i_hi, int g_lo, int g_hi, int zero_from_col) {
       const int gw = g_hi - g_lo;
-      for (int q = tid - 128; q < (i_hi - i_lo) * gw; q += 128) {
+#pragma unroll 2
+      for (int q = lane; q < (i_hi - i_lo) * gw; q += 32) {
         const int i = i_lo + q / gw, j4 = 4 * (g_lo + q % gw);
-        if (i >= nb) continue;
-        float4 t = (j4 >= zero_from_col) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(s + i * DS + j4);
-        if (full) {
+        const float4 t = (j4 >= zero_from_col) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(s + i * DS + j4);
+        if (FULL) {
           store_l4(l11 + static_cast<long long>(i) * a.ldl, h11 + static_cast<long long>(i) * a.ldh,
                    o11 + static_cast<long long>(i) * a.ldh, j4, t, sl);
-        } else {
+        } else if (i < nb) {
           const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
           for (int u = 0; u < 4; ++u)
             if (j4 + u < nb) {
               l11[static_cast<long long>(i) * a.ldl + j4 + u] = tv[u];
@@ -266,107 +359,150 @@ __global__ void __launch_bounds__(256, 2) potrf_panel_h3_kernel(const PanelArgs 
         }
       }
     };
-    for (int p = 0; p < NB / 32; ++p) {
-      const int c0 = 32 * p;
-      // ---- (1) 32 x 32 diagonal block: warp 0, row `lane` in registers; also leaves the block transposed in dT
-      if (warp == 0) {
-        float row[32];
-#pragma unroll
-        for (int k = 0; k < 32; k += 4) {
-          const float4 t = *reinterpret_cast<const float4*>(s + (c0 + lane) * DS + c0 + k);
-          row[k] = t.x; row[k + 1] = t.y; row[k + 2] = t.z; row[k + 3] = t.w;
-        }
-        int isbad = 0;
-        chol32_b8(row, lane, dinv + c0, isbad);
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float v = (k <= lane) ? row[k] : 0.0f;
-          row[k] = v;
-          dT[k * DT + lane] = v;
-        }
-#pragma unroll
-        for (int k = 0; k < 32; k += 4)
-          *reinterpret_cast<float4*>(s + (c0 + lane) * DS + c0 + k) = make_float4(row[k], row[k + 1], row[k + 2], row[k + 3]);
-        if (isbad && lane == 0) bad = 1;
-      }
-      __syncthreads();
-      PT3(2 + 4 * p);
-      // ---- (2) warps 1..3: rows below, x L_pp^T = a, one thread per row (right-looking substitution);
-      //      warps 4..7: store the finished diagonal block (and the zeros to its right) and publish it
-      if (warp >= 4) {
+    // Warp roles from here on: warps 0..6 compute (barrier 2, 224 threads); warp 7 is the publisher - it writes finished
+    // parts of L11 to global memory and releases the epochs, asynchronously to the factorisation (the data it reads is
+    // final and never rewritten).  "Ready" events use one named barrier each (3 + event): 224 arrivals + the publisher.
+    constexpr int NCOMP = 224;
+    if (warp == 7) {
+#pragma unroll 1
+      for (int p = 0; p < NB / 32; ++p) {
+        const int c0 = 32 * p;
+        named_bar_sync(3 + 2 * p, 256);  // diagonal block p factored
         store_rect(c0, c0 + 32, c0 / 4, NB / 4, c0 + 32);
-        named_bar_sync(1, 128);
-        if (tid == 255) {
+        __syncwarp();
+        if (lane == 0) {
           __threadfence();
           st_release_u32(a.ready, a.epoch_base + 2 * p + 1);
         }
-      } else if (tid >= c0 + 32) {
-        float v[32];
-#pragma unroll
-        for (int k = 0; k < 32; k += 4) {
-          const float4 t = *reinterpret_cast<const float4*>(s + tid * DS + c0 + k);
-          v[k] = t.x; v[k + 1] = t.y; v[k + 2] = t.z; v[k + 3] = t.w;
-        }
-        row_solve32(v, dT, dinv + c0);
-#pragma unroll
-        for (int k = 0; k < 32; k += 4)
-          *reinterpret_cast<float4*>(s + tid * DS + c0 + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-      }
-      PT3(3 + 4 * p);
-      if (p == NB / 32 - 1) break;
-      __syncthreads();
-      PT3(4 + 4 * p);
-      // ---- (3) warps 4..7 first store the solved rows of block-column p and publish them; then everyone applies the
-      //      trailing update S[i][k] -= sum_c P[i][c] P[k][c] on the lower triangle of the (NB-c0-32)^2 block in
-      //      interleaved 4x4 register tiles (neighbouring lanes read neighbouring rows: conflict-free float4 loads).
-      //      Tile (ti, tj) holds rows ti + r*mt and columns tj + c*mt: entries with c > r are above the diagonal (never
-      //      formed), c < r below it, c == r below or on it iff tj <= ti.
-      if (warp >= 4) {
+        if (p == NB / 32 - 1) break;
+        named_bar_sync(4 + 2 * p, 256);  // rows below it solved
         store_rect(c0 + 32, NB, c0 / 4, c0 / 4 + 8, NB);
-        named_bar_sync(1, 128);
-        if (tid == 255) {
+        __syncwarp();
+        if (lane == 0) {
           __threadfence();
           st_release_u32(a.ready, a.epoch_base + 2 * p + 2);
         }
       }
-      const int m0 = c0 + 32, mt = (NB - m0) / 4;  // mt = 24, 16, 8
-      for (int t = tid; t < mt * mt; t += 256) {
-        const int ti = t % mt, tj = t / mt;
-        const float* Ar = s + (m0 + ti) * DS;
-        const float* Br = s + (m0 + tj) * DS;
-        float acc[4][4] = {};
-#pragma unroll 2
-        for (int k = c0; k < c0 + 32; k += 4) {
-          float4 av[4], bv[4];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) av[r] = *reinterpret_cast<const float4*>(Ar + r * mt * DS + k);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) bv[c] = *reinterpret_cast<const float4*>(Br + c * mt * DS + k);
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c <= r; ++c)
-              acc[r][c] += av[r].x * bv[c].x + av[r].y * bv[c].y + av[r].z * bv[c].z + av[r].w * bv[c].w;
+    } else {
+#pragma unroll 1
+      for (int p = 0; p < NB / 32; ++p) {
+        const int c0 = 32 * p;
+        // ---- (1) 32 x 32 diagonal block: warp 0, row `lane` in registers; leaves it in s and, transposed, in dT
+        if (warp == 0) chol32_smem(s + (c0 + lane) * DS + c0, lane, dT, dinv, &bad);
+        named_bar_sync(2, NCOMP);
+        asm volatile("bar.arrive %0, %1;" ::"r"(3 + 2 * p), "r"(256) : "memory");
+        PT3(2 + 4 * p);
+        if (p == NB / 32 - 1) break;
+        // ---- (2) rows below: x L_pp^T = a, one thread per row (right-looking substitution)
+        if (tid >= c0 + 32 && tid < NB) row_solve32<0>(s + tid * DS + c0, dT, dinv);
+        PT3(3 + 4 * p);
+        named_bar_sync(2, NCOMP);
+        asm volatile("bar.arrive %0, %1;" ::"r"(4 + 2 * p), "r"(256) : "memory");
+        PT3(4 + 4 * p);
+        // ---- (3) trailing update of the lower triangle of the (NB-c0-32)^2 block on the tensor core:
+        //      S[i][k] -= sum_c P[i][c] P[k][c] with P = the solved slab (rows m0.., columns c0..c0+31), as three tf32 MMAs
+        //      (hi*hi + lo*hi + hi*lo: fp32-grade products, K = 32) into TMEM: every thread splits its share of P into the
+        //      swizzled K-major operand tiles, one thread issues, warps 0..3 drain their rows of the accumulator into s.
+        const int m0 = c0 + 32, R = NB - m0;  // R = 96, 64, 32 rows (and columns) left
+#pragma unroll 1
+        for (int q = tid; q < R * 8; q += NCOMP) {
+          const int r = q >> 3, ch = q & 7;
+          const float4 v = *reinterpret_cast<const float4*>(s + (m0 + r) * DS + c0 + 4 * ch);
+          float4 hi, lo;
+          hi.x = ptx::to_tf32(v.x); lo.x = ptx::to_tf32(v.x - hi.x);
+          hi.y = ptx::to_tf32(v.y); lo.y = ptx::to_tf32(v.y - hi.y);
+          hi.z = ptx::to_tf32(v.z); lo.z = ptx::to_tf32(v.z - hi.z);
+          hi.w = ptx::to_tf32(v.w); lo.w = ptx::to_tf32(v.w - hi.w);
+          const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);  // SWIZZLE_128B
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pt_addr + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pt_addr + 12288 + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
         }
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before_sync();
+        named_bar_sync(2, NCOMP);
+        if (tid == 0) {
+          ptx::tc_fence_after_sync();
+          // c_format F32, a/b TF32, both K-major, N = R, M = 128 (rows beyond R hold stale data: their outputs are ignored)
+          const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(R >> 3) << 17) | (8u << 24);
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t dh = make_smem_desc(pt_addr + kk * 32, 16, 1024, 2);
+            const uint64_t dl = make_smem_desc(pt_addr + 12288 + kk * 32, 16, 1024, 2);
+            ptx::umma_tf32(tmem_base, dh, dh, idesc, kk > 0 ? 1u : 0u);
+            ptx::umma_tf32(tmem_base, dl, dh, idesc, 1u);
+            ptx::umma_tf32(tmem_base, dh, dl, idesc, 1u);
+          }
+          ptx::umma_commit(bar_addr);
+        }
+        if (warp < 4 && 32 * warp < R) {
+          ptx::mbar_wait(bar_addr, p & 1);
+          ptx::tc_fence_after_sync();
+          const int r = 32 * warp + lane;  // accumulator row (TMEM lane quadrant = warp) = row m0 + r of the block
+#pragma unroll 1
+          for (int col0 = 0; col0 <= 32 * warp + 16; col0 += 16) {  // chunks of 16 columns up to the diagonal
+            uint32_t t[16];
+            ptx::tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(32 * warp) << 16) + col0, t);
+            ptx::tmem_ld_wait();
+            float* dst = s + (m0 + r) * DS + m0 + col0;
 #pragma unroll
-          for (int c = 0; c <= r; ++c)
-            if (c < r || tj <= ti) s[(m0 + ti + r * mt) * DS + m0 + tj + c * mt] -= acc[r][c];
+            for (int u = 0; u < 16; u += 4) {
+              if (col0 + u <= r) {
+                float4 o = *reinterpret_cast<float4*>(dst + u);
+                o.x -= __uint_as_float(t[u]);
+                if (col0 + u + 1 <= r) o.y -= __uint_as_float(t[u + 1]);
+                if (col0 + u + 2 <= r) o.z -= __uint_as_float(t[u + 2]);
+                if (col0 + u + 3 <= r) o.w -= __uint_as_float(t[u + 3]);
+                *reinterpret_cast<float4*>(dst + u) = o;
+              }
+            }
+          }
+          ptx::tc_fence_before_sync();
+        }
+        named_bar_sync(2, NCOMP);
+        PT3(5 + 4 * p);
       }
-      __syncthreads();
-      PT3(5 + 4 * p);
     }
     __syncthreads();
+    if (warp == 0) {
+      ptx::tc_fence_after_sync();
+      ptx::tmem_dealloc(tmem_base, 128);
+    }
     if (tid == 0 && bad) atomicOr(a.flag, 1);
     PT3(18);
     return;
   }
 
-  // -------------------------------------------------------------------- TRSM rows (nb == NB whenever rows below exist)
-  const int r0 = j0 + NB + (blockIdx.x - 1) * RPC;
-  const int rows = min(RPC, n - r0);
+  if (!FULL) return;
+  // -------------------------------------------------------------------- TRSM rows (only full panels have rows below)
   if (blockIdx.x == 1) PT3(20);
+  if (static_cast<int>(blockIdx.x) <= a.helpers) {
+    // helper: rows 8 (blockIdx.x - 1) .. +7 of the diagonal block, A11 - sum P, one 16-byte group per thread, all loads in flight
+    const int i = 8 * (blockIdx.x - 1) + (tid >> 5), j4 = (tid & 31) * 4;
+    if (j4 <= i) {
+      float4 v = *reinterpret_cast<const float4*>(a.A + static_cast<long long>(j0 + i) * a.lda + j0 + j4);
+      float4 pv[MAX_SPLITS];
+#pragma unroll
+      for (int sp = 0; sp < MAX_SPLITS; ++sp) {
+        pv[sp] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sp < a.splits) pv[sp] = *reinterpret_cast<const float4*>(a.partials + sp * a.split_stride + static_cast<long long>(i) * NB + j4);
+      }
+#pragma unroll
+      for (int sp = 0; sp < MAX_SPLITS; ++sp) { v.x -= pv[sp].x; v.y -= pv[sp].y; v.z -= pv[sp].z; v.w -= pv[sp].w; }
+      *reinterpret_cast<float4*>(a.d0 + i * NB + j4) = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(a.helper_count, 1u);
+    }
+  }
+  // one CTA per SM (the spin-waits need every CTA resident): a CTA takes row blocks blockIdx.x - 1, + gridDim.x - 1, ...
+  // of 32 rows; from its second block on the epochs it waits for have already been published
+  const int nblocks = (n - j0 - NB + RPC - 1) / RPC;
+#pragma unroll 1
+  for (int rb = blockIdx.x - 1; rb < nblocks; rb += gridDim.x - 1) {
+  const int r0 = j0 + NB + rb * RPC;
+  const int rows = min(RPC, n - r0);
   {
     // this CTA's rows of A21 - sum of the update partials (four 16-byte groups per thread), while CTA 0 factors
     const float* a21 = a.A + static_cast<long long>(r0) * a.lda + j0;
@@ -377,6 +513,7 @@ __global__ void __launch_bounds__(256, 2) potrf_panel_h3_kernel(const PanelArgs 
       v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i < rows) v[e] = *reinterpret_cast<const float4*>(a21 + static_cast<long long>(i) * a.lda + j4);
     }
+#pragma unroll 1
     for (int sp = 0; sp < a.splits; sp += 2) {
       float4 pv[8];
 #pragma unroll
@@ -409,6 +546,7 @@ __global__ void __launch_bounds__(256, 2) potrf_panel_h3_kernel(const PanelArgs 
       // block-update with the finished block-columns I < J of block-row J (final once step J-1's rows are published)
       wait_epoch(a.ready, a.epoch_base + 2 * J, j0);
       const int ncol4 = 8 * J;
+#pragma unroll 1
       for (int q = tid; q < 32 * ncol4; q += 256) {
         const int i = 32 * J + q / ncol4, j4 = (q % ncol4) * 4;
         *reinterpret_cast<float4*>(s + i * DS + j4) = __ldcg(reinterpret_cast<const float4*>(l11 + static_cast<long long>(i) * a.ldl + j4));
@@ -456,40 +594,32 @@ __global__ void __launch_bounds__(256, 2) potrf_panel_h3_kernel(const PanelArgs 
       if (jj <= k && k < jj + 4) dinv[k] = 1.0f / (k == jj ? t.x : k == jj + 1 ? t.y : k == jj + 2 ? t.z : t.w);
     }
     __syncthreads();
-    if (tid < RPC) {  // in-block forward substitution, one thread per row
-      float v[32];
-      float* r = at + tid * DS + 32 * J;
-#pragma unroll
-      for (int k = 0; k < 32; k += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(r + k);
-        v[k] = t.x; v[k + 1] = t.y; v[k + 2] = t.z; v[k + 3] = t.w;
-      }
-      row_solve32(v, dT, dinv);
-#pragma unroll
-      for (int k = 0; k < 32; k += 4)
-        *reinterpret_cast<float4*>(r + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-    }
+    if (tid < RPC) row_solve32<1>(at + tid * DS + 32 * J, dT, dinv);  // in-block forward substitution, one thread per row
     __syncthreads();
   }
   if (blockIdx.x == 1) PT3(23);
   float* l21 = a.L + static_cast<long long>(r0) * a.ldl + j0;
   __half* h21 = a.Lhi + static_cast<long long>(r0) * a.ldh + j0;
   __half* o21 = a.Llo + static_cast<long long>(r0) * a.ldh + j0;
+#pragma unroll 1
   for (int q = tid; q < RPC * 32; q += 256) {
     const int i = q >> 5, j4 = (q & 31) * 4;
     if (i < rows)
       store_l4(l21 + static_cast<long long>(i) * a.ldl, h21 + static_cast<long long>(i) * a.ldh,
                o21 + static_cast<long long>(i) * a.ldh, j4, *reinterpret_cast<const float4*>(at + i * DS + j4), sl);
   }
+  __syncthreads();
+  }  // row blocks
   if (blockIdx.x == 1) PT3(24);
 }
 
-constexpr int PANEL_SMEM = (NB * DS + RPC * DS + 32 * DT) * static_cast<int>(sizeof(float));
+// fp32 arrays + the two 96 x 128 B swizzled tf32 operand tiles of CTA 0's tensor-core update (1 KiB alignment slack)
+constexpr int PANEL_SMEM = (NB * DS + RPC * DS + 32 * DT) * static_cast<int>(sizeof(float)) + 2 * 12288 + 1024;
 
 }  // namespace
 
 size_t potrf_h3_workspace_bytes(int n) {
-  // 256 bytes of scalars (epoch word) + split-K partials: at most MAX_SPLITS x rows x 128 with splits*tiles <= ~148+8
+  // 256 bytes of scalars (epoch word, helper counter) + the helpers' reduced diagonal block [128][128] + split-K partials: at most MAX_SPLITS x rows x 128 with splits*tiles <= ~148+8
   const long long rows = n > 0 ? n : 1;
   long long worst = 0;
   for (long long j0 = NB; j0 < rows; j0 += NB) {
@@ -500,7 +630,7 @@ size_t potrf_h3_workspace_bytes(int n) {
     if (S > j0 / H3_BK) S = j0 / H3_BK;
     if (S * M > worst) worst = S * M;
   }
-  return 256 + static_cast<size_t>(worst) * NB * sizeof(float);
+  return 256 + static_cast<size_t>(NB) * NB * sizeof(float) + static_cast<size_t>(worst) * NB * sizeof(float);
 }
 
 int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long long ldl, const gsmvi_h3_operand& Lh, int n,
@@ -510,18 +640,29 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
     return GSMVI_EALIGN;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(potrf_panel_h3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(potrf_panel_h3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_panel_h3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_panel_h3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
   unsigned* ready = static_cast<unsigned*>(workspace);
-  float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
+  float* d0 = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
+  float* partials = d0 + NB * NB;
+  unsigned helper_target = 0;
   __half* Lhi = static_cast<__half*>(Lh.hi);
   __half* Llo = static_cast<__half*>(Lh.lo);
   potrf_prepare_kernel<<<1, 256, 0, stream>>>(A, lda, n, Lh.scale, ready, flag);
   if (zero_upper && n > NB)
     potrf_zero_upper_kernel<<<dim3((n / 4 + 255) / 256, n), 256, 0, stream>>>(L, ldl, Lhi, Llo, Lh.ld, n);
   unsigned epoch = 0;
+  static int max_ctas = 0;
+  if (max_ctas == 0) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    max_ctas = sms > 17 ? sms : 148;  // one CTA per SM; helpers need 16 TRSM CTAs
+  }
   const bool timing = getenv("GSMVI_POTRF_TIMING") != nullptr;
   for (int j0 = 0; j0 < n; j0 += NB) {
     const int nb = min(NB, n - j0);
@@ -530,7 +671,7 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
     pa.A = A; pa.lda = lda; pa.L = L; pa.ldl = ldl; pa.Lhi = Lhi; pa.Llo = Llo; pa.ldh = Lh.ld; pa.scale_l = Lh.scale;
     pa.n = n; pa.j0 = j0; pa.nb = nb; pa.partials = partials; pa.splits = 0; pa.split_stride = static_cast<long long>(M) * NB;
     pa.flag = flag; pa.ready = ready; pa.epoch_base = epoch;
-    pa.timing = (timing && j0 == NB * 8) ? 1 : 0;
+    pa.d0 = d0; pa.helper_count = ready + 1; pa.helpers = 0; pa.helper_target = 0;
     epoch += 8;
     if (j0 > 0) {
       const int tiles = (M + NB - 1) / NB;
@@ -547,10 +688,19 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
       int rc = launch_gemm_h3(stream, M, nb, j0, va, vb, partials, NB, o);
       if (rc != GSMVI_OK) return rc;
     }
-    potrf_panel_h3_kernel<<<1 + (rest + RPC - 1) / RPC, 256, PANEL_SMEM, stream>>>(pa);
+    int grid = 1 + (rest + RPC - 1) / RPC;
+    if (grid > max_ctas) grid = max_ctas;
+    if (pa.splits > 0 && grid - 1 >= 16) {
+      pa.helpers = 16;
+      helper_target += 16;
+      pa.helper_target = helper_target;
+    }
+    if (nb < NB) potrf_panel_h3_kernel<false, false><<<1, 256, PANEL_SMEM, stream>>>(pa);
+    else if (timing && j0 == NB * 8) potrf_panel_h3_kernel<true, true><<<grid, 256, PANEL_SMEM, stream>>>(pa);
+    else potrf_panel_h3_kernel<true, false><<<grid, 256, PANEL_SMEM, stream>>>(pa);
   }
   if (timing && n > NB * 9) {
-    long long h[32];
+    long long h[64];
     cudaStreamSynchronize(stream);
     cudaMemcpyFromSymbol(h, g_pt3, sizeof(h));
     fprintf(stderr, "[potrf_h3 panel 8] CTA0: load %lld |", h[1] - h[0]);

@@ -313,6 +313,7 @@ def run_ours(args):
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": eng.launches_per_step() * args.steps,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "bam": bam}
         print(json.dumps(line), flush=True)
+    eng.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -320,7 +321,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--D", type=int, default=4096)

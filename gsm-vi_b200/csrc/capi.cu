@@ -2,6 +2,7 @@
 #include "../../include/gsmvi_b200.h"
 
 #include "bam_solve.cuh"
+#include "comm.cuh"
 #include "dgemm.cuh"
 #include "gsm_ensemble.cuh"
 #include "gsm_kernels.cuh"
@@ -116,6 +117,23 @@ int gsmvi_gsm_update_h3(const float* X, long long ldx, const float* G, long long
 int gsmvi_potrf_check(const float* Sigma, long long lds, float* L, long long ldl, int D, int* bad_flag,
                       void* workspace, int npass, void* stream) {
   return potrf_lower(S(stream), Sigma, lds, L, ldl, D, bad_flag, static_cast<float*>(workspace), npass);
+}
+
+long long gsmvi_comm_layout_bytes(int D, int world, gsmvi_comm_layout* lay) { return comm_layout(D, world, lay); }
+int gsmvi_comm_alloc(long long bytes, void** dev_ptr_out, unsigned char* handle64_out) {
+  return comm_alloc(bytes, dev_ptr_out, handle64_out);
+}
+int gsmvi_comm_open(const unsigned char* handle64, void** dev_ptr_out) { return comm_open(handle64, dev_ptr_out); }
+int gsmvi_comm_close(void* peer_ptr) { return comm_close(peer_ptr); }
+int gsmvi_comm_free(void* dev_ptr) { return comm_free(dev_ptr); }
+
+int gsmvi_gsm_update_h3_fused(const float* X, long long ldx, const float* G, long long ldg, const gsmvi_h3_operand* G_split,
+                              const float* mu, const gsmvi_h3_operand* Sigma_split, float* mu_out, void* const* peer_base,
+                              const gsmvi_comm_layout* lay, int rank, int world, int cur, unsigned step, int B, int D,
+                              int B_total, void* workspace, void* stream) {
+  if (!G_split || !Sigma_split || !lay) return GSMVI_EINVAL;
+  return gsm_update_h3_fused(S(stream), X, ldx, G, ldg, *G_split, mu, *Sigma_split, mu_out,
+                             reinterpret_cast<float* const*>(peer_base), *lay, rank, world, cur, step, B, D, B_total, workspace);
 }
 
 int gsmvi_potrf_h3(const float* Sigma, long long lds, float* L, long long ldl, const gsmvi_h3_operand* L_split, int D,

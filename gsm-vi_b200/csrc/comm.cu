@@ -1,0 +1,244 @@
+// Multi-GPU exchange of the GSM batch statistics over NVLink peer memory, fused with the
+// covariance-update GEMM instead of an NCCL all-reduce after it.
+//
+// One process per GPU; every rank owns a "comm buffer" (cudaMalloc + CUDA IPC, mapped by all peers):
+//     [ staging: world x tpo dense 128x128 tiles | Sigma buffer 0 | Sigma buffer 1 | dmu: world x ld | counters ]
+// Lower tile t of the D x D update belongs to rank t % world.  Per iteration, on every rank:
+//   1. the covariance GEMM (h3_gemm.cuh, push mode) computes this rank's partial of EVERY lower tile (K = its batch shard)
+//      and its epilogue stores each tile straight into the owner's staging slot [rank][t / world] through peer memory,
+//      then bumps the owner's per-tile arrival counter (release, system scope): the reduce-scatter rides on the GEMM
+//      epilogue, tile by tile, while later tiles are still in the tensor core;
+//   2. comm_reduce_kernel: one CTA per owned tile waits for its `world` partials, adds them in rank order to the
+//      current Sigma tile (deterministic: every rank ends up with bit-identical state), and stores the new tile and its
+//      mirror into the NEXT Sigma buffer of every rank (the all-gather), then bumps every rank's "final tiles" counter;
+//      one more CTA pushes this rank's mean increment to every rank;
+//   3. comm_finalize_kernel waits until all tiles and all mean increments have arrived and forms the new mean.
+// Counters only ever grow (targets are multiples of the step index), so nothing is reset between iterations.  A staging
+// slot is rewritten by a peer only after that peer has received every final tile of the previous step, which the owner
+// sends after reading the slot; the Sigma buffer a peer writes is never the one this rank is still reading.
+#include "comm.cuh"
+
+#include <stdio.h>
+#include <string.h>
+
+namespace gsmvi {
+
+namespace {
+
+constexpr int TILE = 128;
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_sys(unsigned* p, unsigned v) {
+  asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void spin_until(const unsigned* p, unsigned target, const char* what) {
+  const long long t0 = clock64();
+  while (static_cast<int>(ld_acquire_sys(p) - target) < 0) {
+    __nanosleep(100);
+    if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer never arrived
+      printf("gsmvi: comm watchdog (%s, block %d, have %u want %u)\n", what, blockIdx.x, ld_acquire_sys(p), target);
+      __trap();
+    }
+  }
+}
+
+struct ReduceArgs {
+  float* const* base;  // device array [world] of comm-buffer bases
+  gsmvi_comm_layout lay;
+  int rank, world, D, cur;  // cur: index of the current Sigma buffer; the new one is 1 - cur
+  unsigned step;
+  const float* usum;  // this rank's sum_b u_b
+  float inv_btotal;
+};
+
+__global__ void __launch_bounds__(256) comm_reduce_kernel(const ReduceArgs a) {
+  extern __shared__ float tile_raw[];
+  float (*tile)[TILE + 1] = reinterpret_cast<float (*)[TILE + 1]>(tile_raw);
+  const int tid = threadIdx.x;
+  float* mine = a.base[a.rank];
+  const int ntiles = a.lay.tiles_m * (a.lay.tiles_m + 1) / 2;
+  const int li = blockIdx.x;
+  const int t = li * a.world + a.rank;
+  if (t >= ntiles) {
+    if (li != static_cast<int>(gridDim.x) - 1) return;
+    // last CTA: this rank's mean increment to every rank's dmu[rank][:]
+    for (int p = 0; p < a.world; ++p) {
+      float* dst = a.base[p] + a.lay.dmu_off + static_cast<long long>(a.rank) * a.lay.lds;
+      for (int j = tid; j < a.D; j += 256) dst[j] = a.usum[j] * a.inv_btotal;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();
+      for (int p = 0; p < a.world; ++p)
+        red_release_sys(reinterpret_cast<unsigned*>(a.base[p]) + a.lay.cnt_off + a.lay.tpo + 1, 1u);
+    }
+    return;
+  }
+  int tm = static_cast<int>((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+  while ((tm + 1) * (tm + 2) / 2 <= t) ++tm;
+  while (tm * (tm + 1) / 2 > t) --tm;
+  const int tn = t - tm * (tm + 1) / 2;
+  const int m0 = tm * TILE, n0 = tn * TILE;
+  if (tid == 0)
+    spin_until(reinterpret_cast<const unsigned*>(mine) + a.lay.cnt_off + li, static_cast<unsigned>(a.world) * (a.step + 1), "partial tiles");
+  __syncthreads();
+  // sum of the partials in rank order + the current Sigma tile
+  const float* stage = mine + a.lay.stage_off;
+  const float* s0 = mine + a.lay.s_off[a.cur];
+  for (int q = tid; q < TILE * TILE / 4; q += 256) {
+    const int i = q >> 5, j4 = (q & 31) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < a.world; ++r) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(stage + (static_cast<long long>(r) * a.lay.tpo + li) * (TILE * TILE) + i * TILE + j4));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const int m = m0 + i;
+    if (m < a.D) {
+      const float* srow = s0 + static_cast<long long>(m) * a.lay.lds + n0 + j4;
+      if (n0 + j4 + 0 < a.D) acc.x += srow[0];
+      if (n0 + j4 + 1 < a.D) acc.y += srow[1];
+      if (n0 + j4 + 2 < a.D) acc.z += srow[2];
+      if (n0 + j4 + 3 < a.D) acc.w += srow[3];
+    }
+    tile[i][j4 + 0] = acc.x; tile[i][j4 + 1] = acc.y; tile[i][j4 + 2] = acc.z; tile[i][j4 + 3] = acc.w;
+  }
+  __syncthreads();
+  const bool diag = (tm == tn);
+  const long long sn = a.lay.s_off[1 - a.cur];
+  for (int p = 0; p < a.world; ++p) {
+    float* dst = a.base[p] + sn;
+    // rows of the tile; a diagonal tile takes its upper half from the lower one so the result is exactly symmetric
+    for (int q = tid; q < TILE * TILE / 4; q += 256) {
+      const int i = q >> 5, j4 = (q & 31) * 4;
+      const int m = m0 + i;
+      if (m >= a.D) continue;
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (diag && j4 + u > i) ? tile[j4 + u][i] : tile[i][j4 + u];
+      float* drow = dst + static_cast<long long>(m) * a.lay.lds + n0 + j4;
+      if (n0 + j4 + 3 < a.D) {
+        *reinterpret_cast<float4*>(drow) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+        for (int u = 0; u < 4; ++u)
+          if (n0 + j4 + u < a.D) drow[u] = v[u];
+      }
+    }
+    if (!diag) {  // mirrored tile: row n0 + j of the output is column j of the tile
+      for (int q = tid; q < TILE * TILE / 4; q += 256) {
+        const int j = q >> 5, i4 = (q & 31) * 4;
+        const int n = n0 + j;
+        if (n >= a.D) continue;
+        float* drow = dst + static_cast<long long>(n) * a.lay.lds + m0 + i4;
+        if (m0 + i4 + 3 < a.D) {
+          *reinterpret_cast<float4*>(drow) = make_float4(tile[i4][j], tile[i4 + 1][j], tile[i4 + 2][j], tile[i4 + 3][j]);
+        } else {
+          for (int u = 0; u < 4; ++u)
+            if (m0 + i4 + u < a.D) drow[u] = tile[i4 + u][j];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();
+    for (int p = 0; p < a.world; ++p) red_release_sys(reinterpret_cast<unsigned*>(a.base[p]) + a.lay.cnt_off + a.lay.tpo, 1u);
+  }
+}
+
+__global__ void __launch_bounds__(256) comm_finalize_kernel(float* const* base, gsmvi_comm_layout lay, int rank, int world, int D,
+                                                            unsigned step, const float* __restrict__ mu, float* __restrict__ mu_out) {
+  const float* mine = base[rank];
+  const unsigned* cnt = reinterpret_cast<const unsigned*>(mine) + lay.cnt_off;
+  const int ntiles = lay.tiles_m * (lay.tiles_m + 1) / 2;
+  if (threadIdx.x == 0) {
+    spin_until(cnt + lay.tpo, static_cast<unsigned>(ntiles) * (step + 1), "final tiles");
+    spin_until(cnt + lay.tpo + 1, static_cast<unsigned>(world) * (step + 1), "mean increments");
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < D; j += 256) {
+    float acc = mu[j];
+    for (int r = 0; r < world; ++r) acc += __ldcg(mine + lay.dmu_off + static_cast<long long>(r) * lay.lds + j);
+    mu_out[j] = acc;
+  }
+}
+
+}  // namespace
+
+long long comm_layout(int D, int world, gsmvi_comm_layout* lay) {
+  if (D <= 0 || world <= 0 || !lay) return -1;
+  const long long lds = (D + 31) / 32 * 32;
+  lay->tiles_m = (D + TILE - 1) / TILE;
+  const int ntiles = lay->tiles_m * (lay->tiles_m + 1) / 2;
+  lay->tpo = (ntiles + world - 1) / world;
+  lay->lds = lds;
+  long long off = 0;
+  lay->stage_off = off;
+  off += static_cast<long long>(world) * lay->tpo * TILE * TILE;
+  lay->s_off[0] = off;
+  off += static_cast<long long>(D) * lds;
+  lay->s_off[1] = off;
+  off += static_cast<long long>(D) * lds;
+  lay->dmu_off = off;
+  off += static_cast<long long>(world) * lds;
+  lay->cnt_off = off;
+  off += (lay->tpo + 2 + 31) / 32 * 32;
+  return off * 4;
+}
+
+int comm_alloc(long long bytes, void** ptr, unsigned char* handle64) {
+  if (bytes <= 0 || !ptr || !handle64) return GSMVI_EINVAL;
+  cudaError_t e = cudaMalloc(ptr, static_cast<size_t>(bytes));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaMemset(*ptr, 0, static_cast<size_t>(bytes));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return GSMVI_OK;
+}
+
+int comm_open(const unsigned char* handle64, void** ptr) {
+  if (!handle64 || !ptr) return GSMVI_EINVAL;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
+}
+
+int comm_close(void* peer_ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(peer_ptr);
+  return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
+}
+
+int comm_free(void* ptr) {
+  cudaError_t e = cudaFree(ptr);
+  return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
+}
+
+int comm_reduce_broadcast(cudaStream_t stream, float* const* base, const gsmvi_comm_layout& lay, int rank, int world, int D,
+                          int cur, unsigned step, const float* usum, float inv_btotal, const float* mu, float* mu_out) {
+  ReduceArgs a;
+  a.base = base; a.lay = lay; a.rank = rank; a.world = world; a.D = D; a.cur = cur; a.step = step;
+  a.usum = usum; a.inv_btotal = inv_btotal;
+  const int ntiles = lay.tiles_m * (lay.tiles_m + 1) / 2;
+  const int mine = (ntiles - rank + world - 1) / world;  // tiles t = li * world + rank < ntiles
+  constexpr int SMEM = TILE * (TILE + 1) * static_cast<int>(sizeof(float));
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(comm_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  comm_reduce_kernel<<<mine + 1, 256, SMEM, stream>>>(a);
+  comm_finalize_kernel<<<1, 256, 0, stream>>>(base, lay, rank, world, D, step, mu, mu_out);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
+}
+
+}  // namespace gsmvi

@@ -13,6 +13,7 @@
 // with the "+ Sigma0" and -1/B fused in its epilogue (lower tiles only, mirrored stores).
 #include "gsm_kernels.cuh"
 #include "h3_gemm.cuh"
+#include "comm.cuh"
 
 #include <math.h>
 
@@ -426,11 +427,19 @@ size_t gsm_update_h3_workspace_bytes(int B, int D) {
   return static_cast<size_t>((4LL * B + 1) * ldw + 32) * sizeof(float) + static_cast<size_t>(6LL * B * ldw) * sizeof(__half);
 }
 
-int gsm_update_h3(cudaStream_t stream, const float* X, long long ldx, const float* G, long long ldg, const H3Operand& Gh,
-                  const float* mu, const float* Sigma, long long lds, const H3Operand& Sh, float* mu_out, float* Sigma_out,
-                  long long ldso, unsigned* absmax_sout, int B, int D, int B_total, int mode, void* workspace) {
-  if (!X || !G || !mu || !Sigma || !mu_out || !Sigma_out || !workspace || B <= 0 || D <= 0 || B_total < B)
-    return GSMVI_EINVAL;
+struct FusedComm {
+  float* const* base;
+  const gsmvi_comm_layout* lay;
+  int rank, world, cur;
+  unsigned step;
+};
+
+static int gsm_update_h3_impl(cudaStream_t stream, const float* X, long long ldx, const float* G, long long ldg,
+                              const H3Operand& Gh, const float* mu, const float* Sigma, long long lds, const H3Operand& Sh,
+                              float* mu_out, float* Sigma_out, long long ldso, unsigned* absmax_sout, int B, int D, int B_total,
+                              int mode, void* workspace, const FusedComm* fc) {
+  if (!X || !G || !mu || !mu_out || !workspace || B <= 0 || D <= 0 || B_total < B) return GSMVI_EINVAL;
+  if (!fc && (!Sigma || !Sigma_out)) return GSMVI_EINVAL;
   const long long ldw = round_up(D, 32);
   float* W = static_cast<float*>(workspace);
   float* T = W + static_cast<long long>(B) * ldw;
@@ -460,7 +469,17 @@ int gsm_update_h3(cudaStream_t stream, const float* X, long long ldx, const floa
     o.tri = true;
     o.mirror = true;
     o.absmax_out = absmax_sout;
-    if (mode == 0) {
+    if (fc) {
+      // multi-GPU: the epilogue pushes every partial tile to its owner rank (reduce-scatter fused into the GEMM)
+      o.mirror = false;
+      o.absmax_out = nullptr;
+      o.push_base = fc->base;
+      o.push_stage_off = fc->lay->stage_off;
+      o.push_cnt_off = fc->lay->cnt_off;
+      o.push_rank = fc->rank;
+      o.push_world = fc->world;
+      o.push_tpo = fc->lay->tpo;
+    } else if (mode == 0) {
       o.beta = 1.0f;
       o.Cin = Sigma;
       o.ldcin = lds;
@@ -469,10 +488,30 @@ int gsm_update_h3(cudaStream_t stream, const float* X, long long ldx, const floa
     HView vb{Thi + static_cast<long long>(B) * ldw, Tlo + static_cast<long long>(B) * ldw, 2LL * B, D, ldw, scal + 1};
     if ((rc = launch_gemm_h3(stream, D, D, 2 * B, va, vb, Sigma_out, ldso, o)) != GSMVI_OK) return rc;
   }
+  if (fc)  // owners reduce + broadcast the new Sigma tiles, mean increments exchanged, mu_out formed
+    return comm_reduce_broadcast(stream, fc->base, *fc->lay, fc->rank, fc->world, D, fc->cur, fc->step, usum,
+                                 1.0f / static_cast<float>(B_total), mu, mu_out);
   vec_axpy_kernel<<<(D + 255) / 256, 256, 0, stream>>>(mode == 0 ? mu : nullptr, usum, 1.0f / static_cast<float>(B_total),
                                                       mu_out, D);
   e = cudaGetLastError();
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
+}
+
+int gsm_update_h3(cudaStream_t stream, const float* X, long long ldx, const float* G, long long ldg, const H3Operand& Gh,
+                  const float* mu, const float* Sigma, long long lds, const H3Operand& Sh, float* mu_out, float* Sigma_out,
+                  long long ldso, unsigned* absmax_sout, int B, int D, int B_total, int mode, void* workspace) {
+  return gsm_update_h3_impl(stream, X, ldx, G, ldg, Gh, mu, Sigma, lds, Sh, mu_out, Sigma_out, ldso, absmax_sout, B, D, B_total,
+                            mode, workspace, nullptr);
+}
+
+int gsm_update_h3_fused(cudaStream_t stream, const float* X, long long ldx, const float* G, long long ldg, const H3Operand& Gh,
+                        const float* mu, const H3Operand& Sh, float* mu_out, float* const* peer_base,
+                        const gsmvi_comm_layout& lay, int rank, int world, int cur, unsigned step, int B, int D, int B_total,
+                        void* workspace) {
+  if (!peer_base || world < 1 || rank < 0 || rank >= world || (cur != 0 && cur != 1)) return GSMVI_EINVAL;
+  FusedComm fc{peer_base, &lay, rank, world, cur, step};
+  return gsm_update_h3_impl(stream, X, ldx, G, ldg, Gh, mu, nullptr, 0, Sh, mu_out, nullptr, 0, nullptr, B, D, B_total, 1,
+                            workspace, &fc);
 }
 
 }  // namespace gsmvi

@@ -43,7 +43,7 @@ static int launch_h3_one(cudaStream_t stream, const H3Args& args, const CUtensor
 
 int launch_gemm_h3(cudaStream_t stream, int M, int N, int K, const HView& A, const HView& B, float* C, long long ldc,
                    const H3Opts& o) {
-  if (M <= 0 || N <= 0 || K <= 0 || !C || !A.hi || !A.lo || !B.hi || !B.lo || !A.scale || !B.scale) return GSMVI_EINVAL;
+  if (M <= 0 || N <= 0 || K <= 0 || (!C && !o.push_base) || !A.hi || !A.lo || !B.hi || !B.lo || !A.scale || !B.scale) return GSMVI_EINVAL;
   if (o.tri && M != N) return GSMVI_EINVAL;
   if (o.beta != 0.0f && !o.Cin) return GSMVI_EINVAL;
   if (o.splits < 1 || (o.splits > 1 && (o.beta != 0.0f || o.bias_n || o.mirror))) return GSMVI_EINVAL;
@@ -62,6 +62,13 @@ int launch_gemm_h3(cudaStream_t stream, int M, int N, int K, const HView& A, con
   a.tiles_n = (N + H3_BN - 1) / H3_BN;
   a.splits = o.splits;
   a.split_stride = o.split_stride;
+  a.push_base = o.push_base;
+  a.push_stage_off = o.push_stage_off;
+  a.push_cnt_off = o.push_cnt_off;
+  a.push_rank = o.push_rank;
+  a.push_world = o.push_world;
+  a.push_tpo = o.push_tpo;
+  if (o.push_base && (!o.tri || o.splits != 1 || o.mirror || o.beta != 0.0f || o.bias_n)) return GSMVI_EINVAL;
   const int tiles = o.tri ? a.tiles_m * (a.tiles_m + 1) / 2 : a.tiles_m * a.tiles_n;
   const dim3 grid(tiles, o.splits);
 

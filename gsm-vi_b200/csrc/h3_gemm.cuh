@@ -58,6 +58,13 @@ struct H3Args {
   int tiles_m, tiles_n;
   int splits;              // split-K: blockIdx.y = split index s, output goes to C + s * split_stride (raw partials)
   long long split_stride;
+  // push mode (multi-GPU reduce-scatter fused into the epilogue; tri only): lower tile t belongs to rank t % push_world and is
+  // written, as a dense 128 x 128 tile, straight into the owner's staging area over NVLink peer memory
+  //   push_base[owner] + push_stage_off + ((push_rank * push_tpo + t / push_world) * 128 * 128)
+  // followed by a system-scope release increment of the owner's per-tile arrival counter (4-byte words at push_cnt_off).
+  float* const* push_base;
+  long long push_stage_off, push_cnt_off;
+  int push_rank, push_world, push_tpo;
 };
 
 __host__ __device__ constexpr uint32_t make_idesc_f16(bool a_mn, bool b_mn) {
@@ -265,7 +272,17 @@ gemm_h3_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, con
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
       const int nbase = n0 + c0;
-      if (m < args.M && nbase < args.N) {
+      if (args.push_base != nullptr) {
+        const int t = blockIdx.x, owner = t % args.push_world;
+        float* tile = args.push_base[owner] + args.push_stage_off +
+                      (static_cast<long long>(args.push_rank) * args.push_tpo + t / args.push_world) * (H3_BM * H3_BN);
+        float* prow = tile + (q * 32 + lane) * H3_BN + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(prow + j) =
+              make_float4(alpha * __uint_as_float(r[j]), alpha * __uint_as_float(r[j + 1]), alpha * __uint_as_float(r[j + 2]),
+                          alpha * __uint_as_float(r[j + 3]));
+      } else if (m < args.M && nbase < args.N) {
         float* crow = Cout + static_cast<long long>(m) * args.ldc + nbase;
         const float* cin = (beta != 0.0f) ? args.Cin + static_cast<long long>(m) * args.ldcin + nbase : nullptr;
         const bool vec_ok = !diag_tile && (nbase + 32 <= args.N) && ((args.ldc & 3) == 0) &&
@@ -317,6 +334,16 @@ gemm_h3_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, con
       const unsigned bits = __reduce_max_sync(0xffffffffu, amax);
       if (lane == 0 && bits != 0u) atomicMax(args.absmax_out, bits);
     }
+    if (args.push_base != nullptr) {
+      // all eight epilogue warps have issued their peer stores: one thread publishes the tile to its owner
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const int t = blockIdx.x, owner = t % args.push_world;
+        unsigned* cnt = reinterpret_cast<unsigned*>(args.push_base[owner]) + args.push_cnt_off + t / args.push_world;
+        __threadfence_system();
+        asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(cnt), "r"(1u) : "memory");
+      }
+    }
     ptx::tc_fence_before_sync();
   }
 
@@ -349,6 +376,9 @@ struct H3Opts {
   unsigned* absmax_out = nullptr;
   int splits = 1;
   long long split_stride = 0;
+  float* const* push_base = nullptr;  // push mode, see H3Args
+  long long push_stage_off = 0, push_cnt_off = 0;
+  int push_rank = 0, push_world = 1, push_tpo = 0;
 };
 
 int launch_gemm_h3(cudaStream_t stream, int M, int N, int K, const HView& A, const HView& B, float* C, long long ldc,

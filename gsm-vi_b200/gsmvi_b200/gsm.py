@@ -51,12 +51,22 @@ class GSMEngine:
         B = self.B = batch_size // self.world
         self.seed = key_to_seed(key)
         self.score_input = score_input
+        self.h3 = npass == 4
         # state, double-buffered so a rejected update is simply not swapped in
-        self.Sb, self.S = new_mat(D, D, dev)
-        self.Snb, self.Sn = new_mat(D, D, dev)
+        self.comm = None
+        if self.h3 and self.world > 1:
+            # batch-sharded fit on the h3 engine: the two Sigma buffers live in this rank's peer-mapped exchange buffer and
+            # the statistics travel through NVLink peer memory, fused with the covariance GEMM (csrc/comm.cu)
+            from ._comm import CommBuffer
+            self.comm = CommBuffer(D, process_group, self.dist)
+            self.Sb, self.Snb = self.comm.S[0], self.comm.S[1]
+            self.S, self.Sn = self.Sb[:, :D], self.Snb[:, :D]
+            self.cur = 0
+        else:
+            self.Sb, self.S = new_mat(D, D, dev)
+            self.Snb, self.Sn = new_mat(D, D, dev)
         self.Lb, _ = new_mat(D, D, dev)
         self.Lnb, _ = new_mat(D, D, dev)
-        self.h3 = npass == 4
         if not self.h3:
             # pre-split low parts of the reused GEMM operands (Sigma for W = G Sigma, L for the sampler), kept per buffer
             self.Shi, self.Slo = new_mat(D, D, dev)[0], new_mat(D, D, dev)[0]
@@ -77,7 +87,7 @@ class GSMEngine:
             self.ws_p = torch.empty(L.workspace_bytes(L.WS_POTRF, B, D) // 4, dtype=torch.float32, device=dev)
             self.ws_u = torch.empty(L.workspace_bytes(L.WS_GSM_UPDATE, B, D) // 4, dtype=torch.float32, device=dev)
         self.bad = torch.zeros(1, dtype=torch.int32, device=dev)
-        if self.world > 1:
+        if self.world > 1 and self.comm is None:
             self.dSb, _ = new_mat(D, D, dev)
             self.dmu = new_vec(D, dev)
         if z_tape is not None and not isinstance(z_tape, torch.Tensor):
@@ -181,11 +191,10 @@ class GSMEngine:
             L.gsm_update_h3(self.Xb, self.Gb, self.Gh, self.mu, self.Sb, self.Sh, self.mun, self.Snb, sl[2:3], B, D, B, 0,
                             self.ws_u)
         else:
-            L.gsm_update_h3(self.Xb, self.Gb, self.Gh, self.mu, self.Sb, self.Sh, self.dmu, self.dSb, None, B, D,
-                            self.batch_size, 1, self.ws_u)
-            self.dist.all_reduce(self.dSb, group=self.group)
-            self.dist.all_reduce(self.dmu, group=self.group)
-            L.gsm_apply_stats(self.Sb, self.dSb, self.mu, self.dmu, self.Snb, self.mun, D)
+            # the exchange is fused into the update: partial tiles pushed to their owner rank from the GEMM epilogue,
+            # reduced there in rank order and stored into every rank's next Sigma buffer (bit-identical replicas)
+            self.comm.update_fused(self.Xb, self.Gb, self.Gh, self.mu, self.Sh, self.mun, self.cur, B, D, self.batch_size,
+                                   self.ws_u)
             L.h3_absmax(self.Sn, D, D, sl[2:3])
         # ---- goodness check = Cholesky of the new covariance, reused as the next sampling factor (gsm.py:125)
         L.potrf_h3(self.Snb, self.Lnb, self.Lnh, D, self.bad, self.ws_p, zero_upper=False)
@@ -196,9 +205,17 @@ class GSMEngine:
             self.Lb, self.Lnb = self.Lnb, self.Lb
             self.Sh, self.Snh, self.Lh, self.Lnh = self.Snh, self.Sh, self.Lnh, self.Lh
             self.mu, self.mun = self.mun, self.mu
+            if self.comm is not None:
+                self.cur = 1 - self.cur
         else:
             self.n_reverts += 1
         return ok
+
+    def close(self):
+        """Release the peer-mapped exchange buffer (collective: every rank must call it)."""
+        if self.comm is not None:
+            self.comm.close()
+            self.comm = None
 
     def step(self, i):
         if self.h3:
@@ -294,4 +311,6 @@ class GSM:
         if monitor is not None:  # gsm.py:131-132
             monitor(i, [eng.mean(), eng.cov()], self.lp, key, nevals=nevals)
         self.n_reverts = eng.n_reverts
-        return eng.mean().clone(), eng.cov().clone()
+        mean, cov = eng.mean().clone(), eng.cov().clone()
+        eng.close()
+        return mean, cov

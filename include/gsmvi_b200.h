@@ -42,6 +42,16 @@ typedef struct gsmvi_h3_operand {
   long long ld;
 } gsmvi_h3_operand;
 
+/* Layout of a rank's peer-mapped exchange buffer (offsets in 4-byte words from its base), gsmvi_comm_layout_bytes. */
+typedef struct gsmvi_comm_layout {
+  long long stage_off;  /* staging: world x tpo dense 128 x 128 partial tiles, slot [source rank][owned tile] */
+  long long s_off[2];   /* the two Sigma buffers (D x lds), used alternately as current / next */
+  long long dmu_off;    /* world x lds: every rank's mean increment */
+  long long cnt_off;    /* unsigned counters: [0, tpo) partial arrivals per owned tile, [tpo] final tiles, [tpo+1] mean */
+  long long lds;
+  int tiles_m, tpo;
+} gsmvi_comm_layout;
+
 int gsmvi_abi_version(void);
 
 /* Bytes of device scratch the call of that kind needs for batch B, dimension D (-1: unknown kind). */
@@ -92,6 +102,26 @@ int gsmvi_gsm_update_h3(const float* X, long long ldx, const float* G, long long
                         const float* mu, const float* Sigma, long long lds, const gsmvi_h3_operand* Sigma_split,
                         float* mu_out, float* Sigma_out, long long ldso, unsigned* absmax_sout, int B, int D, int B_total,
                         int mode, void* workspace, void* stream);
+
+/* Multi-GPU (one process per GPU): batch statistics exchanged through NVLink peer memory, fused with the covariance GEMM
+ * instead of an all-reduce after it (replaces nothing in the reference, which is single-device).
+ * gsmvi_comm_layout_bytes: fill *lay for dimension D and `world` ranks, return the buffer size in bytes.
+ * gsmvi_comm_alloc: cudaMalloc + zero + CUDA IPC handle (64 bytes, to be exchanged between the processes);
+ * gsmvi_comm_open / _close: map / unmap a peer's buffer; gsmvi_comm_free: release the own one.
+ * gsmvi_gsm_update_h3_fused: gsmvi_gsm_update_h3 for a batch shard with the exchange fused in: the covariance GEMM's
+ *   epilogue pushes each partial tile to its owner rank, the owner adds the partials in rank order to the current Sigma
+ *   (buffer `cur` inside its comm buffer) and stores the new tile into buffer 1 - cur of every rank; mu_out = mu + the
+ *   summed mean increments.  peer_base: DEVICE array of `world` comm-buffer pointers (own buffer at [rank]); `step` must
+ *   increase by one per call on every rank (counters are monotonic).  Every rank must make the same sequence of calls. */
+long long gsmvi_comm_layout_bytes(int D, int world, gsmvi_comm_layout* lay);
+int gsmvi_comm_alloc(long long bytes, void** dev_ptr_out, unsigned char* handle64_out);
+int gsmvi_comm_open(const unsigned char* handle64, void** dev_ptr_out);
+int gsmvi_comm_close(void* peer_ptr);
+int gsmvi_comm_free(void* dev_ptr);
+int gsmvi_gsm_update_h3_fused(const float* X, long long ldx, const float* G, long long ldg, const gsmvi_h3_operand* G_split,
+                              const float* mu, const gsmvi_h3_operand* Sigma_split, float* mu_out, void* const* peer_base,
+                              const gsmvi_comm_layout* lay, int rank, int world, int cur, unsigned step, int B, int D,
+                              int B_total, void* workspace, void* stream);
 
 /* L <- chol(Sigma) (lower, upper triangle zeroed), *bad_flag <- 0 if Sigma is positive definite else 1.
  * Replaces GSM._check_goodness / BaM._check_goodness (gsmvi/gsm.py:136-150, gsmvi/bam.py:219-233: host

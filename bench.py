@@ -225,7 +225,11 @@ def run_ours(args):
                 "kernel": ("gemm_h3_kernel (scaled 3xFP16 split, kind::f16)" if h3 else "gemm_tf32_kernel<3xTF32>") +
                           ": sample, score, W=G*Sigma, E^T U + U^T D",
                 "achieved": achieved, "peak": pipe_peak, "unit": "TFLOP/s", "frac": achieved / pipe_peak,
-                "traffic": None, "executed_tflops": executed, "executed_frac": executed / pipe_peak,
+                "traffic": (389.4e6 if (h3 and D == 4096 and B == 4096 and world == 1) else None), "traffic_note":
+                "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the four launches in the ncu --set full "
+                "capture profiles/r01_ncu_gemm_h3_summary.txt (195 / 369 / 386 / 606 MB; algorithmic operand + result "
+                "bytes 201 / 201 / 201 / 302 MB)",
+                "executed_tflops": executed, "executed_frac": executed / pipe_peak,
                 "launches_per_step": 4, "avg_launch_ms": gemm_ms / (4 * nrep),
                 "launch_ms": {"sample": per_call[0] / nrep, "score": per_call[1] / nrep, "w": per_call[2] / nrep,
                               "cov_update": per_call[3] / nrep},
@@ -240,11 +244,14 @@ def run_ours(args):
     if world == 1:
         mean_h = torch.zeros(D).pin_memory()
         cov_h = torch.eye(D).pin_memory()
+        m_host, c_host = torch.empty(D).pin_memory(), torch.empty(D, D).pin_memory()
         g = GSM(D, tgt.lp, tgt.lp_g)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         m_fit, c_fit = g.fit(99, mean=mean_h, cov=cov_h, batch_size=B, niter=args.steps - 1, verbose=False, npass=npass)
-        m_host, c_host = m_fit.cpu(), c_fit.cpu()
+        m_host.copy_(m_fit, non_blocking=True)  # D2H into pinned host memory
+        c_host.copy_(c_fit, non_blocking=True)
+        torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         per = (D * D + D) * 4.0 / args.steps
         e2e = {"value": args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": per, "d2h_bytes_per_step": per + 4,

@@ -10,6 +10,7 @@
 // Samples and scores come from the fp32 tensor-core path; the statistics and everything D x D / K x K here are fp64
 // (dgemm.cu): V = S0 + reg*C amplifies C's rounding by reg, and the solve mixes scales of 1 and ~1e9.
 #include "bam_solve.cuh"
+#include "oz_gemm.cuh"
 
 #include <math.h>
 #include <stdio.h>
@@ -236,6 +237,31 @@ static inline cudaError_t last() { return cudaGetLastError(); }
     if (e__ != cudaSuccess) return static_cast<int>(e__);      \
   } while (0)
 
+// The large fp64 products of the solve CAN run on the int8 tensor cores (oz_gemm.cuh): GSMVI_OZ_SLICES = 2..8 in the
+// environment picks the digit count.  It is OFF by default: the solve amplifies product errors by ~1e8, and the
+// fixed-point-per-row error of the digit split (9e-16 normwise at 8 digits) costs one to two digits against true fp64
+// (single update, D = 2048, kappa = 1e2: relF 1.4e-7 vs 2.7e-8; D = 1024, kappa = 1e4: 2.7e-4 vs 2.9e-6, over the
+// 1e-4 bar) for a 1.4x faster product (profiles/r01_oz_probe.json).
+struct OzCtx {
+  void* ws = nullptr;
+  int slices = 0;
+};
+static int oz_slices_env() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GSMVI_OZ_SLICES");
+    v = e ? atoi(e) : 0;
+    if (v != 0 && (v < 2 || v > 8)) v = 8;
+  }
+  return v;
+}
+static int dgemm_big(cudaStream_t st, int M, int N, int K, const double* A, long long lda, bool a_mn, const double* B,
+                     long long ldb, bool b_mn, double* C, long long ldc, const DgemmOpts& o, const OzCtx& oz) {
+  if (oz.ws && oz.slices >= 2 && M >= 1024 && N >= 1024 && K >= 512 && K <= 8192)
+    return launch_dgemm_oz(st, M, N, K, A, lda, a_mn, B, ldb, b_mn, C, ldc, o, oz.ws, oz.slices);
+  return launch_dgemm(st, M, N, K, A, lda, a_mn, B, ldb, b_mn, C, ldc, o);
+}
+
 // In-place blocked Cholesky of the lower triangle of A (n x n fp64); upper triangle zeroed.  dinv receives the inverse
 // of every 64x64 diagonal block ([ceil(n/64)] x 64 x 64).  flag |= 1 on a bad pivot.
 static int potrf64_inplace(cudaStream_t st, double* A, long long lda, int n, double* dinv, int* flag) {
@@ -323,7 +349,7 @@ static void dbg_stage(cudaStream_t st, const char* name, const double* A, long l
 // at kappa ~ 1e11 (measured).  Needs 4 scratch n x n buffers.  Synchronises the stream once per iteration
 // to read the residual ||I - Z Y||_F.
 static int ns_sqrt64(cudaStream_t st, double* Y, long long ld, int n, double* Z, double* P, double* Y2, double* Z2,
-                     double* scal_dev, int max_iter, double tol, double lam_min, int* iters_out) {
+                     double* scal_dev, int max_iter, double tol, double lam_min, int* iters_out, const OzCtx& oz = OzCtx()) {
   double h[2];
   GSMVI_CUDA(cudaMemsetAsync(scal_dev, 0, 2 * sizeof(double), st));
   frob_inf64_kernel<<<n, 256, 0, st>>>(Y, ld, n, 0.0, scal_dev);
@@ -351,12 +377,12 @@ static int ns_sqrt64(cudaStream_t st, double* Y, long long ld, int n, double* Z,
     DgemmOpts p;  // P = a I + b Z Y   (B operand MN-major: the product is exactly Z Y)
     p.alpha = b;
     p.diag_add = a;
-    GSMVI_TRY(launch_dgemm(st, n, n, n, Z, ld, false, Y, ld, true, P, ld, p));
+    GSMVI_TRY(dgemm_big(st, n, n, n, Z, ld, false, Y, ld, true, P, ld, p, oz));
     GSMVI_CUDA(cudaMemsetAsync(scal_dev, 0, 2 * sizeof(double), st));
     frob_inf64_kernel<<<n, 256, 0, st>>>(P, ld, n, a + b, scal_dev);  // ||P - (a+b) I||_F = |b| ||I - Z Y||_F
     DgemmOpts o;
-    GSMVI_TRY(launch_dgemm(st, n, n, n, Y, ld, false, P, ld, true, Y2, ld, o));   // Y2 = Y P
-    GSMVI_TRY(launch_dgemm(st, n, n, n, P, ld, false, Z, ld, true, Z2, ld, o));   // Z2 = P Z
+    GSMVI_TRY(dgemm_big(st, n, n, n, Y, ld, false, P, ld, true, Y2, ld, o, oz));   // Y2 = Y P
+    GSMVI_TRY(dgemm_big(st, n, n, n, P, ld, false, Z, ld, true, Z2, ld, o, oz));   // Z2 = P Z
     double* t = Y; Y = Y2; Y2 = t;
     t = Z; Z = Z2; Z2 = t;
     if (last_round) { ++it; break; }
@@ -394,8 +420,11 @@ size_t bam_solve_workspace_bytes(int B, int D, int lowrank) {
   const long long nblk = (D + NB64 - 1) / NB64;
   const long long K = B + 1, ldk = rup(K, 8), kblk = (K + NB64 - 1) / NB64;
   if (!lowrank) {
-    // 6 D x D fp64 buffers + Q, W [D x ldk] + 2 sets of diagonal-block inverses + scalars
-    return static_cast<size_t>(6 * D * ld + 2 * D * ldk + 2 * nblk * NB64 * NB64 + 16) * sizeof(double);
+    // 6 D x D fp64 buffers + Q, W [D x ldk] + 2 sets of diagonal-block inverses + scalars (+ the int8 digit planes and
+    // fp64 accumulator of the tensor-core products, 1 KiB aligned, when D is large enough to use them)
+    size_t b = static_cast<size_t>(6 * D * ld + 2 * D * ldk + 2 * nblk * NB64 * NB64 + 16) * sizeof(double);
+    if (D >= 1024) b = static_cast<size_t>(rup(static_cast<long long>(b), 1024)) + 1024 + oz_workspace_bytes(D, D, D > K ? D : K, 8);
+    return b;
   }
   // V [D x ld], S [D x ld], Q, A = VQ, W = A F [D x ldk], 6 K x K buffers, inverses, scalars
   return static_cast<size_t>(2 * D * ld + 3 * D * ldk + 6 * K * ldk + kblk * NB64 * NB64 + 16) * sizeof(double);
@@ -453,6 +482,11 @@ int bam_solve_full(cudaStream_t st, const double* stats_ws, int B, int D, int Bt
   double* dinvL = W + D * ldk;
   double* dinvR = dinvL + nblk * NB64 * NB64;
   double* scal = dinvR + nblk * NB64 * NB64;
+  OzCtx oz;
+  if (D >= 1024 && oz_slices_env() >= 2) {
+    oz.ws = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(scal + 16) + 1023) & ~static_cast<uintptr_t>(1023));
+    oz.slices = oz_slices_env();
+  }
   if (phase != 2) {
   GSMVI_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
   bam_v_kernel<<<grid2(D, D), 256, 0, st>>>(C, ld, S0, lds0, xbar, mu0, reg, b1, ld, D);
@@ -463,13 +497,13 @@ int bam_solve_full(cudaStream_t st, const double* stats_ws, int B, int D, int Bt
                                                                Btot, world, Q, ldk);  // sum over ranks of Q Q^T = U
   DgemmOpts o;
   o.krange = KR_A_UPPER;  // A operand is L^T given as MN-major L: (L^T)[i][k] = L[k][i] == 0 for k < i
-  GSMVI_TRY(launch_dgemm(st, D, K, D, b1, ld, true, Q, ldk, true, W, ldk, o));     // W = L^T Q
+  GSMVI_TRY(dgemm_big(st, D, K, D, b1, ld, true, Q, ldk, true, W, ldk, o, oz));     // W = L^T Q
   DgemmOpts m;
   m.alpha = 4.0;
   m.diag_add = 1.0 / world;
   m.tri = true;
   m.mirror = true;
-  GSMVI_TRY(launch_dgemm(st, D, D, K, W, ldk, false, W, ldk, false, b3, ld, m));   // M = I + 4 W W^T  (= I + 4 L^T U L)
+  GSMVI_TRY(dgemm_big(st, D, D, K, W, ldk, false, W, ldk, false, b3, ld, m, oz));   // M = I + 4 W W^T  (= I + 4 L^T U L)
   dbg_stage(st, "M", b3, ld, D, scal, flag);
   }
   if (phase == 1) {
@@ -477,7 +511,7 @@ int bam_solve_full(cudaStream_t st, const double* stats_ws, int B, int D, int Bt
     return GSMVI_OK;
   }
   int iters = 0;
-  GSMVI_TRY(ns_sqrt64(st, b3, ld, D, b2, b4, b5, b0, scal, max_ns, 1e-11, 1.0, &iters));  // b3 = N = M^{1/2}
+  GSMVI_TRY(ns_sqrt64(st, b3, ld, D, b2, b4, b5, b0, scal, max_ns, 1e-11, 1.0, &iters, oz));  // b3 = N = M^{1/2}
   if (ns_iters_host) *ns_iters_host = iters;
   dbg_stage(st, "N=sqrt(M)", b3, ld, D, scal, flag);
   scale_diag64_kernel<<<grid2(D, D), 256, 0, st>>>(b3, ld, D, 1.0, 1.0);          // I + N
@@ -488,7 +522,7 @@ int bam_solve_full(cudaStream_t st, const double* stats_ws, int B, int D, int Bt
   DgemmOpts s;
   s.tri = true;
   s.mirror = true;
-  GSMVI_TRY(launch_dgemm(st, D, D, D, b4, ld, false, b4, ld, false, b5, ld, s));   // b5 = T T^T ; S = 2 b5
+  GSMVI_TRY(dgemm_big(st, D, D, D, b4, ld, false, b4, ld, false, b5, ld, s, oz));   // b5 = T T^T ; S = 2 b5
   bam_mean_kernel<<<(D + 7) / 8, 256, 0, st>>>(b5, ld, 2.0, gbar, xbar, mu0, reg, mu_out, D);
   bam_finish_cov_kernel<<<grid2(D, D), 256, 0, st>>>(b5, ld, S_out, ldso, D, 2.0, jitter);
   GSMVI_CUDA(last());

@@ -8,6 +8,7 @@
 #include "gsm_kernels.cuh"
 #include "h3_gemm.cuh"
 #include "monitor.cuh"
+#include "oz_gemm.cuh"
 #include "potrf.cuh"
 #include "tc_gemm.cuh"
 
@@ -191,6 +192,24 @@ int gsmvi_dgemm(const double* A, long long lda, int a_mn, const double* B, long 
   o.mirror = mirror != 0;
   o.krange = krange;
   return launch_dgemm(S(stream), M, N, K, A, lda, a_mn != 0, B, ldb, b_mn != 0, C, ldc, o);
+}
+
+long long gsmvi_dgemm_oz_workspace_bytes(int M, int N, int K, int slices) {
+  return static_cast<long long>(oz_workspace_bytes(M, N, K, slices));
+}
+
+int gsmvi_dgemm_oz(const double* A, long long lda, int a_mn, const double* B, long long ldb, int b_mn, double* C,
+                   long long ldc, int M, int N, int K, double alpha, double beta, const double* Cin, long long ldcin,
+                   double diag_add, int tri, int mirror, void* workspace, int slices, void* stream) {
+  DgemmOpts o;
+  o.alpha = alpha;
+  o.beta = beta;
+  o.diag_add = diag_add;
+  o.Cin = Cin;
+  o.ldcin = ldcin;
+  o.tri = tri != 0;
+  o.mirror = mirror != 0;
+  return launch_dgemm_oz(S(stream), M, N, K, A, lda, a_mn != 0, B, ldb, b_mn != 0, C, ldc, o, workspace, slices);
 }
 
 int gsmvi_bam_stats(const float* X, long long ldx, const float* G, long long ldg, int B, int D, int B_total,

@@ -367,3 +367,33 @@ def potrf_h3(Sigma, L_out, Lh, D, bad_flag, ws, zero_upper=True):
     """L_out <- chol(Sigma[:D,:D]) (fp32) and Lh <- its fp16 split; bad_flag <- 0 if PD else 1.  No sync."""
     check(lib().gsmvi_potrf_h3(ptr(Sigma), Sigma.stride(0), ptr(L_out), L_out.stride(0), Lh.ref, D, ptr(bad_flag), ptr(ws),
                                int(zero_upper), stream_ptr()), "gsmvi_potrf_h3")
+
+
+# ------------------------------------------------------------------------------------------------ fp64 on int8 tensor cores
+def _declare_oz(L):
+    L.gsmvi_dgemm_oz_workspace_bytes.restype = c_ll
+    L.gsmvi_dgemm_oz_workspace_bytes.argtypes = [c_i, c_i, c_i, c_i]
+    L.gsmvi_dgemm_oz.restype = c_i
+    L.gsmvi_dgemm_oz.argtypes = [c_p, c_ll, c_i, c_p, c_ll, c_i, c_p, c_ll, c_i, c_i, c_i, c_d, c_d, c_p, c_ll, c_d, c_i,
+                                 c_i, c_p, c_i, c_p]
+
+
+_declare_h3_level = _declare
+
+
+def _declare(L):  # noqa: F811
+    _declare_h3_level(L)
+    _declare_oz(L)
+
+
+def dgemm_oz(A, B, C, M, N, K, a_mn=False, b_mn=False, alpha=1.0, beta=0.0, Cin=None, diag_add=0.0, tri=False,
+             mirror=False, slices=8, ws=None):
+    """fp64 C = alpha op(A) op(B)^T + beta Cin + diag_add I on the int8 tensor cores (gsmvi_dgemm_oz)."""
+    import torch
+    if ws is None:
+        ws = torch.empty(lib().gsmvi_dgemm_oz_workspace_bytes(M, N, K, slices) + 1024, dtype=torch.uint8, device=A.device)
+    base = (ws.data_ptr() + 1023) // 1024 * 1024
+    check(lib().gsmvi_dgemm_oz(ptr(A), A.stride(0), int(a_mn), ptr(B), B.stride(0), int(b_mn), ptr(C), C.stride(0), M, N, K,
+                               alpha, beta, ptr(Cin), Cin.stride(0) if Cin is not None else 0, diag_add, int(tri),
+                               int(mirror), ctypes.c_void_p(base), slices, stream_ptr()), "gsmvi_dgemm_oz")
+    return C

@@ -178,6 +178,15 @@ int gsmvi_dgemm(const double* A, long long lda, int a_mn, const double* B, long 
                 long long ldc, int M, int N, int K, double alpha, double beta, const double* Cin, long long ldcin,
                 double diag_add, int tri, int mirror, int krange, void* stream);
 
+/* The same fp64 contraction on the int8 tensor cores (Ozaki splitting: `slices` signed 7-bit digits per operand row,
+ * 2..8; exact int32 accumulation of every digit-pair product, fp64 recombination; K <= 8192).  The BaM solve uses it for
+ * its D^3-sized products (GSMVI_OZ_SLICES=0 in the environment falls back to the FP64-pipe kernel).
+ * workspace: gsmvi_dgemm_oz_workspace_bytes(M, N, K, slices) bytes, 1 KiB aligned. */
+long long gsmvi_dgemm_oz_workspace_bytes(int M, int N, int K, int slices);
+int gsmvi_dgemm_oz(const double* A, long long lda, int a_mn, const double* B, long long ldb, int b_mn, double* C,
+                   long long ldc, int M, int N, int K, double alpha, double beta, const double* Cin, long long ldcin,
+                   double diag_add, int tri, int mirror, void* workspace, int slices, void* stream);
+
 /* BaM batch statistics.  Replaces gsmvi/bam.py:49-57 (xbar, C, gbar; vmapped outer products there).  Inputs are the
  * fp32 samples / scores; the statistics are fp64 (V = S0 + reg*C multiplies C's rounding by reg, ~100 early on).
  * stats_workspace (gsmvi_workspace_bytes(GSMVI_WS_BAM_STATS, B, D)) layout, in DOUBLES with ld = roundup(D, 8):

@@ -37,6 +37,24 @@ def test_dgemm_matches_fp64(lib, M, N, K, a_mn, b_mn):
     assert float((C - ref).norm() / ref.norm()) < 1e-14
 
 
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(1024, 1024, 1024, False, True), (1100, 1024, 1000, True, True),
+                                             (256, 384, 200, False, False)])
+def test_dgemm_on_int8_tensor_cores_matches_fp64(lib, M, N, K, a_mn, b_mn):
+    """Ozaki-split fp64 GEMM (tcgen05 kind::i8, exact int32 accumulation): 8 digits reproduce fp64 to ~1e-15 normwise."""
+    g = torch.Generator().manual_seed(M + K)
+    A = torch.randn(M, K, generator=g, dtype=torch.float64).cuda()
+    B = torch.randn(N, K, generator=g, dtype=torch.float64).cuda()
+    Aop = A.t().contiguous() if a_mn else A
+    Bop = B.t().contiguous() if b_mn else B
+    ref = A @ B.t()
+    C = torch.full((M, N), float("nan"), dtype=torch.float64, device="cuda")
+    lib.dgemm_oz(Aop, Bop, C, M, N, K, a_mn=a_mn, b_mn=b_mn, slices=8)
+    assert float((C - ref).norm() / ref.norm()) < 5e-15
+    Cin = torch.randn(M, N, generator=g, dtype=torch.float64).cuda()
+    lib.dgemm_oz(Aop, Bop, C, M, N, K, a_mn=a_mn, b_mn=b_mn, alpha=-0.5, beta=2.0, Cin=Cin, slices=6)
+    assert float((C - (-0.5 * ref + 2.0 * Cin)).norm() / ref.norm()) < 5e-11
+
+
 def test_dgemm_tri_mirror_and_kranges(lib):
     n = 333
     g = torch.Generator().manual_seed(3)

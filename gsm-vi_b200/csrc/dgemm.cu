@@ -12,6 +12,8 @@
 // Operand conventions match tc_gemm.cuh: K-major operand = [rows, K] row-major, MN-major = [K, rows] row-major.
 #include "dgemm.cuh"
 
+#include <stdlib.h>
+
 namespace gsmvi {
 
 constexpr int DBK = 16, DTHREADS = 256;
@@ -152,6 +154,223 @@ __global__ void __launch_bounds__(DTHREADS, (DBM == 128) ? 1 : 2) dgemm_kernel(c
   }
 }
 
+// ------------------------------------------------------------------------------------------------ DMMA variant
+// Same tiling and register-staged double buffering, but the inner product runs on the FP64 tensor-core path
+// (mma.sync m8n8k4): a warp owns a (DBM/2) x (DBN/4) sub-tile as 8x8 accumulator blocks, operand fragments are one
+// 8-byte shared-memory load per thread and feed 4 (A) / 8 (B) MMAs each, so the kernel needs 12 shared-memory wavefronts
+// per 32 MMAs where the DFMA version needs 12 per 64 FMAs and is co-limited by shared-memory bandwidth.
+// smem layout [k][row] with row stride DBM + 4 doubles: the 4 (k) x 8 (row) fragment touches 32 distinct 8-byte slots.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// m16n8k16: A fragment a_i at row g + 8 (i & 1), k = t + 4 (i >> 1); B fragment b_i at k = t + 4 i, column g;
+// C fragment c0, c1 at row g, columns 2t, 2t+1 and c2, c3 at row g + 8 (g = lane / 4, t = lane % 4).
+__device__ __forceinline__ void dmma16816(double (&c)[4], const double (&a)[8], const double (&b)[4]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0, %1, %2, %3}, {%4, %5, %6, %7, %8, %9, %10, %11}, "
+      "{%12, %13, %14, %15}, {%0, %1, %2, %3};"
+      : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(b[0]), "d"(b[1]),
+        "d"(b[2]), "d"(b[3]));
+}
+
+template <int ROWS, bool MN>
+__device__ __forceinline__ void dstore4(double* __restrict__ S, const double (&reg)[ROWS * DBK / DTHREADS]) {
+  constexpr int PER = ROWS * DBK / DTHREADS;
+#pragma unroll
+  for (int e = 0; e < PER; ++e) {
+    const int idx = threadIdx.x + e * DTHREADS;
+    int r, k;
+    if (MN) {
+      r = idx % ROWS;
+      k = idx / ROWS;
+    } else {
+      k = idx % DBK;
+      r = idx / DBK;
+    }
+    if (MN) S[k * (ROWS + 4) + r] = reg[e];  // rows arrive contiguous: [k][row], conflict-free stores
+    else S[r * (DBK + 4) + k] = reg[e];       // k arrives contiguous: [row][k] with stride 20 keeps stores AND fragments conflict-free
+  }
+}
+// element (row r, k) of a staged operand tile
+template <int ROWS, bool MN>
+__device__ __forceinline__ int sidx(int r, int k) {
+  return MN ? k * (ROWS + 4) + r : r * (DBK + 4) + k;
+}
+
+template <int DBM, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(DTHREADS, (DBM == 128) ? 1 : 2) dgemm_mma_kernel(const DgemmArgs a) {
+  constexpr int DBN = DBM;
+  constexpr int WM = DBM / 2, WN = DBN / 4;  // warp sub-tile (8 warps as 2 x 4)
+  constexpr int BI = WM / 8, BJ = WN / 8;    // 8x8 blocks per warp
+  __shared__ __align__(16) double As[DBM * (DBK + 4)];  // covers both [row][k+4] and [k][row+4]
+  __shared__ __align__(16) double Bs[DBN * (DBK + 4)];
+  int tm, tn;
+  {
+    const int tiles_n = (a.N + DBN - 1) / DBN;
+    tm = blockIdx.x / tiles_n;
+    tn = blockIdx.x % tiles_n;
+    if (a.tri && tn > tm) return;  // lower tiles only
+  }
+  const int m0 = tm * DBM, n0 = tn * DBN;
+  int k_begin = 0, k_end = a.K;
+  if (a.krange & KR_A_LOWER) k_end = min(k_end, m0 + DBM);
+  if (a.krange & KR_B_LOWER) k_end = min(k_end, n0 + DBN);
+  if (a.krange & KR_A_UPPER) k_begin = max(k_begin, m0);
+  if (a.krange & KR_B_UPPER) k_begin = max(k_begin, n0);
+  k_begin = (k_begin / DBK) * DBK;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wr = (warp >> 2) * WM, wc = (warp & 3) * WN;  // this warp's sub-tile origin inside the CTA tile
+  const int fr = lane >> 2, fk = lane & 3;                 // fragment row / k of this lane
+  double acc[BI][BJ][2];
+#pragma unroll
+  for (int i = 0; i < BI; ++i)
+#pragma unroll
+    for (int j = 0; j < BJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  double ra[DBM * DBK / DTHREADS], rb[DBN * DBK / DTHREADS];
+  if (k_begin < k_end) {
+    dload<DBM, A_MN>(a.A, a.lda, a.M, a.K, m0, k_begin, ra);
+    dload<DBN, B_MN>(a.B, a.ldb, a.N, a.K, n0, k_begin, rb);
+  }
+  for (int k0 = k_begin; k0 < k_end; k0 += DBK) {
+    __syncthreads();
+    dstore4<DBM, A_MN>(As, ra);
+    dstore4<DBN, B_MN>(Bs, rb);
+    __syncthreads();
+    if (k0 + DBK < k_end) {
+      dload<DBM, A_MN>(a.A, a.lda, a.M, a.K, m0, k0 + DBK, ra);
+      dload<DBN, B_MN>(a.B, a.ldb, a.N, a.K, n0, k0 + DBK, rb);
+    }
+#pragma unroll
+    for (int k4 = 0; k4 < DBK; k4 += 4) {
+      double af[BI], bf[BJ];
+#pragma unroll
+      for (int i = 0; i < BI; ++i) af[i] = As[sidx<DBM, A_MN>(wr + fr + 8 * i, k4 + fk)];
+#pragma unroll
+      for (int j = 0; j < BJ; ++j) bf[j] = Bs[sidx<DBN, B_MN>(wc + fr + 8 * j, k4 + fk)];
+#pragma unroll
+      for (int i = 0; i < BI; ++i)
+#pragma unroll
+        for (int j = 0; j < BJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  // epilogue: block (i, j): lane holds row 8 i + lane / 4, columns 8 j + 2 (lane % 4) + {0, 1} of the warp sub-tile
+#pragma unroll
+  for (int i = 0; i < BI; ++i) {
+    const int m = m0 + wr + 8 * i + fr;
+    if (m >= a.M) continue;
+#pragma unroll
+    for (int j = 0; j < BJ; ++j)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int n = n0 + wc + 8 * j + 2 * fk + u;
+        if (n >= a.N) continue;
+        if (a.tri && n > m) continue;
+        double v = a.alpha * acc[i][j][u];
+        if (a.beta != 0.0) v += a.beta * a.Cin[static_cast<long long>(m) * a.ldcin + n];
+        if (m == n) v += a.diag_add;
+        a.C[static_cast<long long>(m) * a.ldc + n] = v;
+        if (a.mirror && n != m) a.C[static_cast<long long>(n) * a.ldc + m] = v;
+      }
+  }
+}
+
+template <int DBM, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(DTHREADS, (DBM == 128) ? 1 : 2) dgemm_mma16_kernel(const DgemmArgs a) {
+  constexpr int DBN = DBM;
+  constexpr int WM = DBM / 2, WN = DBN / 4;   // warp sub-tile (8 warps as 2 x 4)
+  constexpr int BI = WM / 16, BJ = WN / 8;    // 16x8 blocks per warp
+  static_assert(DBK == 16, "one m16n8k16 step per staged k-block");
+  __shared__ __align__(16) double As[DBM * (DBK + 4)];  // covers both [row][k+4] and [k][row+4]
+  __shared__ __align__(16) double Bs[DBN * (DBK + 4)];
+  int tm, tn;
+  {
+    const int tiles_n = (a.N + DBN - 1) / DBN;
+    tm = blockIdx.x / tiles_n;
+    tn = blockIdx.x % tiles_n;
+    if (a.tri && tn > tm) return;
+  }
+  const int m0 = tm * DBM, n0 = tn * DBN;
+  int k_begin = 0, k_end = a.K;
+  if (a.krange & KR_A_LOWER) k_end = min(k_end, m0 + DBM);
+  if (a.krange & KR_B_LOWER) k_end = min(k_end, n0 + DBN);
+  if (a.krange & KR_A_UPPER) k_begin = max(k_begin, m0);
+  if (a.krange & KR_B_UPPER) k_begin = max(k_begin, n0);
+  k_begin = (k_begin / DBK) * DBK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wr = (warp >> 2) * WM, wc = (warp & 3) * WN;
+  const int fg = lane >> 2, ft = lane & 3;
+  double acc[BI][BJ][4];
+#pragma unroll
+  for (int i = 0; i < BI; ++i)
+#pragma unroll
+    for (int j = 0; j < BJ; ++j)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[i][j][u] = 0.0;
+  double ra[DBM * DBK / DTHREADS], rb[DBN * DBK / DTHREADS];
+  if (k_begin < k_end) {
+    dload<DBM, A_MN>(a.A, a.lda, a.M, a.K, m0, k_begin, ra);
+    dload<DBN, B_MN>(a.B, a.ldb, a.N, a.K, n0, k_begin, rb);
+  }
+  for (int k0 = k_begin; k0 < k_end; k0 += DBK) {
+    __syncthreads();
+    dstore4<DBM, A_MN>(As, ra);
+    dstore4<DBN, B_MN>(Bs, rb);
+    __syncthreads();
+    if (k0 + DBK < k_end) {
+      dload<DBM, A_MN>(a.A, a.lda, a.M, a.K, m0, k0 + DBK, ra);
+      dload<DBN, B_MN>(a.B, a.ldb, a.N, a.K, n0, k0 + DBK, rb);
+    }
+    double af[BI][8], bf[BJ][4];
+#pragma unroll
+    for (int i = 0; i < BI; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) af[i][e] = As[sidx<DBM, A_MN>(wr + 16 * i + fg + 8 * (e & 1), ft + 4 * (e >> 1))];
+#pragma unroll
+    for (int j = 0; j < BJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) bf[j][e] = Bs[sidx<DBN, B_MN>(wc + 8 * j + fg, ft + 4 * e)];
+#pragma unroll
+    for (int i = 0; i < BI; ++i)
+#pragma unroll
+      for (int j = 0; j < BJ; ++j) dmma16816(acc[i][j], af[i], bf[j]);
+  }
+#pragma unroll
+  for (int i = 0; i < BI; ++i)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = m0 + wr + 16 * i + fg + 8 * h;
+      if (m >= a.M) continue;
+#pragma unroll
+      for (int j = 0; j < BJ; ++j)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int n = n0 + wc + 8 * j + 2 * ft + u;
+          if (n >= a.N) continue;
+          if (a.tri && n > m) continue;
+          double v = a.alpha * acc[i][j][2 * h + u];
+          if (a.beta != 0.0) v += a.beta * a.Cin[static_cast<long long>(m) * a.ldcin + n];
+          if (m == n) v += a.diag_add;
+          a.C[static_cast<long long>(m) * a.ldc + n] = v;
+          if (a.mirror && n != m) a.C[static_cast<long long>(n) * a.ldc + m] = v;
+        }
+    }
+}
+
+static int dgemm_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GSMVI_DGEMM");  // fma: DFMA kernel; mma8: m8n8k4; default: m16n8k16
+    v = (e && e[0] == 'f') ? 0 : ((e && e[0] == 'm' && e[3] == '8') ? 1 : 2);
+  }
+  return v;
+}
+
 int launch_dgemm(cudaStream_t stream, int M, int N, int K, const double* A, long long lda, bool a_mn, const double* B,
                  long long ldb, bool b_mn, double* C, long long ldc, const DgemmOpts& o) {
   if (M <= 0 || N <= 0 || K < 0 || !C || (K > 0 && (!A || !B))) return GSMVI_EINVAL;
@@ -164,15 +383,21 @@ int launch_dgemm(cudaStream_t stream, int M, int N, int K, const double* A, long
   a.tri = o.tri ? 1 : 0; a.mirror = o.mirror ? 1 : 0; a.krange = o.krange;
   const long long tiles128 = static_cast<long long>((M + 127) / 128) * ((N + 127) / 128);
   const bool big = (o.tri ? tiles128 / 2 : tiles128) >= 120;  // enough 128x128 tiles to fill 148 SMs
-#define GSMVI_DG(BMV)                                                                            \
-  {                                                                                              \
-    const int grid = ((M + BMV - 1) / BMV) * ((N + BMV - 1) / BMV);                              \
-    if (!a_mn && !b_mn) dgemm_kernel<BMV, false, false><<<grid, DTHREADS, 0, stream>>>(a);        \
-    else if (a_mn && !b_mn) dgemm_kernel<BMV, true, false><<<grid, DTHREADS, 0, stream>>>(a);     \
-    else if (!a_mn && b_mn) dgemm_kernel<BMV, false, true><<<grid, DTHREADS, 0, stream>>>(a);     \
-    else dgemm_kernel<BMV, true, true><<<grid, DTHREADS, 0, stream>>>(a);                         \
+#define GSMVI_DG(KERN, BMV)                                                              \
+  {                                                                                      \
+    const int grid = ((M + BMV - 1) / BMV) * ((N + BMV - 1) / BMV);                      \
+    if (!a_mn && !b_mn) KERN<BMV, false, false><<<grid, DTHREADS, 0, stream>>>(a);        \
+    else if (a_mn && !b_mn) KERN<BMV, true, false><<<grid, DTHREADS, 0, stream>>>(a);     \
+    else if (!a_mn && b_mn) KERN<BMV, false, true><<<grid, DTHREADS, 0, stream>>>(a);     \
+    else KERN<BMV, true, true><<<grid, DTHREADS, 0, stream>>>(a);                         \
   }
-  if (big) GSMVI_DG(128) else GSMVI_DG(64)
+  if (dgemm_variant() == 2) {
+    if (big) GSMVI_DG(dgemm_mma16_kernel, 128) else GSMVI_DG(dgemm_mma16_kernel, 64)
+  } else if (dgemm_variant() == 1) {
+    if (big) GSMVI_DG(dgemm_mma_kernel, 128) else GSMVI_DG(dgemm_mma_kernel, 64)
+  } else {
+    if (big) GSMVI_DG(dgemm_kernel, 128) else GSMVI_DG(dgemm_kernel, 64)
+  }
 #undef GSMVI_DG
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);

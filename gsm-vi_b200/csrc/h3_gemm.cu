@@ -28,13 +28,27 @@ static int make_tmap_h(CUtensorMap* out, const __half* ptr, long long rows, long
 
 template <bool A_MN, bool B_MN>
 static int launch_h3_one(cudaStream_t stream, const H3Args& args, const CUtensorMap& tah, const CUtensorMap& tbh,
-                         const CUtensorMap& tal, const CUtensorMap& tbl, dim3 grid) {
+                         const CUtensorMap& tal, const CUtensorMap& tbl, dim3 grid, bool pdl) {
   static bool attr_set = false;
   auto kern = gemm_h3_kernel<A_MN, B_MN>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
+  }
+  if (pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(H3_THREADS);
+    cfg.dynamicSmemBytes = H3_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args, tah, tbh, tal, tbl);
+    return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
   }
   kern<<<grid, H3_THREADS, H3_SMEM_BYTES, stream>>>(args, tah, tbh, tal, tbl);
   cudaError_t e = cudaGetLastError();
@@ -81,10 +95,10 @@ int launch_gemm_h3(cudaStream_t stream, int M, int N, int K, const HView& A, con
   if ((rc = make_tmap_h(&tbh, B.hi, B.rows, B.cols, B.ld, abc, bbr)) != GSMVI_OK) return rc;
   if ((rc = make_tmap_h(&tbl, B.lo, B.rows, B.cols, B.ld, abc, bbr)) != GSMVI_OK) return rc;
 
-  if (!o.a_mn && !o.b_mn) return launch_h3_one<false, false>(stream, a, tah, tbh, tal, tbl, grid);
-  if (o.a_mn && !o.b_mn) return launch_h3_one<true, false>(stream, a, tah, tbh, tal, tbl, grid);
-  if (!o.a_mn && o.b_mn) return launch_h3_one<false, true>(stream, a, tah, tbh, tal, tbl, grid);
-  return launch_h3_one<true, true>(stream, a, tah, tbh, tal, tbl, grid);
+  if (!o.a_mn && !o.b_mn) return launch_h3_one<false, false>(stream, a, tah, tbh, tal, tbl, grid, o.pdl);
+  if (o.a_mn && !o.b_mn) return launch_h3_one<true, false>(stream, a, tah, tbh, tal, tbl, grid, o.pdl);
+  if (!o.a_mn && o.b_mn) return launch_h3_one<false, true>(stream, a, tah, tbh, tal, tbl, grid, o.pdl);
+  return launch_h3_one<true, true>(stream, a, tah, tbh, tal, tbl, grid, o.pdl);
 }
 
 // ------------------------------------------------------------------------------------------------ operand split

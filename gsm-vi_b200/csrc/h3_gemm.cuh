@@ -166,6 +166,10 @@ gemm_h3_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, con
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above overlapped the tail of the previous kernel in the stream; from here
+  // on its results are needed (no-ops when the kernel was launched without the attribute)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -376,6 +380,7 @@ struct H3Opts {
   unsigned* absmax_out = nullptr;
   int splits = 1;
   long long split_stride = 0;
+  bool pdl = false;                   // launch with programmatic stream serialization (prologue overlaps the previous kernel)
   float* const* push_base = nullptr;  // push mode, see H3Args
   long long push_stage_off = 0, push_cnt_off = 0;
   int push_rank = 0, push_world = 1, push_tpo = 0;

@@ -234,6 +234,9 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_h3_kernel(const PanelArgs 
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int j0 = a.j0, nb = a.nb, n = a.n;
+  // programmatic dependent launch: the launch itself overlapped the tail of the update GEMM; its partials are needed now
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const float sl = *a.scale_l;
   if (tid == 0) bad = 0;
 
@@ -664,6 +667,12 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
     max_ctas = sms > 17 ? sms : 148;  // one CTA per SM; helpers need 16 TRSM CTAs
   }
   const bool timing = getenv("GSMVI_POTRF_TIMING") != nullptr;
+  static int pdl_env = -1;
+  if (pdl_env < 0) {
+    const char* e = getenv("GSMVI_POTRF_PDL");
+    pdl_env = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool pdl = pdl_env == 1 && !timing;
   for (int j0 = 0; j0 < n; j0 += NB) {
     const int nb = min(NB, n - j0);
     const int M = n - j0, rest = M - nb;
@@ -685,6 +694,7 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
       H3Opts o;
       o.splits = S;
       o.split_stride = pa.split_stride;
+      o.pdl = pdl;
       int rc = launch_gemm_h3(stream, M, nb, j0, va, vb, partials, NB, o);
       if (rc != GSMVI_OK) return rc;
     }
@@ -697,7 +707,20 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
     }
     if (nb < NB) potrf_panel_h3_kernel<false, false><<<1, 256, PANEL_SMEM, stream>>>(pa);
     else if (timing && j0 == NB * 8) potrf_panel_h3_kernel<true, true><<<grid, 256, PANEL_SMEM, stream>>>(pa);
-    else potrf_panel_h3_kernel<true, false><<<grid, 256, PANEL_SMEM, stream>>>(pa);
+    else if (pdl) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = PANEL_SMEM;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t le = cudaLaunchKernelEx(&cfg, potrf_panel_h3_kernel<true, false>, pa);
+      if (le != cudaSuccess) return static_cast<int>(le);
+    } else potrf_panel_h3_kernel<true, false><<<grid, 256, PANEL_SMEM, stream>>>(pa);
   }
   if (timing && n > NB * 9) {
     long long h[64];

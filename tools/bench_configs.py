@@ -28,11 +28,12 @@ def timed(fn, n, warm):
 # configs[1]: GSM D=512, B=64, dense-Gaussian target, 1000 iterations
 mean_t, cov_t = orc.dense_gaussian_target(512, 0)
 tgt = DenseGaussianTarget(mean_t, cov_t)
-eng = GSMEngine(512, 64, tgt.lp_g, key=99)
-ms = timed(eng.step, 1000, 20)
-out["gsm_D512_B64"] = {"ms_per_iter": ms, "iters_per_s": 1e3 / ms, "launches_per_iter": eng.launches_per_step(),
-                       "algorithmic_gflop_per_iter": (9 * 64 * 512**2 + 512**3 / 3) / 1e9, "reverts": eng.n_reverts}
-print(out["gsm_D512_B64"], flush=True)
+for npass in (4, 3):
+    eng = GSMEngine(512, 64, tgt.lp_g, key=99, npass=npass)
+    ms = timed(eng.step, 1000, 20)
+    out["gsm_D512_B64_npass%d" % npass] = {"ms_per_iter": ms, "iters_per_s": 1e3 / ms, "launches_per_iter": eng.launches_per_step(),
+                                           "algorithmic_gflop_per_iter": (9 * 64 * 512**2 + 512**3 / 3) / 1e9, "reverts": eng.n_reverts}
+    print(npass, out["gsm_D512_B64_npass%d" % npass], flush=True)
 # configs[2]: BaM D=1024, B=256, ill-conditioned Gaussian target kappa=1e2, schedule 100/(1+i), full and low-rank
 mean_t, cov_t = orc.illcond_gaussian_target(1024, 1e2, 0)
 tgt = DenseGaussianTarget(mean_t, cov_t)

@@ -95,15 +95,20 @@ int gsmvi_philox_normal_h3(const gsmvi_h3_operand* Z, int B, int D, unsigned lon
 }
 
 int gsmvi_sample_h3(const float* mu, const gsmvi_h3_operand* L, const gsmvi_h3_operand* Z, float* X, long long ldx,
-                    unsigned* absmax_x, int B, int D, void* stream) {
+                    unsigned* absmax_x, const gsmvi_h3_operand* X_split, int B, int D, void* stream) {
   if (!mu || !L || !Z || !X || B <= 0 || D <= 0) return GSMVI_EINVAL;
-  return sample_mvn_h3(S(stream), mu, *L, *Z, X, ldx, absmax_x, B, D);
+  return sample_mvn_h3(S(stream), mu, *L, *Z, X, ldx, absmax_x, B, D, X_split);
 }
 
 int gsmvi_gauss_score_h3(const gsmvi_h3_operand* X, const gsmvi_h3_operand* P, const float* c, float* G, long long ldg,
-                         unsigned* absmax_g, int B, int D, void* stream) {
+                         unsigned* absmax_g, const gsmvi_h3_operand* G_split, int B, int D, void* stream) {
   if (!X || !P || !c || !G || B <= 0 || D <= 0) return GSMVI_EINVAL;
-  return gauss_score_h3(S(stream), *X, *P, c, G, ldg, absmax_g, B, D);
+  return gauss_score_h3(S(stream), *X, *P, c, G, ldg, absmax_g, B, D, G_split);
+}
+
+int gsmvi_h3_bound_scales(const float* mu, int D, const unsigned* sigma_absmax, const unsigned* zmax_bits, float zmax_const,
+                          float pnorm, float cmax, float* scale_x, float* scale_g, void* stream) {
+  return h3_bound_scales(S(stream), mu, D, sigma_absmax, zmax_bits, zmax_const, pnorm, cmax, scale_x, scale_g);
 }
 
 int gsmvi_gsm_update_h3(const float* X, long long ldx, const float* G, long long ldg, const gsmvi_h3_operand* G_split,

@@ -402,22 +402,34 @@ static inline HView hview(const H3Operand& o, long long rows, long long cols) {
 }
 
 int sample_mvn_h3(cudaStream_t stream, const float* mu, const H3Operand& L, const H3Operand& Z, float* X, long long ldx,
-                  unsigned* absmax_x, int B, int D) {
+                  unsigned* absmax_x, int B, int D, const H3Operand* Xsplit) {
   // X[b,i] = mu[i] + sum_{k<=i} Z[b,k] L[i,k]
   H3Opts o;
   o.bias_n = mu;
   o.krange = KR_B_LOWER;
   o.absmax_out = absmax_x;
+  if (Xsplit) {  // the epilogue also writes X as the fp16 pair with the caller's (a-priori) scale
+    o.split_hi = static_cast<__half*>(Xsplit->hi);
+    o.split_lo = static_cast<__half*>(Xsplit->lo);
+    o.split_ld = Xsplit->ld;
+    o.split_scale = Xsplit->scale;
+  }
   return launch_gemm_h3(stream, B, D, D, hview(Z, B, D), hview(L, D, D), X, ldx, o);
 }
 
 int gauss_score_h3(cudaStream_t stream, const H3Operand& X, const H3Operand& P, const float* c, float* G, long long ldg,
-                   unsigned* absmax_g, int B, int D) {
+                   unsigned* absmax_g, int B, int D, const H3Operand* Gsplit) {
   // G = -X P + c,  c = P m   (P symmetric: P[n,k] read K-major as-is)
   H3Opts o;
   o.alpha = -1.0f;
   o.bias_n = c;
   o.absmax_out = absmax_g;
+  if (Gsplit) {
+    o.split_hi = static_cast<__half*>(Gsplit->hi);
+    o.split_lo = static_cast<__half*>(Gsplit->lo);
+    o.split_ld = Gsplit->ld;
+    o.split_scale = Gsplit->scale;
+  }
   return launch_gemm_h3(stream, B, D, D, hview(X, B, D), hview(P, D, D), G, ldg, o);
 }
 

@@ -24,9 +24,9 @@ typedef gsmvi_h3_operand H3Operand;
 int philox_normal_h3(cudaStream_t stream, const H3Operand& Z, int B, int D, unsigned long long seed,
                      unsigned long long offset);
 int sample_mvn_h3(cudaStream_t stream, const float* mu, const H3Operand& L, const H3Operand& Z, float* X, long long ldx,
-                  unsigned* absmax_x, int B, int D);
+                  unsigned* absmax_x, int B, int D, const H3Operand* Xsplit = nullptr);
 int gauss_score_h3(cudaStream_t stream, const H3Operand& X, const H3Operand& P, const float* c, float* G, long long ldg,
-                   unsigned* absmax_g, int B, int D);
+                   unsigned* absmax_g, int B, int D, const H3Operand* Gsplit = nullptr);
 size_t gsm_update_h3_workspace_bytes(int B, int D);
 int gsm_update_h3(cudaStream_t stream, const float* X, long long ldx, const float* G, long long ldg, const H3Operand& Gh,
                   const float* mu, const float* Sigma, long long lds, const H3Operand& Sh, float* mu_out, float* Sigma_out,

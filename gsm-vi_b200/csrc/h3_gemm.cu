@@ -82,6 +82,11 @@ int launch_gemm_h3(cudaStream_t stream, int M, int N, int K, const HView& A, con
   a.push_rank = o.push_rank;
   a.push_world = o.push_world;
   a.push_tpo = o.push_tpo;
+  a.split_hi = o.split_hi;
+  a.split_lo = o.split_lo;
+  a.split_ld = o.split_ld;
+  a.split_scale = o.split_scale;
+  if (o.split_hi && (!o.split_lo || !o.split_scale || (o.split_ld & 3) != 0 || o.tri || o.splits != 1 || o.push_base)) return GSMVI_EINVAL;
   if (o.push_base && (!o.tri || o.splits != 1 || o.mirror || o.beta != 0.0f || o.bias_n)) return GSMVI_EINVAL;
   const int tiles = o.tri ? a.tiles_m * (a.tiles_m + 1) / 2 : a.tiles_m * a.tiles_n;
   const dim3 grid(tiles, o.splits);
@@ -149,6 +154,34 @@ __global__ void __launch_bounds__(256) h3_split_kernel(const float* __restrict__
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(256) h3_bound_scales_kernel(const float* __restrict__ mu, int D,
+                                                              const unsigned* __restrict__ sigma_absmax,
+                                                              const unsigned* __restrict__ zmax_bits, float zmax_const,
+                                                              float pnorm, float cmax, float* __restrict__ scale_x,
+                                                              float* __restrict__ scale_g) {
+  __shared__ unsigned smax[8];
+  unsigned m = 0u;
+  for (int i = threadIdx.x; i < D; i += 256) m = max(m, __float_as_uint(fabsf(mu[i])));
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = max(m, smax[w]);
+    const float zmax = zmax_bits ? __uint_as_float(*zmax_bits) : zmax_const;
+    const float xb = __uint_as_float(m) + zmax * sqrtf(static_cast<float>(D)) * sqrtf(__uint_as_float(*sigma_absmax));
+    *scale_x = h3_scale_from_absmax(__float_as_uint(xb), 0);
+    if (scale_g) *scale_g = h3_scale_from_absmax(__float_as_uint(xb * pnorm + cmax), 0);
+  }
+}
+
+int h3_bound_scales(cudaStream_t stream, const float* mu, int D, const unsigned* sigma_absmax, const unsigned* zmax_bits,
+                    float zmax_const, float pnorm, float cmax, float* scale_x, float* scale_g) {
+  if (!mu || D <= 0 || !sigma_absmax || !scale_x) return GSMVI_EINVAL;
+  h3_bound_scales_kernel<<<1, 256, 0, stream>>>(mu, D, sigma_absmax, zmax_bits, zmax_const, pnorm, cmax, scale_x, scale_g);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
 }
 
 static inline dim3 rowwise_grid(int rows, int cols) {

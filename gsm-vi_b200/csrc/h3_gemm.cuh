@@ -65,6 +65,12 @@ struct H3Args {
   float* const* push_base;
   long long push_stage_off, push_cnt_off;
   int push_rank, push_world, push_tpo;
+  // fused split: also write C as the fp16 pair (split_hi, split_lo; leading dimension split_ld) with the GIVEN scale
+  // *split_scale - for results whose magnitude is bounded a priori, so no max|C| pass and no separate split kernel
+  __half* split_hi;
+  __half* split_lo;
+  long long split_ld;
+  const float* split_scale;
 };
 
 __host__ __device__ constexpr uint32_t make_idesc_f16(bool a_mn, bool b_mn) {
@@ -87,6 +93,8 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       : "memory");
 }
 }  // namespace ptx
+
+__device__ __forceinline__ void h3_split1(float v, float s, __half& hi, __half& lo);
 
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(H3_THREADS, 1)
@@ -125,6 +133,9 @@ gemm_h3_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, con
     const int r = t - g * per_group;
     tm = first_m + r % rows;
     tn = r / rows;
+    // triangular operand: K length grows with the tile index, so hand out the long tiles first (no long tail at the end)
+    if (args.krange & KR_B_LOWER) tn = args.tiles_n - 1 - tn;
+    if (args.krange & KR_A_LOWER) tm = args.tiles_m - 1 - tm;
   }
   const int m0 = tm * H3_BM, n0 = tn * H3_BN;
 
@@ -242,6 +253,7 @@ gemm_h3_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, con
     // ===================== epilogue: TMEM -> registers -> global =====================
     const float sa = *args.scale_a, sb = *args.scale_b;
     const float alpha = (args.alpha / sa) / sb, beta = args.beta;
+    const float ssplit = args.split_hi ? *args.split_scale : 0.0f;
     ptx::mbar_wait(acc_bar, 0);
     ptx::tc_fence_after_sync();
     const int q = warp & 3;            // TMEM lane quadrant this warp may read
@@ -309,6 +321,16 @@ gemm_h3_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, con
               o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
             }
             *reinterpret_cast<float4*>(crow + j) = o;
+            if (args.split_hi) {
+              __half h[4], l[4];
+              h3_split1(o.x, ssplit, h[0], l[0]);
+              h3_split1(o.y, ssplit, h[1], l[1]);
+              h3_split1(o.z, ssplit, h[2], l[2]);
+              h3_split1(o.w, ssplit, h[3], l[3]);
+              const long long so = static_cast<long long>(m) * args.split_ld + nbase + j;
+              *reinterpret_cast<uint2*>(args.split_hi + so) = *reinterpret_cast<const uint2*>(h);
+              *reinterpret_cast<uint2*>(args.split_lo + so) = *reinterpret_cast<const uint2*>(l);
+            }
             amax = max(max(amax, __float_as_uint(fabsf(o.x))), max(__float_as_uint(fabsf(o.y)), max(__float_as_uint(fabsf(o.z)), __float_as_uint(fabsf(o.w)))));
             r[j + 0] = __float_as_uint(o.x); r[j + 1] = __float_as_uint(o.y);
             r[j + 2] = __float_as_uint(o.z); r[j + 3] = __float_as_uint(o.w);
@@ -327,6 +349,10 @@ gemm_h3_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, con
               if (cin) o += beta * cin[j];
               if (args.bias_n) o += args.bias_n[n];
               crow[j] = o;
+              if (args.split_hi) {
+                const long long so = static_cast<long long>(m) * args.split_ld + n;
+                h3_split1(o, ssplit, args.split_hi[so], args.split_lo[so]);
+              }
               amax = max(amax, __float_as_uint(fabsf(o)));
               if (args.mirror && n != m) Cout[static_cast<long long>(n) * args.ldc + m] = o;
             }
@@ -381,6 +407,10 @@ struct H3Opts {
   int splits = 1;
   long long split_stride = 0;
   bool pdl = false;                   // launch with programmatic stream serialization (prologue overlaps the previous kernel)
+  __half* split_hi = nullptr;         // fused split of the result with a given scale, see H3Args
+  __half* split_lo = nullptr;
+  long long split_ld = 0;
+  const float* split_scale = nullptr;
   float* const* push_base = nullptr;  // push mode, see H3Args
   long long push_stage_off = 0, push_cnt_off = 0;
   int push_rank = 0, push_world = 1, push_tpo = 0;
@@ -395,6 +425,15 @@ int h3_split(cudaStream_t stream, const float* A, long long lda, int rows, int c
              float* scale_out, __half* Hi, __half* Lo, long long ldo);
 // *out <- max(*out, max |A|) as a float bit pattern (zero *out first).
 int h3_absmax(cudaStream_t stream, const float* A, long long lda, int rows, int cols, unsigned* out);
+
+// Scales for results bounded a priori (fused split in the producing GEMM's epilogue):
+//   |x_i| <= max|mu| + zmax sqrt(D) sqrt(max Sigma_ii)   (Cauchy-Schwarz on x = mu + L z, |z_k| <= zmax),
+//   |g_j| <= xbound * pnorm + cmax                        (g = -x P + c, pnorm = max_j sum_k |P_kj|).
+// The bounds are loose by up to 2^8.5 / 2^15; the fp16 pair keeps an absolute precision of 2^-35 of the scaled range
+// (hi and lo subnormals included), i.e. >= 2^-20 relative to the typical entry even then.
+// zmax_bits: device word with the bit pattern of max|z| (or null to use zmax_const); sigma_absmax: bit pattern of max|Sigma|.
+int h3_bound_scales(cudaStream_t stream, const float* mu, int D, const unsigned* sigma_absmax, const unsigned* zmax_bits,
+                    float zmax_const, float pnorm, float cmax, float* scale_x, float* scale_g);
 
 __device__ __forceinline__ float h3_scale_from_absmax(unsigned bits, int sqrt_mode) {
   float m = __uint_as_float(bits);

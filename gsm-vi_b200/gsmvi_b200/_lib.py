@@ -269,9 +269,11 @@ def _declare_h3(L):
     L.gsmvi_philox_normal_h3.restype = c_i
     L.gsmvi_philox_normal_h3.argtypes = [hp, c_i, c_i, c_ull, c_ull, c_p]
     L.gsmvi_sample_h3.restype = c_i
-    L.gsmvi_sample_h3.argtypes = [c_p, hp, hp, c_p, c_ll, c_p, c_i, c_i, c_p]
+    L.gsmvi_sample_h3.argtypes = [c_p, hp, hp, c_p, c_ll, c_p, hp, c_i, c_i, c_p]
     L.gsmvi_gauss_score_h3.restype = c_i
-    L.gsmvi_gauss_score_h3.argtypes = [hp, hp, c_p, c_p, c_ll, c_p, c_i, c_i, c_p]
+    L.gsmvi_gauss_score_h3.argtypes = [hp, hp, c_p, c_p, c_ll, c_p, hp, c_i, c_i, c_p]
+    L.gsmvi_h3_bound_scales.restype = c_i
+    L.gsmvi_h3_bound_scales.argtypes = [c_p, c_i, c_p, c_p, c_f, c_f, c_f, c_p, c_p, c_p]
     L.gsmvi_potrf_h3.restype = c_i
     L.gsmvi_potrf_h3.argtypes = [c_p, c_ll, c_p, c_ll, hp, c_i, c_p, c_p, c_i, c_p]
     L.gsmvi_gsm_update_h3.restype = c_i
@@ -343,14 +345,20 @@ def philox_normal_h3(Zh, B, D, seed, offset):
           "gsmvi_philox_normal_h3")
 
 
-def sample_h3(mu, Lh, Zh, X, absmax_x, B, D):
-    check(lib().gsmvi_sample_h3(ptr(mu), Lh.ref, Zh.ref, ptr(X), X.stride(0), ptr(absmax_x), B, D, stream_ptr()),
-          "gsmvi_sample_h3")
+def sample_h3(mu, Lh, Zh, X, absmax_x, B, D, X_split=None):
+    check(lib().gsmvi_sample_h3(ptr(mu), Lh.ref, Zh.ref, ptr(X), X.stride(0), ptr(absmax_x),
+                                X_split.ref if X_split is not None else None, B, D, stream_ptr()), "gsmvi_sample_h3")
 
 
-def gauss_score_h3(Xh, Ph, c, G, absmax_g, B, D):
-    check(lib().gsmvi_gauss_score_h3(Xh.ref, Ph.ref, ptr(c), ptr(G), G.stride(0), ptr(absmax_g), B, D, stream_ptr()),
+def gauss_score_h3(Xh, Ph, c, G, absmax_g, B, D, G_split=None):
+    check(lib().gsmvi_gauss_score_h3(Xh.ref, Ph.ref, ptr(c), ptr(G), G.stride(0), ptr(absmax_g),
+                                     G_split.ref if G_split is not None else None, B, D, stream_ptr()),
           "gsmvi_gauss_score_h3")
+
+
+def h3_bound_scales(mu, D, sigma_absmax, zmax_bits, zmax_const, pnorm, cmax, scale_x, scale_g):
+    check(lib().gsmvi_h3_bound_scales(ptr(mu), D, ptr(sigma_absmax), ptr(zmax_bits), zmax_const, pnorm, cmax, ptr(scale_x),
+                                      ptr(scale_g), stream_ptr()), "gsmvi_h3_bound_scales")
 
 
 def gsm_update_h3(X, G, Gh, mu, Sigma, Sh, mu_out, Sigma_out, absmax_sout, B, D, B_total, mode, ws):

@@ -120,9 +120,9 @@ class GSMEngine:
         if self.h3:
             potrf = 1 + panels + (panels - 1)  # prepare, panel kernels, left-looking update GEMMs
             draw = 2 if self.z_tape is not None else 1  # |Z| max + split of a tape slice, or Philox written split
-            score = 3 if self.target is not None else 2  # split X, score GEMM, split G | |G| max + split G
-            upd = 5 + 1  # W GEMM, row pass, split T, covariance GEMM, axpy + split Sigma_new
-            return draw + 1 + score + upd + potrf + (3 if self.world > 1 else 0)
+            score = 4 if self.target is not None else 3  # sample, split X, score GEMM, split G | sample, |G| max, split G
+            upd = 5 + 2  # W GEMM, row pass, split T, covariance GEMM, axpy + split Sigma_new, its max|.| word copied
+            return draw + score + upd + potrf + (3 if self.world > 1 else 0)
         potrf = 1 + panels + (panels - 1)  # tril copy, panel kernels, SYRK GEMMs
         upd = 4 + 2  # W GEMM, row pass, covariance GEMM, axpy + the two tf32_split launches (Sigma_new, L_new)
         return (0 if self.z_tape is not None else 1) + 1 + (1 if self.target is not None else 0) + upd + potrf + \
@@ -174,11 +174,14 @@ class GSMEngine:
             self.Zh.split_from(self.Z)
         else:
             L.philox_normal_h3(self.Zh, B, D, self.seed, i * self.world + self.rank)
+        tgt = self.target
         L.sample_h3(self.mu, self.Lh, self.Zh, self.Xb, sl[0:1], B, D)
-        # ---- score (gsm.py:121)
-        if self.target is not None:
+        if tgt is not None:
+            # (the GEMMs can also write their result's fp16 split themselves with an a-priori bound as scale -
+            # gsmvi_h3_bound_scales / X_split, G_split - but the strided 8-byte stores lengthen the un-overlapped epilogue
+            # by 60-75 us per launch, twice what the separate HBM-bound split pass costs: measured, not used)
             self.Xh.split_from(self.X, absmax=sl[0:1])
-            L.gauss_score_h3(self.Xh, self.target.Ph, self.target.c, self.Gb, sl[1:2], B, D)
+            L.gauss_score_h3(self.Xh, tgt.Ph, tgt.c, self.Gb, sl[1:2], B, D)
             self.Gh.split_from(self.G, absmax=sl[1:2])
         else:
             if self.score_input == "numpy":
@@ -204,6 +207,7 @@ class GSMEngine:
             self.Sb, self.Snb, self.S, self.Sn = self.Snb, self.Sb, self.Sn, self.S
             self.Lb, self.Lnb = self.Lnb, self.Lb
             self.Sh, self.Snh, self.Lh, self.Lnh = self.Snh, self.Sh, self.Lnh, self.Lh
+            self.Sh.absmax.copy_(sl[2:3])  # max|Sigma| of the accepted state (bounds the next draws)
             self.mu, self.mun = self.mun, self.mu
             if self.comm is not None:
                 self.cur = 1 - self.cur

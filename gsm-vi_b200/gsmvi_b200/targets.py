@@ -26,6 +26,9 @@ class DenseGaussianTarget:
         self.Plob, _ = new_mat(self.D, self.D, dev)
         L.tf32_split(self.Pb, self.Phib, self.Plob, self.D, self.D)
         self.Ph = L.HOperand(self.D, self.D, dev).split_from(self.P)  # fp16 (hi, lo) form for the scaled 3xFP16 engine
+        Pf = np.asarray(P, dtype=np.float32).astype(np.float64)
+        self.pnorm = float(np.abs(Pf).sum(axis=0).max())  # max_j sum_k |P_kj|: bound |x P| <= max|x| pnorm
+        self.cmax = float(np.abs(P @ mean).max())
         self.c = new_vec(self.D, dev)
         self.c[: self.D].copy_(torch.as_tensor(P @ mean, dtype=torch.float32))
         self.m = torch.as_tensor(mean, dtype=torch.float32, device=dev)

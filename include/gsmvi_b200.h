@@ -95,9 +95,15 @@ int gsmvi_h3_split(const float* A, long long lda, int rows, int cols, const unsi
 int gsmvi_philox_normal_h3(const gsmvi_h3_operand* Z, int B, int D, unsigned long long seed, unsigned long long offset,
                            void* stream);
 int gsmvi_sample_h3(const float* mu, const gsmvi_h3_operand* L, const gsmvi_h3_operand* Z, float* X, long long ldx,
-                    unsigned* absmax_x, int B, int D, void* stream);
+                    unsigned* absmax_x, const gsmvi_h3_operand* X_split, int B, int D, void* stream);
 int gsmvi_gauss_score_h3(const gsmvi_h3_operand* X, const gsmvi_h3_operand* P, const float* c, float* G, long long ldg,
-                         unsigned* absmax_g, int B, int D, void* stream);
+                         unsigned* absmax_g, const gsmvi_h3_operand* G_split, int B, int D, void* stream);
+/* X_split / G_split (optional): the epilogue also writes the result as the fp16 pair with the scale ALREADY in
+ * *X_split->scale - an a-priori bound from gsmvi_h3_bound_scales:  |x| <= max|mu| + zmax sqrt(D) sqrt(max Sigma_ii),
+ * |g| <= xbound * pnorm + cmax (pnorm = max_j sum_k |P_kj|, cmax = max|c|) - which saves the max|.| pass and the separate
+ * split kernel.  zmax_bits: device word with the bit pattern of max|z| (NULL: zmax_const, 5.9 for the Philox draws). */
+int gsmvi_h3_bound_scales(const float* mu, int D, const unsigned* sigma_absmax, const unsigned* zmax_bits, float zmax_const,
+                          float pnorm, float cmax, float* scale_x, float* scale_g, void* stream);
 int gsmvi_gsm_update_h3(const float* X, long long ldx, const float* G, long long ldg, const gsmvi_h3_operand* G_split,
                         const float* mu, const float* Sigma, long long lds, const gsmvi_h3_operand* Sigma_split,
                         float* mu_out, float* Sigma_out, long long ldso, unsigned* absmax_sout, int B, int D, int B_total,

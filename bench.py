@@ -37,14 +37,17 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  nvidia-smi takes
+    a noticeable fraction of a second to produce its first row (longer on an 8-GPU box), so the sampler is started early
+    (`start()`), rows are time-stamped on arrival, and `summary()` keeps the rows that fall inside [mark_begin, mark_end]."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
-    def __enter__(self):
+    def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
@@ -55,11 +58,22 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def wait_first_row(self, timeout=5.0):
+        t = time.time()
+        while self.proc is not None and not self.rows and time.time() - t < timeout:
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def __exit__(self, *a):
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    def stop(self):
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -68,10 +82,12 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        # a row printed at time t describes the ~20 ms before it: accept rows up to one period after the region
+        rows = [r for (t, r) in self.rows if self.t0 is not None and self.t0 <= t <= self.t1 + 0.03 and len(r) >= 7]
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
 
@@ -176,19 +192,23 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clk = ClockSampler(local).start()
     it = 0
     for _ in range(args.warmup):
         eng.step(it)
         it += 1
+    clk.wait_first_row()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        ev0.record()
-        for _ in range(args.steps):
-            eng.step(it)
-            it += 1
-        ev1.record()
-        barrier()
+    clk.mark_begin()
+    ev0.record()
+    for _ in range(args.steps):
+        eng.step(it)
+        it += 1
+    ev1.record()
+    barrier()
+    clk.mark_end()
+    clk.stop()
     ms = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([ms], device="cuda")

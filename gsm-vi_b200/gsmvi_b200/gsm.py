@@ -103,6 +103,9 @@ class GSMEngine:
             self.Sh, self.Snh, self.Lh, self.Lnh = H(D, D, dev), H(D, D, dev), H(D, D, dev), H(D, D, dev)
             self.Zh, self.Xh, self.Gh = H(B, D, dev), H(B, D, dev), H(B, D, dev)
             self.slots = torch.zeros(8, dtype=torch.int32, device=dev)  # |X|, |G|, |Sigma_new| maxima (bit patterns)
+            self.bad_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self.flag_event = torch.cuda.Event()
+            self.z_drawn_for = -1
             self.ws_u = torch.empty(L.workspace_bytes(L.WS_GSM_UPDATE_H3, B, D) // 4, dtype=torch.float32, device=dev)
             self.ws_p = torch.empty(L.workspace_bytes(L.WS_POTRF_H3, B, D) // 4, dtype=torch.float32, device=dev)
             L.potrf_h3(self.Sb, self.Lb, self.Lh, D, self.bad, self.ws_p, zero_upper=False)  # buffers start zeroed
@@ -172,7 +175,7 @@ class GSMEngine:
         if self.z_tape is not None:
             self.Z.copy_(self.z_tape[i, self.rank * B:(self.rank + 1) * B], non_blocking=True)
             self.Zh.split_from(self.Z)
-        else:
+        elif self.z_drawn_for != i:
             L.philox_normal_h3(self.Zh, B, D, self.seed, i * self.world + self.rank)
         tgt = self.target
         L.sample_h3(self.mu, self.Lh, self.Zh, self.Xb, sl[0:1], B, D)
@@ -201,8 +204,16 @@ class GSMEngine:
             L.h3_absmax(self.Sn, D, D, sl[2:3])
         # ---- goodness check = Cholesky of the new covariance, reused as the next sampling factor (gsm.py:125)
         L.potrf_h3(self.Snb, self.Lnb, self.Lnh, D, self.bad, self.ws_p, zero_upper=False)
-        self.Snh.split_from(self.Sn, absmax=sl[2:3])  # queued before the flag is read: overlap the host round trip
-        ok = int(self.bad.item()) == 0  # the step's only device->host read (4 bytes)
+        self.Snh.split_from(self.Sn, absmax=sl[2:3])
+        # the step's only device->host read (4 bytes): copy the flag, then queue the NEXT iteration's draws (they depend
+        # on nothing but the counter) so the GPU has work while the host waits for the flag and issues the next launches
+        self.bad_host.copy_(self.bad, non_blocking=True)
+        self.flag_event.record()
+        if self.z_tape is None:
+            L.philox_normal_h3(self.Zh, B, D, self.seed, (i + 1) * self.world + self.rank)
+            self.z_drawn_for = i + 1
+        self.flag_event.synchronize()
+        ok = int(self.bad_host[0]) == 0
         if ok:  # gsm.py:126-127
             self.Sb, self.Snb, self.S, self.Sn = self.Snb, self.Sb, self.Sn, self.S
             self.Lb, self.Lnb = self.Lnb, self.Lb

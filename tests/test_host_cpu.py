@@ -35,6 +35,34 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.gsmvi_workspace_bytes(99, 1, 1) == -1
 
 
+def test_h3_and_comm_host_queries_match_the_header_structs():
+    """Pure host queries of the scaled-3xFP16 / peer-exchange entry points (no GPU): workspace sizes, the exchange-buffer
+    layout, and the ctypes mirrors of the two public structs have the sizes the C header implies."""
+    from gsmvi_b200 import _lib
+    from gsmvi_b200._comm import CommLayoutC, _declare
+    lib = _lib.lib()
+    _declare(lib)
+    assert ctypes.sizeof(_lib.H3OperandC) == 32          # void*, void*, float*, long long
+    assert ctypes.sizeof(CommLayoutC) == 8 * 6 + 4 * 2   # 6 long long + 2 int
+    D, B = 4096, 4096
+    ldw = 4096
+    # W + T fp32 (4B x ld) + usum + 32 scalars, then T_hi, T_lo fp16 (3B x ld each)
+    assert lib.gsmvi_workspace_bytes(_lib.WS_GSM_UPDATE_H3, B, D) == ((4 * B + 1) * ldw + 32) * 4 + 6 * B * ldw * 2
+    assert lib.gsmvi_workspace_bytes(_lib.WS_POTRF_H3, 0, D) > 256 + 128 * 128 * 4
+    for world in (1, 2, 8):
+        lay = CommLayoutC()
+        nbytes = lib.gsmvi_comm_layout_bytes(D, world, ctypes.byref(lay))
+        ntiles = 32 * 33 // 2
+        assert lay.tiles_m == 32 and lay.tpo == -(-ntiles // world) and lay.lds == 4096
+        assert lay.stage_off == 0 and lay.s_off[0] == world * lay.tpo * 128 * 128
+        assert lay.s_off[1] - lay.s_off[0] == D * lay.lds and lay.dmu_off - lay.s_off[1] == D * lay.lds
+        assert lay.cnt_off - lay.dmu_off == world * lay.lds
+        assert nbytes == 4 * (lay.cnt_off + (lay.tpo + 2 + 31) // 32 * 32)
+    assert lib.gsmvi_comm_layout_bytes(0, 2, ctypes.byref(CommLayoutC())) == -1
+    # Ozaki scratch: digit planes of both operands + fp64 accumulator + scales
+    assert lib.gsmvi_dgemm_oz_workspace_bytes(4096, 4096, 4096, 8) >= 2 * 8 * 4096 * 4096 + 8 * 4096 * 4096
+
+
 def test_header_cites_reference_for_each_hot_path_entry():
     with open(os.path.join(ROOT, "include", "gsmvi_b200.h")) as f:
         src = f.read()

@@ -135,11 +135,12 @@ int gsmvi_comm_free(void* dev_ptr) { return comm_free(dev_ptr); }
 
 int gsmvi_gsm_update_h3_fused(const float* X, long long ldx, const float* G, long long ldg, const gsmvi_h3_operand* G_split,
                               const float* mu, const gsmvi_h3_operand* Sigma_split, float* mu_out, void* const* peer_base,
-                              const gsmvi_comm_layout* lay, int rank, int world, int cur, unsigned step, int B, int D,
+                              void* own_base, const gsmvi_comm_layout* lay, int rank, int world, int cur, unsigned step, int B, int D,
                               int B_total, void* workspace, void* stream) {
   if (!G_split || !Sigma_split || !lay) return GSMVI_EINVAL;
   return gsm_update_h3_fused(S(stream), X, ldx, G, ldg, *G_split, mu, *Sigma_split, mu_out,
-                             reinterpret_cast<float* const*>(peer_base), *lay, rank, world, cur, step, B, D, B_total, workspace);
+                             reinterpret_cast<float* const*>(peer_base), static_cast<float*>(own_base), *lay, rank, world, cur,
+                             step, B, D, B_total, workspace);
 }
 
 int gsmvi_potrf_h3(const float* Sigma, long long lds, float* L, long long ldl, const gsmvi_h3_operand* L_split, int D,

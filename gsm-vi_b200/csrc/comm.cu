@@ -55,16 +55,21 @@ struct ReduceArgs {
   float inv_btotal;
 };
 
+constexpr int RQ = 4;              // CTAs per owned tile
+constexpr int RROWS = TILE / RQ;   // rows of the tile per CTA
+
+// blockIdx.x = li * RQ + quarter for the owned tiles, then one more CTA for the mean increment.  Only the lower triangle
+// travels: each CTA stores its rows of the new tile (columns <= row on a diagonal tile) into every rank's next Sigma
+// buffer; the upper triangle is mirrored locally afterwards (comm_mirror_kernel), which halves the NVLink traffic of
+// the all-gather and keeps the result exactly symmetric.
 __global__ void __launch_bounds__(256) comm_reduce_kernel(const ReduceArgs a) {
-  extern __shared__ float tile_raw[];
-  float (*tile)[TILE + 1] = reinterpret_cast<float (*)[TILE + 1]>(tile_raw);
   const int tid = threadIdx.x;
   float* mine = a.base[a.rank];
   const int ntiles = a.lay.tiles_m * (a.lay.tiles_m + 1) / 2;
-  const int li = blockIdx.x;
+  const int li = blockIdx.x / RQ, quarter = blockIdx.x % RQ;
   const int t = li * a.world + a.rank;
   if (t >= ntiles) {
-    if (li != static_cast<int>(gridDim.x) - 1) return;
+    if (blockIdx.x != gridDim.x - 1) return;
     // last CTA: this rank's mean increment to every rank's dmu[rank][:]
     for (int p = 0; p < a.world; ++p) {
       float* dst = a.base[p] + a.lay.dmu_off + static_cast<long long>(a.rank) * a.lay.lds;
@@ -83,63 +88,36 @@ __global__ void __launch_bounds__(256) comm_reduce_kernel(const ReduceArgs a) {
   while (tm * (tm + 1) / 2 > t) --tm;
   const int tn = t - tm * (tm + 1) / 2;
   const int m0 = tm * TILE, n0 = tn * TILE;
+  const bool diag = (tm == tn);
   if (tid == 0)
     spin_until(reinterpret_cast<const unsigned*>(mine) + a.lay.cnt_off + li, static_cast<unsigned>(a.world) * (a.step + 1), "partial tiles");
   __syncthreads();
-  // sum of the partials in rank order + the current Sigma tile
   const float* stage = mine + a.lay.stage_off;
   const float* s0 = mine + a.lay.s_off[a.cur];
-  for (int q = tid; q < TILE * TILE / 4; q += 256) {
-    const int i = q >> 5, j4 = (q & 31) * 4;
+  const long long sn = a.lay.s_off[1 - a.cur];
+  // RROWS x 128 elements = RROWS * 32 float4 groups, 256 threads: sum of the partials in rank order + current Sigma
+  for (int q = tid; q < RROWS * TILE / 4; q += 256) {
+    const int i = quarter * RROWS + (q >> 5), j4 = (q & 31) * 4;
+    const int m = m0 + i;
+    if (m >= a.D || (diag && j4 > i)) continue;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = 0; r < a.world; ++r) {
       const float4 v = __ldcg(reinterpret_cast<const float4*>(stage + (static_cast<long long>(r) * a.lay.tpo + li) * (TILE * TILE) + i * TILE + j4));
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    const int m = m0 + i;
-    if (m < a.D) {
-      const float* srow = s0 + static_cast<long long>(m) * a.lay.lds + n0 + j4;
-      if (n0 + j4 + 0 < a.D) acc.x += srow[0];
-      if (n0 + j4 + 1 < a.D) acc.y += srow[1];
-      if (n0 + j4 + 2 < a.D) acc.z += srow[2];
-      if (n0 + j4 + 3 < a.D) acc.w += srow[3];
-    }
-    tile[i][j4 + 0] = acc.x; tile[i][j4 + 1] = acc.y; tile[i][j4 + 2] = acc.z; tile[i][j4 + 3] = acc.w;
-  }
-  __syncthreads();
-  const bool diag = (tm == tn);
-  const long long sn = a.lay.s_off[1 - a.cur];
-  for (int p = 0; p < a.world; ++p) {
-    float* dst = a.base[p] + sn;
-    // rows of the tile; a diagonal tile takes its upper half from the lower one so the result is exactly symmetric
-    for (int q = tid; q < TILE * TILE / 4; q += 256) {
-      const int i = q >> 5, j4 = (q & 31) * 4;
-      const int m = m0 + i;
-      if (m >= a.D) continue;
-      float v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = (diag && j4 + u > i) ? tile[j4 + u][i] : tile[i][j4 + u];
-      float* drow = dst + static_cast<long long>(m) * a.lay.lds + n0 + j4;
-      if (n0 + j4 + 3 < a.D) {
-        *reinterpret_cast<float4*>(drow) = make_float4(v[0], v[1], v[2], v[3]);
-      } else {
-        for (int u = 0; u < 4; ++u)
-          if (n0 + j4 + u < a.D) drow[u] = v[u];
-      }
-    }
-    if (!diag) {  // mirrored tile: row n0 + j of the output is column j of the tile
-      for (int q = tid; q < TILE * TILE / 4; q += 256) {
-        const int j = q >> 5, i4 = (q & 31) * 4;
-        const int n = n0 + j;
-        if (n >= a.D) continue;
-        float* drow = dst + static_cast<long long>(n) * a.lay.lds + m0 + i4;
-        if (m0 + i4 + 3 < a.D) {
-          *reinterpret_cast<float4*>(drow) = make_float4(tile[i4][j], tile[i4 + 1][j], tile[i4 + 2][j], tile[i4 + 3][j]);
-        } else {
-          for (int u = 0; u < 4; ++u)
-            if (m0 + i4 + u < a.D) drow[u] = tile[i4 + u][j];
+    const long long off = static_cast<long long>(m) * a.lay.lds + n0 + j4;
+    const bool full4 = (n0 + j4 + 3 < a.D);
+    if (full4) {
+      const float4 c = *reinterpret_cast<const float4*>(s0 + off);
+      acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+      for (int p = 0; p < a.world; ++p) *reinterpret_cast<float4*>(a.base[p] + sn + off) = acc;
+    } else {
+      const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+      for (int u = 0; u < 4; ++u)
+        if (n0 + j4 + u < a.D) {
+          const float o = v[u] + s0[off + u];
+          for (int p = 0; p < a.world; ++p) a.base[p][sn + off + u] = o;
         }
-      }
     }
   }
   __syncthreads();
@@ -149,13 +127,47 @@ __global__ void __launch_bounds__(256) comm_reduce_kernel(const ReduceArgs a) {
   }
 }
 
+// Upper triangle of the new Sigma from its lower triangle (local, after every tile has arrived): one CTA per lower tile,
+// transposed through shared memory; a diagonal tile mirrors inside itself.
+__global__ void __launch_bounds__(256) comm_mirror_kernel(float* __restrict__ S, long long lds, int D, int tiles_m) {
+  extern __shared__ float tile_raw[];
+  float (*tile)[TILE + 1] = reinterpret_cast<float (*)[TILE + 1]>(tile_raw);
+  const int t = blockIdx.x;
+  int tm = static_cast<int>((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+  while ((tm + 1) * (tm + 2) / 2 <= t) ++tm;
+  while (tm * (tm + 1) / 2 > t) --tm;
+  const int tn = t - tm * (tm + 1) / 2;
+  const int m0 = tm * TILE, n0 = tn * TILE;
+  for (int q = threadIdx.x; q < TILE * TILE / 4; q += 256) {
+    const int i = q >> 5, j4 = (q & 31) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (m0 + i < D) {
+      const float* row = S + static_cast<long long>(m0 + i) * lds + n0 + j4;
+      for (int u = 0; u < 4; ++u)
+        if (n0 + j4 + u < D) v[u] = row[u];
+    }
+    tile[i][j4] = v[0]; tile[i][j4 + 1] = v[1]; tile[i][j4 + 2] = v[2]; tile[i][j4 + 3] = v[3];
+  }
+  __syncthreads();
+  const bool diag = (tm == tn);
+  for (int q = threadIdx.x; q < TILE * TILE / 4; q += 256) {
+    const int j = q >> 5, i4 = (q & 31) * 4;  // output row n0 + j, columns m0 + i4 ..
+    if (n0 + j >= D) continue;
+    float* drow = S + static_cast<long long>(n0 + j) * lds + m0 + i4;
+    for (int u = 0; u < 4; ++u) {
+      const int i = i4 + u;
+      if (m0 + i < D && (!diag || i > j)) drow[u] = tile[i][j];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) comm_finalize_kernel(float* const* base, gsmvi_comm_layout lay, int rank, int world, int D,
                                                             unsigned step, const float* __restrict__ mu, float* __restrict__ mu_out) {
   const float* mine = base[rank];
   const unsigned* cnt = reinterpret_cast<const unsigned*>(mine) + lay.cnt_off;
   const int ntiles = lay.tiles_m * (lay.tiles_m + 1) / 2;
   if (threadIdx.x == 0) {
-    spin_until(cnt + lay.tpo, static_cast<unsigned>(ntiles) * (step + 1), "final tiles");
+    spin_until(cnt + lay.tpo, static_cast<unsigned>(ntiles) * RQ * (step + 1), "final tiles");
     spin_until(cnt + lay.tpo + 1, static_cast<unsigned>(world) * (step + 1), "mean increments");
   }
   __syncthreads();
@@ -221,8 +233,10 @@ int comm_free(void* ptr) {
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
 }
 
-int comm_reduce_broadcast(cudaStream_t stream, float* const* base, const gsmvi_comm_layout& lay, int rank, int world, int D,
-                          int cur, unsigned step, const float* usum, float inv_btotal, const float* mu, float* mu_out) {
+int comm_reduce_broadcast(cudaStream_t stream, float* const* base, float* own_base, const gsmvi_comm_layout& lay, int rank,
+                          int world, int D, int cur, unsigned step, const float* usum, float inv_btotal, const float* mu,
+                          float* mu_out) {
+  if (!own_base) return GSMVI_EINVAL;
   ReduceArgs a;
   a.base = base; a.lay = lay; a.rank = rank; a.world = world; a.D = D; a.cur = cur; a.step = step;
   a.usum = usum; a.inv_btotal = inv_btotal;
@@ -231,12 +245,13 @@ int comm_reduce_broadcast(cudaStream_t stream, float* const* base, const gsmvi_c
   constexpr int SMEM = TILE * (TILE + 1) * static_cast<int>(sizeof(float));
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(comm_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(comm_mirror_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  comm_reduce_kernel<<<mine + 1, 256, SMEM, stream>>>(a);
+  comm_reduce_kernel<<<mine * RQ + 1, 256, 0, stream>>>(a);
   comm_finalize_kernel<<<1, 256, 0, stream>>>(base, lay, rank, world, D, step, mu, mu_out);
+  comm_mirror_kernel<<<ntiles, 256, SMEM, stream>>>(own_base + lay.s_off[1 - cur], lay.lds, D, lay.tiles_m);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
 }

@@ -13,7 +13,9 @@ int comm_close(void* peer_ptr);
 int comm_free(void* ptr);
 // reduce the staged partial tiles this rank owns into the next Sigma buffer of every rank, exchange the mean increments
 // and form mu_out = mu + sum_r dmu_r (see comm.cu)
-int comm_reduce_broadcast(cudaStream_t stream, float* const* base, const gsmvi_comm_layout& lay, int rank, int world, int D,
-                          int cur, unsigned step, const float* usum, float inv_btotal, const float* mu, float* mu_out);
+// own_base: this rank's buffer (the value of base[rank], as a host-visible pointer)
+int comm_reduce_broadcast(cudaStream_t stream, float* const* base, float* own_base, const gsmvi_comm_layout& lay, int rank,
+                          int world, int D, int cur, unsigned step, const float* usum, float inv_btotal, const float* mu,
+                          float* mu_out);
 
 }  // namespace gsmvi

@@ -441,6 +441,7 @@ size_t gsm_update_h3_workspace_bytes(int B, int D) {
 
 struct FusedComm {
   float* const* base;
+  float* own_base;
   const gsmvi_comm_layout* lay;
   int rank, world, cur;
   unsigned step;
@@ -501,7 +502,7 @@ static int gsm_update_h3_impl(cudaStream_t stream, const float* X, long long ldx
     if ((rc = launch_gemm_h3(stream, D, D, 2 * B, va, vb, Sigma_out, ldso, o)) != GSMVI_OK) return rc;
   }
   if (fc)  // owners reduce + broadcast the new Sigma tiles, mean increments exchanged, mu_out formed
-    return comm_reduce_broadcast(stream, fc->base, *fc->lay, fc->rank, fc->world, D, fc->cur, fc->step, usum,
+    return comm_reduce_broadcast(stream, fc->base, fc->own_base, *fc->lay, fc->rank, fc->world, D, fc->cur, fc->step, usum,
                                  1.0f / static_cast<float>(B_total), mu, mu_out);
   vec_axpy_kernel<<<(D + 255) / 256, 256, 0, stream>>>(mode == 0 ? mu : nullptr, usum, 1.0f / static_cast<float>(B_total),
                                                       mu_out, D);
@@ -517,11 +518,11 @@ int gsm_update_h3(cudaStream_t stream, const float* X, long long ldx, const floa
 }
 
 int gsm_update_h3_fused(cudaStream_t stream, const float* X, long long ldx, const float* G, long long ldg, const H3Operand& Gh,
-                        const float* mu, const H3Operand& Sh, float* mu_out, float* const* peer_base,
+                        const float* mu, const H3Operand& Sh, float* mu_out, float* const* peer_base, float* own_base,
                         const gsmvi_comm_layout& lay, int rank, int world, int cur, unsigned step, int B, int D, int B_total,
                         void* workspace) {
-  if (!peer_base || world < 1 || rank < 0 || rank >= world || (cur != 0 && cur != 1)) return GSMVI_EINVAL;
-  FusedComm fc{peer_base, &lay, rank, world, cur, step};
+  if (!peer_base || !own_base || world < 1 || rank < 0 || rank >= world || (cur != 0 && cur != 1)) return GSMVI_EINVAL;
+  FusedComm fc{peer_base, own_base, &lay, rank, world, cur, step};
   return gsm_update_h3_impl(stream, X, ldx, G, ldg, Gh, mu, nullptr, 0, Sh, mu_out, nullptr, 0, nullptr, B, D, B_total, 1,
                             workspace, &fc);
 }

@@ -33,7 +33,7 @@ int gsm_update_h3(cudaStream_t stream, const float* X, long long ldx, const floa
                   long long ldso, unsigned* absmax_sout, int B, int D, int B_total, int mode, void* workspace);
 
 int gsm_update_h3_fused(cudaStream_t stream, const float* X, long long ldx, const float* G, long long ldg, const H3Operand& Gh,
-                        const float* mu, const H3Operand& Sh, float* mu_out, float* const* peer_base,
+                        const float* mu, const H3Operand& Sh, float* mu_out, float* const* peer_base, float* own_base,
                         const gsmvi_comm_layout& lay, int rank, int world, int cur, unsigned step, int B, int D, int B_total,
                         void* workspace);
 

@@ -36,7 +36,7 @@ def _declare(lib):
     hp = ctypes.POINTER(L.H3OperandC)
     lib.gsmvi_gsm_update_h3_fused.restype = ctypes.c_int
     lib.gsmvi_gsm_update_h3_fused.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong, hp,
-                                              ctypes.c_void_p, hp, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_void_p, hp, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.POINTER(CommLayoutC), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_uint, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                               ctypes.c_void_p]
@@ -81,7 +81,8 @@ class CommBuffer:
     def update_fused(self, X, G, Gh, mu, Sh, mu_out, cur, B, D, B_total, ws):
         """One fused update + exchange (gsmvi_gsm_update_h3_fused); the new Sigma lands in buffer 1 - cur of every rank."""
         L.check(self.lib.gsmvi_gsm_update_h3_fused(L.ptr(X), X.stride(0), L.ptr(G), G.stride(0), Gh.ref, L.ptr(mu), Sh.ref,
-                                                   L.ptr(mu_out), L.ptr(self.peer_base), ctypes.byref(self.lay), self.rank,
+                                                   L.ptr(mu_out), L.ptr(self.peer_base), ctypes.c_void_p(self.own),
+                                                   ctypes.byref(self.lay), self.rank,
                                                    self.world, cur, self.step, B, D, B_total, L.ptr(ws), L.stream_ptr()),
                 "gsmvi_gsm_update_h3_fused")
         self.step += 1

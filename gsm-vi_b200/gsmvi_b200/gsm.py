@@ -51,6 +51,8 @@ class GSMEngine:
         B = self.B = batch_size // self.world
         self.seed = key_to_seed(key)
         self.score_input = score_input
+        self._phase_on = bool(__import__("os").environ.get("GSMVI_PHASE_TIMING"))
+        self._phase_events = []
         self.h3 = npass == 4
         # state, double-buffered so a rejected update is simply not swapped in
         self.comm = None
@@ -170,6 +172,8 @@ class GSMEngine:
         """One iteration on the scaled 3xFP16 engine (same sequence as `step`)."""
         D, B = self.D, self.B
         sl = self.slots
+        tm = self._phase_mark
+        tm("start")
         sl.zero_()
         # ---- sample (gsm.py:117-119)
         if self.z_tape is not None:
@@ -178,7 +182,9 @@ class GSMEngine:
         elif self.z_drawn_for != i:
             L.philox_normal_h3(self.Zh, B, D, self.seed, i * self.world + self.rank)
         tgt = self.target
+        tm("draw")
         L.sample_h3(self.mu, self.Lh, self.Zh, self.Xb, sl[0:1], B, D)
+        tm("sample")
         if tgt is not None:
             # (the GEMMs can also write their result's fp16 split themselves with an a-priori bound as scale -
             # gsmvi_h3_bound_scales / X_split, G_split - but the strided 8-byte stores lengthen the un-overlapped epilogue
@@ -192,6 +198,7 @@ class GSMEngine:
             else:
                 self.G.copy_(to_dev(self.lp_g(self.X), self.dev))
             self.Gh.split_from(self.G)
+        tm("score+splits")
         # ---- update (gsm.py:122)
         if self.world == 1:
             L.gsm_update_h3(self.Xb, self.Gb, self.Gh, self.mu, self.Sb, self.Sh, self.mun, self.Snb, sl[2:3], B, D, B, 0,
@@ -202,9 +209,12 @@ class GSMEngine:
             self.comm.update_fused(self.Xb, self.Gb, self.Gh, self.mu, self.Sh, self.mun, self.cur, B, D, self.batch_size,
                                    self.ws_u)
             L.h3_absmax(self.Sn, D, D, sl[2:3])
+        tm("update(+exchange)")
         # ---- goodness check = Cholesky of the new covariance, reused as the next sampling factor (gsm.py:125)
         L.potrf_h3(self.Snb, self.Lnb, self.Lnh, D, self.bad, self.ws_p, zero_upper=False)
+        tm("cholesky")
         self.Snh.split_from(self.Sn, absmax=sl[2:3])
+        tm("split Sigma")
         # the step's only device->host read (4 bytes): copy the flag, then queue the NEXT iteration's draws (they depend
         # on nothing but the counter) so the GPU has work while the host waits for the flag and issues the next launches
         self.bad_host.copy_(self.bad, non_blocking=True)
@@ -226,8 +236,35 @@ class GSMEngine:
             self.n_reverts += 1
         return ok
 
+    def _phase_mark(self, name):
+        """GSMVI_PHASE_TIMING=1: CUDA-event stamps between the phases of a step; averages printed by close()."""
+        if not self._phase_on:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self._phase_events.append((name, ev))
+
+    def _phase_report(self):
+        if not self._phase_on or not self._phase_events:
+            return
+        torch.cuda.synchronize()
+        tot, cnt, order = {}, {}, []
+        prev = None
+        for name, ev in self._phase_events:
+            if name != "start" and prev is not None:
+                tot[name] = tot.get(name, 0.0) + prev.elapsed_time(ev)
+                cnt[name] = cnt.get(name, 0) + 1
+                if name not in order:
+                    order.append(name)
+            prev = ev
+        if self.rank == 0:
+            print("[gsmvi phase timing, rank 0, ms per step] " + "  ".join("%s %.3f" % (n, tot[n] / cnt[n]) for n in order),
+                  file=__import__("sys").stderr, flush=True)
+
     def close(self):
         """Release the peer-mapped exchange buffer (collective: every rank must call it)."""
+        self._phase_report()
+        self._phase_events = []
         if self.comm is not None:
             self.comm.close()
             self.comm = None

@@ -117,7 +117,8 @@ int gsmvi_gsm_update_h3(const float* X, long long ldx, const float* G, long long
  * gsmvi_gsm_update_h3_fused: gsmvi_gsm_update_h3 for a batch shard with the exchange fused in: the covariance GEMM's
  *   epilogue pushes each partial tile to its owner rank, the owner adds the partials in rank order to the current Sigma
  *   (buffer `cur` inside its comm buffer) and stores the new tile into buffer 1 - cur of every rank; mu_out = mu + the
- *   summed mean increments.  peer_base: DEVICE array of `world` comm-buffer pointers (own buffer at [rank]); `step` must
+ *   summed mean increments (only the lower triangle travels; the upper one is mirrored locally).  peer_base: DEVICE
+ *   array of `world` comm-buffer pointers (own buffer at [rank], also passed as the plain pointer own_base); `step` must
  *   increase by one per call on every rank (counters are monotonic).  Every rank must make the same sequence of calls. */
 long long gsmvi_comm_layout_bytes(int D, int world, gsmvi_comm_layout* lay);
 int gsmvi_comm_alloc(long long bytes, void** dev_ptr_out, unsigned char* handle64_out);
@@ -126,7 +127,7 @@ int gsmvi_comm_close(void* peer_ptr);
 int gsmvi_comm_free(void* dev_ptr);
 int gsmvi_gsm_update_h3_fused(const float* X, long long ldx, const float* G, long long ldg, const gsmvi_h3_operand* G_split,
                               const float* mu, const gsmvi_h3_operand* Sigma_split, float* mu_out, void* const* peer_base,
-                              const gsmvi_comm_layout* lay, int rank, int world, int cur, unsigned step, int B, int D,
+                              void* own_base, const gsmvi_comm_layout* lay, int rank, int world, int cur, unsigned step, int B, int D,
                               int B_total, void* workspace, void* stream);
 
 /* L <- chol(Sigma) (lower, upper triangle zeroed), *bad_flag <- 0 if Sigma is positive definite else 1.

@@ -18,6 +18,7 @@
 // sends after reading the slot; the Sigma buffer a peer writes is never the one this rank is still reading.
 #include "comm.cuh"
 
+#include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -96,21 +97,22 @@ __global__ void __launch_bounds__(256) comm_reduce_kernel(const ReduceArgs a) {
   const float* s0 = mine + a.lay.s_off[a.cur];
   const long long sn = a.lay.s_off[1 - a.cur];
   // RROWS x 128 elements = RROWS * 32 float4 groups, 256 threads: sum of the partials in rank order + current Sigma
+  __shared__ __align__(16) float srow[RROWS][TILE + 4];
+  const bool interior = (m0 + TILE <= a.D) && (n0 + TILE <= a.D);
   for (int q = tid; q < RROWS * TILE / 4; q += 256) {
-    const int i = quarter * RROWS + (q >> 5), j4 = (q & 31) * 4;
+    const int il = q >> 5, i = quarter * RROWS + il, j4 = (q & 31) * 4;
     const int m = m0 + i;
-    if (m >= a.D || (diag && j4 > i)) continue;
+    if (m >= a.D || (diag && !interior && j4 > i)) continue;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = 0; r < a.world; ++r) {
       const float4 v = __ldcg(reinterpret_cast<const float4*>(stage + (static_cast<long long>(r) * a.lay.tpo + li) * (TILE * TILE) + i * TILE + j4));
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     const long long off = static_cast<long long>(m) * a.lay.lds + n0 + j4;
-    const bool full4 = (n0 + j4 + 3 < a.D);
-    if (full4) {
+    if (interior) {
       const float4 c = *reinterpret_cast<const float4*>(s0 + off);
       acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
-      for (int p = 0; p < a.world; ++p) *reinterpret_cast<float4*>(a.base[p] + sn + off) = acc;
+      *reinterpret_cast<float4*>(&srow[il][j4]) = acc;  // staged: leaves as whole 512-byte rows below
     } else {
       const float v[4] = {acc.x, acc.y, acc.z, acc.w};
       for (int u = 0; u < 4; ++u)
@@ -120,8 +122,22 @@ __global__ void __launch_bounds__(256) comm_reduce_kernel(const ReduceArgs a) {
         }
     }
   }
+  if (interior) {
+    // one bulk copy (shared -> peer global) per (row, rank): 512 contiguous bytes each, full-size NVLink packets.  On a
+    // diagonal tile the entries right of the diagonal are stale; the local mirror pass overwrites them before any use.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const int il = tid & 31;
+    const uint32_t src = static_cast<uint32_t>(__cvta_generic_to_shared(&srow[il][0]));
+    const long long off = static_cast<long long>(m0 + quarter * RROWS + il) * a.lay.lds + n0;
+    for (int p = tid >> 5; p < a.world; p += 8)
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 512;" ::"l"(a.base[p] + sn + off), "r"(src) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
   __syncthreads();
   if (tid == 0) {
+    asm volatile("fence.proxy.async;" ::: "memory");
     __threadfence_system();
     for (int p = 0; p < a.world; ++p) red_release_sys(reinterpret_cast<unsigned*>(a.base[p]) + a.lay.cnt_off + a.lay.tpo, 1u);
   }

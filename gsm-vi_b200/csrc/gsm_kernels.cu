@@ -16,6 +16,8 @@
 #include "comm.cuh"
 
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace gsmvi {
 
@@ -72,16 +74,16 @@ __global__ void __launch_bounds__(RP_THREADS) gsm_rowpass_kernel(const float* __
                                                                  const float* __restrict__ mu, float* __restrict__ T,
                                                                  float* __restrict__ Tlo, long long ldt,
                                                                  float* __restrict__ usum, int B, int D,
-                                                                 unsigned* __restrict__ absmax) {
+                                                                 unsigned* __restrict__ absmax, int rows_per_cta) {
   __shared__ float s_alpha[RP_ROWS], s_beta[RP_ROWS];
   unsigned amax = 0u;  // MODE 1: bit pattern of max |e|, |u|, |d| (as unsigned, NaN > Inf > finite)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * RP_ROWS;
+  const int row0 = blockIdx.x * rows_per_cta;  // rows_per_cta <= RP_ROWS; small batches use fewer so the grid fills the GPU
   const bool vec = ((D & 3) == 0) && ((ldx & 3) == 0) && ((ldg & 3) == 0) && ((ldw & 3) == 0) && ((ldt & 3) == 0) &&
                    (((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(W) |
                       reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(mu)) & 15) == 0) &&
                    (MODE == 1 || (reinterpret_cast<uintptr_t>(Tlo) & 15) == 0);
-  for (int r = warp; r < RP_ROWS; r += RP_THREADS / 32) {
+  for (int r = warp; r < rows_per_cta; r += RP_THREADS / 32) {
     const int b = row0 + r;
     if (b >= B) break;
     const float* x = X + b * ldx;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(RP_THREADS) gsm_rowpass_kernel(const float* __
     }
   }
   __syncthreads();
-  const int nrows = min(RP_ROWS, B - row0);
+  const int nrows = min(rows_per_cta, B - row0);
   if (vec) {
     for (int j = threadIdx.x * 4; j < D; j += RP_THREADS * 4) {
       const float4 mv = *reinterpret_cast<const float4*>(mu + j);
@@ -174,6 +176,13 @@ __global__ void __launch_bounds__(RP_THREADS) gsm_rowpass_kernel(const float* __
     amax = __reduce_max_sync(0xffffffffu, amax);
     if (lane == 0 && amax != 0u) atomicMax(absmax, amax);
   }
+}
+
+// 16 rows per CTA amortise the column-sum atomics; batch shards too small to give every SM a few CTAs that way use fewer
+static inline int rowpass_rows_per_cta(int B) {
+  int r = RP_ROWS;
+  while (r > 2 && (B + r - 1) / r < 296) r >>= 1;
+  return r;
 }
 
 // out[j] = a[j] + scale * s[j]
@@ -304,7 +313,8 @@ int gsm_update(cudaStream_t stream, const float* X, long long ldx, const float* 
     if (rc != GSMVI_OK) return rc;
   }
   // (ii) row pass
-  gsm_rowpass_kernel<0><<<(B + RP_ROWS - 1) / RP_ROWS, RP_THREADS, 0, stream>>>(X, ldx, G, ldg, W, ldw, mu, T, Tlo, ldw, usum, B, D, nullptr);
+  const int rpc = rowpass_rows_per_cta(B);
+  gsm_rowpass_kernel<0><<<(B + rpc - 1) / rpc, RP_THREADS, 0, stream>>>(X, ldx, G, ldg, W, ldw, mu, T, Tlo, ldw, usum, B, D, nullptr, rpc);
   e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   // (iii) Sigma_out = [Sigma0] - (E^T U + U^T D) / B_total : rows of T are K, so both operands are MN-major views
@@ -439,6 +449,41 @@ size_t gsm_update_h3_workspace_bytes(int B, int D) {
   return static_cast<size_t>((4LL * B + 1) * ldw + 32) * sizeof(float) + static_cast<size_t>(6LL * B * ldw) * sizeof(__half);
 }
 
+// GSMVI_UPDATE_TIMING=1: CUDA-event stamps between the launches of gsm_update_h3 (synchronises; diagnostics only)
+struct UpdTimer {
+  bool on;
+  cudaStream_t st;
+  cudaEvent_t ev[10];
+  const char* name[10];
+  int n = 0;
+  explicit UpdTimer(cudaStream_t s) : st(s) {
+    static int v = -1;
+    if (v < 0) v = getenv("GSMVI_UPDATE_TIMING") ? 1 : 0;
+    on = v == 1;
+  }
+  void mark(const char* what) {
+    if (!on || n >= 10) return;
+    cudaEventCreate(&ev[n]);
+    cudaEventRecord(ev[n], st);
+    name[n++] = what;
+  }
+  void report(int rank) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    static int calls = 0;
+    if (rank == 0 && (++calls % 16) == 0) {
+      fprintf(stderr, "[gsmvi update timing, ms]");
+      for (int i = 1; i < n; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+        fprintf(stderr, " %s %.3f", name[i], ms);
+      }
+      fprintf(stderr, "\n");
+    }
+    for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+  }
+};
+
 struct FusedComm {
   float* const* base;
   float* own_base;
@@ -460,6 +505,8 @@ static int gsm_update_h3_impl(cudaStream_t stream, const float* X, long long ldx
   float* scal = usum + ldw;  // [0] = |T| max (bit pattern), [1] = T scale
   __half* Thi = reinterpret_cast<__half*>(scal + 32);
   __half* Tlo = Thi + 3LL * B * ldw;
+  UpdTimer tmr(stream);
+  tmr.mark("start");
   cudaError_t e = cudaMemsetAsync(usum, 0, (ldw + 32) * sizeof(float), stream);
   if (e != cudaSuccess) return static_cast<int>(e);
   int rc;
@@ -468,12 +515,16 @@ static int gsm_update_h3_impl(cudaStream_t stream, const float* X, long long ldx
     H3Opts o;
     if ((rc = launch_gemm_h3(stream, B, D, D, hview(Gh, B, D), hview(Sh, D, D), W, ldw, o)) != GSMVI_OK) return rc;
   }
+  tmr.mark("W");
   // (ii) row pass -> T = [E; U; D] (fp32), |T| max, column sums of U; then the fp16 split of T
-  gsm_rowpass_kernel<1><<<(B + RP_ROWS - 1) / RP_ROWS, RP_THREADS, 0, stream>>>(X, ldx, G, ldg, W, ldw, mu, T, nullptr, ldw,
-                                                                                usum, B, D, reinterpret_cast<unsigned*>(scal));
+  const int rpc = rowpass_rows_per_cta(B);
+  gsm_rowpass_kernel<1><<<(B + rpc - 1) / rpc, RP_THREADS, 0, stream>>>(X, ldx, G, ldg, W, ldw, mu, T, nullptr, ldw, usum, B, D,
+                                                                        reinterpret_cast<unsigned*>(scal), rpc);
   if ((e = cudaGetLastError()) != cudaSuccess) return static_cast<int>(e);
+  tmr.mark("rowpass");
   if ((rc = h3_split(stream, T, ldw, 3 * B, D, reinterpret_cast<const unsigned*>(scal), 0, scal + 1, Thi, Tlo, ldw)) != GSMVI_OK)
     return rc;
+  tmr.mark("splitT");
   // (iii) Sigma_out = [Sigma0] - (E^T U + U^T D) / B_total : rows of T are K, so both operands are MN-major views
   {
     H3Opts o;
@@ -501,9 +552,14 @@ static int gsm_update_h3_impl(cudaStream_t stream, const float* X, long long ldx
     HView vb{Thi + static_cast<long long>(B) * ldw, Tlo + static_cast<long long>(B) * ldw, 2LL * B, D, ldw, scal + 1};
     if ((rc = launch_gemm_h3(stream, D, D, 2 * B, va, vb, Sigma_out, ldso, o)) != GSMVI_OK) return rc;
   }
-  if (fc)  // owners reduce + broadcast the new Sigma tiles, mean increments exchanged, mu_out formed
-    return comm_reduce_broadcast(stream, fc->base, fc->own_base, *fc->lay, fc->rank, fc->world, D, fc->cur, fc->step, usum,
-                                 1.0f / static_cast<float>(B_total), mu, mu_out);
+  tmr.mark("covGEMM");
+  if (fc) {  // owners reduce + broadcast the new Sigma tiles, mean increments exchanged, mu_out formed
+    rc = comm_reduce_broadcast(stream, fc->base, fc->own_base, *fc->lay, fc->rank, fc->world, D, fc->cur, fc->step, usum,
+                               1.0f / static_cast<float>(B_total), mu, mu_out);
+    tmr.mark("reduce+finalize+mirror");
+    tmr.report(fc->rank);
+    return rc;
+  }
   vec_axpy_kernel<<<(D + 255) / 256, 256, 0, stream>>>(mode == 0 ? mu : nullptr, usum, 1.0f / static_cast<float>(B_total),
                                                       mu_out, D);
   e = cudaGetLastError();

@@ -289,13 +289,12 @@ gemm_h3_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, con
       }
       const int nbase = n0 + c0;
       if (args.push_base != nullptr) {
-        const int t = blockIdx.x, owner = t % args.push_world;
-        float* tile = args.push_base[owner] + args.push_stage_off +
-                      (static_cast<long long>(args.push_rank) * args.push_tpo + t / args.push_world) * (H3_BM * H3_BN);
-        float* prow = tile + (q * 32 + lane) * H3_BN + c0;
+        // stage the scaled tile in shared memory (the pipeline stages are idle: every MMA has retired), row stride 132
+        // floats = conflict-free float4 stores; it leaves for the owner rank as 128 bulk copies of one 512-byte row each
+        float* srow = reinterpret_cast<float*>(smem + BAR_BYTES) + (q * 32 + lane) * 132 + c0;
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(prow + j) =
+          *reinterpret_cast<float4*>(srow + j) =
               make_float4(alpha * __uint_as_float(r[j]), alpha * __uint_as_float(r[j + 1]), alpha * __uint_as_float(r[j + 2]),
                           alpha * __uint_as_float(r[j + 3]));
       } else if (m < args.M && nbase < args.N) {
@@ -365,11 +364,25 @@ gemm_h3_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, con
       if (lane == 0 && bits != 0u) atomicMax(args.absmax_out, bits);
     }
     if (args.push_base != nullptr) {
-      // all eight epilogue warps have issued their peer stores: one thread publishes the tile to its owner
+      // the tile is complete in shared memory: 128 threads send one row each (cp.async.bulk, shared -> peer global:
+      // full-size NVLink packets instead of 16-byte scattered stores), wait for their copies, then one thread
+      // publishes the tile to its owner
+      const int t = blockIdx.x, owner = t % args.push_world;
+      ptx::fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int prow = threadIdx.x - 64;
+      if (prow < H3_BM) {
+        float* tile = args.push_base[owner] + args.push_stage_off +
+                      (static_cast<long long>(args.push_rank) * args.push_tpo + t / args.push_world) * (H3_BM * H3_BN);
+        const uint32_t src = bar_base + BAR_BYTES + prow * 132 * 4;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 512;" ::"l"(tile + prow * H3_BN), "r"(src) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x == 64) {
-        const int t = blockIdx.x, owner = t % args.push_world;
         unsigned* cnt = reinterpret_cast<unsigned*>(args.push_base[owner]) + args.push_cnt_off + t / args.push_world;
+        asm volatile("fence.proxy.async;" ::: "memory");
         __threadfence_system();
         asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(cnt), "r"(1u) : "memory");
       }

@@ -89,9 +89,9 @@ int gsmvi_h3_split(const float* A, long long lda, int rows, int cols, const unsi
 }
 
 int gsmvi_philox_normal_h3(const gsmvi_h3_operand* Z, int B, int D, unsigned long long seed, unsigned long long offset,
-                           void* stream) {
+                           const unsigned long long* offset_dev, void* stream) {
   if (!Z) return GSMVI_EINVAL;
-  return philox_normal_h3(S(stream), *Z, B, D, seed, offset);
+  return philox_normal_h3(S(stream), *Z, B, D, seed, offset, offset_dev);
 }
 
 int gsmvi_sample_h3(const float* mu, const gsmvi_h3_operand* L, const gsmvi_h3_operand* Z, float* X, long long ldx,

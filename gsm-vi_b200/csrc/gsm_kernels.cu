@@ -359,7 +359,9 @@ int gsm_apply_stats(cudaStream_t stream, const float* Sigma, long long lds, cons
 // Philox4x32-10 normals written as the fp16 pair with the fixed scale 2^11 (|z| <= sqrt(-2 ln 2^-25) = 5.9 < 2^3).
 constexpr float Z_H3_SCALE = 2048.0f;
 __global__ void philox_normal_h3_kernel(__half* __restrict__ Zhi, __half* __restrict__ Zlo, long long ldz, int B, int D,
-                                        unsigned long long seed, unsigned long long offset, float* __restrict__ scale_out) {
+                                        unsigned long long seed, unsigned long long offset,
+                                        const unsigned long long* __restrict__ offset_dev, float* __restrict__ scale_out) {
+  if (offset_dev) offset = *offset_dev;  // counter kept on the device: the launch can be replayed from a CUDA graph
   const int groups_per_row = (D + 3) / 4;
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid == 0) *scale_out = Z_H3_SCALE;
@@ -398,11 +400,11 @@ __global__ void philox_normal_h3_kernel(__half* __restrict__ Zhi, __half* __rest
 }
 
 int philox_normal_h3(cudaStream_t stream, const H3Operand& Z, int B, int D, unsigned long long seed,
-                     unsigned long long offset) {
+                     unsigned long long offset, const unsigned long long* offset_dev) {
   if (!Z.hi || !Z.lo || !Z.scale || B <= 0 || D <= 0 || Z.ld < D) return GSMVI_EINVAL;
   const long long n = static_cast<long long>(B) * ((D + 3) / 4);
   philox_normal_h3_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-      static_cast<__half*>(Z.hi), static_cast<__half*>(Z.lo), Z.ld, B, D, seed, offset, Z.scale);
+      static_cast<__half*>(Z.hi), static_cast<__half*>(Z.lo), Z.ld, B, D, seed, offset, offset_dev, Z.scale);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
 }

@@ -22,7 +22,7 @@ int gsm_apply_stats(cudaStream_t stream, const float* Sigma, long long lds, cons
 // ---- scaled 3xFP16 path (h3_gemm.cuh): operands are gsmvi_h3_operand (fp16 hi / lo + device scale)
 typedef gsmvi_h3_operand H3Operand;
 int philox_normal_h3(cudaStream_t stream, const H3Operand& Z, int B, int D, unsigned long long seed,
-                     unsigned long long offset);
+                     unsigned long long offset, const unsigned long long* offset_dev = nullptr);
 int sample_mvn_h3(cudaStream_t stream, const float* mu, const H3Operand& L, const H3Operand& Z, float* X, long long ldx,
                   unsigned* absmax_x, int B, int D, const H3Operand* Xsplit = nullptr);
 int gauss_score_h3(cudaStream_t stream, const H3Operand& X, const H3Operand& P, const float* c, float* G, long long ldg,

@@ -267,7 +267,7 @@ def _declare_h3(L):
     L.gsmvi_h3_split.argtypes = [c_p, c_ll, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_ll, c_p]
     hp = ctypes.POINTER(H3OperandC)
     L.gsmvi_philox_normal_h3.restype = c_i
-    L.gsmvi_philox_normal_h3.argtypes = [hp, c_i, c_i, c_ull, c_ull, c_p]
+    L.gsmvi_philox_normal_h3.argtypes = [hp, c_i, c_i, c_ull, c_ull, c_p, c_p]
     L.gsmvi_sample_h3.restype = c_i
     L.gsmvi_sample_h3.argtypes = [c_p, hp, hp, c_p, c_ll, c_p, hp, c_i, c_i, c_p]
     L.gsmvi_gauss_score_h3.restype = c_i
@@ -340,9 +340,9 @@ def gemm_h3(A, B, C, M, N, K, a_mn=False, b_mn=False, alpha=1.0, beta=0.0, Cin=N
     return C
 
 
-def philox_normal_h3(Zh, B, D, seed, offset):
-    check(lib().gsmvi_philox_normal_h3(Zh.ref, B, D, seed & (2**64 - 1), offset & (2**64 - 1), stream_ptr()),
-          "gsmvi_philox_normal_h3")
+def philox_normal_h3(Zh, B, D, seed, offset, offset_dev=None):
+    check(lib().gsmvi_philox_normal_h3(Zh.ref, B, D, seed & (2**64 - 1), offset & (2**64 - 1), ptr(offset_dev),
+                                       stream_ptr()), "gsmvi_philox_normal_h3")
 
 
 def sample_h3(mu, Lh, Zh, X, absmax_x, B, D, X_split=None):

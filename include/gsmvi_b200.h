@@ -86,14 +86,15 @@ int gsmvi_h3_split(const float* A, long long lda, int rows, int cols, const unsi
                    float* scale_out, void* A_hi, void* A_lo, long long ldo, void* stream);
 
 /* The GSM iteration on the scaled 3xFP16 engine (same reference lines as the fp32-operand calls below).
- * gsmvi_philox_normal_h3: Z written directly as the fp16 pair (fixed scale 2^11).
+ * gsmvi_philox_normal_h3: Z written directly as the fp16 pair (fixed scale 2^11); offset_dev (optional device word)
+ *   overrides `offset`, so that the launch can sit in a replayed CUDA graph while the counter advances on the device.
  * gsmvi_sample_h3 / gsmvi_gauss_score_h3: as gsmvi_sample / gsmvi_gauss_score with pre-split operands; *absmax_x /
  *   *absmax_g (device words, zeroed by the caller) receive the bit pattern of max |X| / max |G| for the next split.
  * gsmvi_gsm_update_h3: as gsmvi_gsm_update; G is given both as fp32 (row pass) and split (W = G Sigma), Sigma both as
  *   fp32 (epilogue) and split; *absmax_sout receives max |Sigma_out| (lower tiles; Sigma_out is symmetric).
  *   workspace: gsmvi_workspace_bytes(GSMVI_WS_GSM_UPDATE_H3, B, D). */
 int gsmvi_philox_normal_h3(const gsmvi_h3_operand* Z, int B, int D, unsigned long long seed, unsigned long long offset,
-                           void* stream);
+                           const unsigned long long* offset_dev, void* stream);
 int gsmvi_sample_h3(const float* mu, const gsmvi_h3_operand* L, const gsmvi_h3_operand* Z, float* X, long long ldx,
                     unsigned* absmax_x, const gsmvi_h3_operand* X_split, int B, int D, void* stream);
 int gsmvi_gauss_score_h3(const gsmvi_h3_operand* X, const gsmvi_h3_operand* P, const float* c, float* G, long long ldg,

@@ -260,6 +260,25 @@ def test_gsm_fit_user_callable_and_philox(lib):
     assert relF(cov2, cov_t) < 2e-3
 
 
+@pytest.mark.parametrize("D,B", [(96, 32), (512, 64)])
+def test_gsm_graph_replay_matches_eager_launches(lib, monkeypatch, D, B):
+    """Built-in target + Philox draws on one GPU: after three eager steps the launches of a step are replayed from a CUDA
+    graph (one per buffer parity).  Same kernels, same Philox counters: the fit must equal the eager one up to the
+    summation order of the column-sum atomics (the only run-to-run variation of either path)."""
+    from gsmvi_b200.gsm import GSM
+    from gsmvi_b200.targets import DenseGaussianTarget
+    mean_t, cov_t = orc.dense_gaussian_target(D, 2)
+    tgt = DenseGaussianTarget(mean_t, cov_t)
+    monkeypatch.setenv("GSMVI_GRAPH", "1")
+    g1 = GSM(D, tgt.lp, tgt.lp_g)
+    m1, c1 = g1.fit(5, niter=40, batch_size=B, verbose=False)
+    monkeypatch.setenv("GSMVI_GRAPH", "0")
+    g0 = GSM(D, tgt.lp, tgt.lp_g)
+    m0, c0 = g0.fit(5, niter=40, batch_size=B, verbose=False)
+    assert g1.n_reverts == g0.n_reverts
+    assert relF(c1, c0.cpu().double().numpy()) < 1e-5 and relF(m1, m0.cpu().double().numpy()) < 1e-5
+
+
 def test_gsm_large_trajectory_parity(lib):
     """D = B = 2048, 4 iterations, identical z-tape: device loop vs fp64 oracle loop."""
     from gsmvi_b200.gsm import GSM

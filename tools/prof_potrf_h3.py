@@ -14,6 +14,10 @@ Lo3 = torch.zeros(D, D, device="cuda")
 for _ in range(2):
     L.potrf_h3(S, Lo3, Lh, D, bad, ws3, zero_upper=False)
 torch.cuda.synchronize(); print("h3 ok", int(bad.item()))
+if len(sys.argv) > 3:  # correctness against torch at this size
+    ref = torch.linalg.cholesky(S.double())
+    print("relF(L) vs fp64 cholesky: %.2e, split dequant max err %.2e" % (float((Lo3.double() - ref).norm() / ref.norm()),
+          float((Lh.dequant() - Lo3).abs().max())))
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 s.record()
 for _ in range(reps):

@@ -121,27 +121,38 @@ __global__ void __launch_bounds__(RP_THREADS) gsm_rowpass_kernel(const float* __
     for (int j = threadIdx.x * 4; j < D; j += RP_THREADS * 4) {
       const float4 mv = *reinterpret_cast<const float4*>(mu + j);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < nrows; ++r) {
-        const long long b = row0 + r;
-        const float4 xv = *reinterpret_cast<const float4*>(X + b * ldx + j);
-        const float4 wv = *reinterpret_cast<const float4*>(W + b * ldw + j);
-        const float al = s_alpha[r], be = s_beta[r];
-        float4 d, u, e;
-        d.x = mv.x - xv.x; d.y = mv.y - xv.y; d.z = mv.z - xv.z; d.w = mv.w - xv.w;
-        u.x = al * wv.x + be * d.x; u.y = al * wv.y + be * d.y; u.z = al * wv.z + be * d.z; u.w = al * wv.w + be * d.w;
-        e.x = d.x + u.x; e.y = d.y + u.y; e.z = d.z + u.z; e.w = d.w + u.w;
-        acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
-        if (MODE == 0) {
-          store_split4(T + b * ldt + j, Tlo + b * ldt + j, e);
-          store_split4(T + (b + B) * ldt + j, Tlo + (b + B) * ldt + j, u);
-          store_split4(T + (b + 2LL * B) * ldt + j, Tlo + (b + 2LL * B) * ldt + j, d);
-        } else {
-          *reinterpret_cast<float4*>(T + b * ldt + j) = e;
-          *reinterpret_cast<float4*>(T + (b + B) * ldt + j) = u;
-          *reinterpret_cast<float4*>(T + (b + 2LL * B) * ldt + j) = d;
-          amax = max(amax, max4_bits(e));
-          amax = max(amax, max4_bits(u));
-          amax = max(amax, max4_bits(d));
+      // four rows per trip: their eight loads are issued before any is consumed (the pass is HBM / L2 latency bound)
+      for (int r0 = 0; r0 < nrows; r0 += 4) {
+        float4 xv[4], wv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const long long b = row0 + min(r0 + q, nrows - 1);
+          xv[q] = *reinterpret_cast<const float4*>(X + b * ldx + j);
+          wv[q] = *reinterpret_cast<const float4*>(W + b * ldw + j);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = r0 + q;
+          if (r >= nrows) break;
+          const long long b = row0 + r;
+          const float al = s_alpha[r], be = s_beta[r];
+          float4 d, u, e;
+          d.x = mv.x - xv[q].x; d.y = mv.y - xv[q].y; d.z = mv.z - xv[q].z; d.w = mv.w - xv[q].w;
+          u.x = al * wv[q].x + be * d.x; u.y = al * wv[q].y + be * d.y; u.z = al * wv[q].z + be * d.z; u.w = al * wv[q].w + be * d.w;
+          e.x = d.x + u.x; e.y = d.y + u.y; e.z = d.z + u.z; e.w = d.w + u.w;
+          acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
+          if (MODE == 0) {
+            store_split4(T + b * ldt + j, Tlo + b * ldt + j, e);
+            store_split4(T + (b + B) * ldt + j, Tlo + (b + B) * ldt + j, u);
+            store_split4(T + (b + 2LL * B) * ldt + j, Tlo + (b + 2LL * B) * ldt + j, d);
+          } else {
+            *reinterpret_cast<float4*>(T + b * ldt + j) = e;
+            *reinterpret_cast<float4*>(T + (b + B) * ldt + j) = u;
+            *reinterpret_cast<float4*>(T + (b + 2LL * B) * ldt + j) = d;
+            amax = max(amax, max4_bits(e));
+            amax = max(amax, max4_bits(u));
+            amax = max(amax, max4_bits(d));
+          }
         }
       }
       atomicAdd(usum + j + 0, acc.x);

@@ -135,22 +135,32 @@ __global__ void __launch_bounds__(256) h3_split_kernel(const float* __restrict__
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *scale_out = s;
   const bool vec = ((lda & 3) == 0) && ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
                    (((reinterpret_cast<uintptr_t>(Hi) | reinterpret_cast<uintptr_t>(Lo)) & 7) == 0);
-  for (long long i = blockIdx.y; i < rows; i += gridDim.y) {
-    const float* row = A + i * lda;
-    __half* hrow = Hi + i * ldo;
-    __half* lrow = Lo + i * ldo;
+  // four rows per trip (blockIdx.y walks row quads): four independent 16-byte loads in flight per thread
+  for (long long i0 = 4LL * blockIdx.y; i0 < rows; i0 += 4LL * gridDim.y) {
     for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4; j < cols; j += gridDim.x * blockDim.x * 4) {
       if (vec && j + 3 < cols) {
-        const float4 v = *reinterpret_cast<const float4*>(row + j);
-        __half h[4], l[4];
-        h3_split1(v.x, s, h[0], l[0]);
-        h3_split1(v.y, s, h[1], l[1]);
-        h3_split1(v.z, s, h[2], l[2]);
-        h3_split1(v.w, s, h[3], l[3]);
-        *reinterpret_cast<uint2*>(hrow + j) = *reinterpret_cast<const uint2*>(h);
-        *reinterpret_cast<uint2*>(lrow + j) = *reinterpret_cast<const uint2*>(l);
+        float4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const long long i = (i0 + q < rows) ? i0 + q : rows - 1;
+          v[q] = *reinterpret_cast<const float4*>(A + i * lda + j);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const long long i = i0 + q;
+          if (i >= rows) break;
+          __half h[4], l[4];
+          h3_split1(v[q].x, s, h[0], l[0]);
+          h3_split1(v[q].y, s, h[1], l[1]);
+          h3_split1(v[q].z, s, h[2], l[2]);
+          h3_split1(v[q].w, s, h[3], l[3]);
+          *reinterpret_cast<uint2*>(Hi + i * ldo + j) = *reinterpret_cast<const uint2*>(h);
+          *reinterpret_cast<uint2*>(Lo + i * ldo + j) = *reinterpret_cast<const uint2*>(l);
+        }
       } else {
-        for (int t = 0; t < 4 && j + t < cols; ++t) h3_split1(row[j + t], s, hrow[j + t], lrow[j + t]);
+        for (int q = 0; q < 4 && i0 + q < rows; ++q)
+          for (int t = 0; t < 4 && j + t < cols; ++t)
+            h3_split1(A[(i0 + q) * lda + j + t], s, Hi[(i0 + q) * ldo + j + t], Lo[(i0 + q) * ldo + j + t]);
       }
     }
   }
@@ -205,7 +215,9 @@ int h3_absmax(cudaStream_t stream, const float* A, long long lda, int rows, int 
 int h3_split(cudaStream_t stream, const float* A, long long lda, int rows, int cols, const unsigned* absmax, int sqrt_mode,
              float* scale_out, __half* Hi, __half* Lo, long long ldo) {
   if (!A || !absmax || !scale_out || !Hi || !Lo || rows <= 0 || cols <= 0) return GSMVI_EINVAL;
-  h3_split_kernel<<<rowwise_grid(rows, cols), 256, 0, stream>>>(A, lda, rows, cols, absmax, sqrt_mode, scale_out, Hi, Lo, ldo);
+  dim3 g = rowwise_grid(rows, cols);
+  g.y = (rows + 3) / 4 > 65535 ? 65535 : (rows + 3) / 4;
+  h3_split_kernel<<<g, 256, 0, stream>>>(A, lda, rows, cols, absmax, sqrt_mode, scale_out, Hi, Lo, ldo);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
 }

@@ -107,6 +107,14 @@ __global__ void bam_v_kernel(const double* __restrict__ C, long long ldc, const 
 }
 
 // A = scale * A (+ diag_add on the diagonal)
+// B = scale * A + diag_add * I (out of place)
+__global__ void affine_diag64_kernel(const double* __restrict__ A, double* __restrict__ Bm, long long ld, int n, double scale,
+                                     double diag_add) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = blockIdx.y;
+  if (j < n) Bm[i * ld + j] = scale * A[i * ld + j] + ((i == j) ? diag_add : 0.0);
+}
+
 __global__ void scale_diag64_kernel(double* __restrict__ A, long long lda, int n, double scale, double diag_add) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const long long i = blockIdx.y;
@@ -374,15 +382,26 @@ static int ns_sqrt64(cudaStream_t st, double* Y, long long ld, int n, double* Z,
       b = -0.5 * al * al * al;
       lo = a * lo + b * lo * lo * lo;
     }
-    DgemmOpts p;  // P = a I + b Z Y   (B operand MN-major: the product is exactly Z Y)
-    p.alpha = b;
-    p.diag_add = a;
-    GSMVI_TRY(dgemm_big(st, n, n, n, Z, ld, false, Y, ld, true, P, ld, p, oz));
-    GSMVI_CUDA(cudaMemsetAsync(scal_dev, 0, 2 * sizeof(double), st));
-    frob_inf64_kernel<<<n, 256, 0, st>>>(P, ld, n, a + b, scal_dev);  // ||P - (a+b) I||_F = |b| ||I - Z Y||_F
     DgemmOpts o;
-    GSMVI_TRY(dgemm_big(st, n, n, n, Y, ld, false, P, ld, true, Y2, ld, o, oz));   // Y2 = Y P
-    GSMVI_TRY(dgemm_big(st, n, n, n, P, ld, false, Z, ld, true, Z2, ld, o, oz));   // Z2 = P Z
+    if (it == 0) {
+      // Z0 = I: the products Z Y and P Z are Y and P themselves - one GEMM instead of three
+      affine_diag64_kernel<<<grid2(n, n), 256, 0, st>>>(Y, P, ld, n, b, a);                      // P = a I + b Y
+      GSMVI_CUDA(cudaMemsetAsync(scal_dev, 0, 2 * sizeof(double), st));
+      frob_inf64_kernel<<<n, 256, 0, st>>>(P, ld, n, a + b, scal_dev);
+      GSMVI_TRY(dgemm_big(st, n, n, n, Y, ld, false, P, ld, true, Y2, ld, o, oz));               // Y2 = Y P
+      GSMVI_CUDA(cudaMemcpy2DAsync(Z2, ld * sizeof(double), P, ld * sizeof(double), n * sizeof(double), n,
+                                   cudaMemcpyDeviceToDevice, st));                               // Z2 = P
+    } else {
+      DgemmOpts p;  // P = a I + b Z Y   (B operand MN-major: the product is exactly Z Y)
+      p.alpha = b;
+      p.diag_add = a;
+      GSMVI_TRY(dgemm_big(st, n, n, n, Z, ld, false, Y, ld, true, P, ld, p, oz));
+      GSMVI_CUDA(cudaMemsetAsync(scal_dev, 0, 2 * sizeof(double), st));
+      frob_inf64_kernel<<<n, 256, 0, st>>>(P, ld, n, a + b, scal_dev);  // ||P - (a+b) I||_F = |b| ||I - Z Y||_F
+      GSMVI_TRY(dgemm_big(st, n, n, n, Y, ld, false, P, ld, true, Y2, ld, o, oz));   // Y2 = Y P
+      // the last round only needs Y: its Z update is skipped
+      if (!last_round) GSMVI_TRY(dgemm_big(st, n, n, n, P, ld, false, Z, ld, true, Z2, ld, o, oz));   // Z2 = P Z
+    }
     double* t = Y; Y = Y2; Y2 = t;
     t = Z; Z = Z2; Z2 = t;
     if (last_round) { ++it; break; }

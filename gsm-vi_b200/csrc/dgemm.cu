@@ -12,6 +12,7 @@
 // Operand conventions match tc_gemm.cuh: K-major operand = [rows, K] row-major, MN-major = [K, rows] row-major.
 #include "dgemm.cuh"
 
+#include <stdint.h>
 #include <stdlib.h>
 
 namespace gsmvi {
@@ -362,11 +363,146 @@ __global__ void __launch_bounds__(DTHREADS, (DBM == 128) ? 1 : 2) dgemm_mma16_ke
     }
 }
 
+// ------------------------------------------------------------------------------------------------ pipelined DMMA variant
+// Same m16n8k16 inner product, but the operand tiles travel global -> shared memory with cp.async (16-byte chunks, no
+// register staging) through a three-stage ring, so two k-blocks of loads are always in flight behind the MMAs and the
+// only barrier per k-block is the one that hands a filled stage over.  Needs 16-byte aligned operands with an even
+// leading dimension (every call of the BaM solve; anything else takes dgemm_mma16_kernel).
+constexpr int PSTAGES = 3;
+constexpr int PSTAGE_DOUBLES = 2 * 128 * (DBK + 4);  // A and B tiles, the larger ([row][k+4]) of the two layouts each
+constexpr int PIPE_SMEM_BYTES = PSTAGES * PSTAGE_DOUBLES * static_cast<int>(sizeof(double));
+
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int src_bytes) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+// one 128 x DBK operand tile (rows r0.., k from k0) into its stage buffer; out-of-range elements are zero-filled
+template <bool MN>
+__device__ __forceinline__ void pipe_load(double* __restrict__ S, const double* __restrict__ P, long long ld, int nrows, int K,
+                                          int r0, int k0) {
+#pragma unroll
+  for (int e = 0; e < 128 * DBK / 2 / DTHREADS; ++e) {  // 16-byte chunks: 4 per thread
+    const int c = threadIdx.x + e * DTHREADS;
+    int r, k, nr, nk;
+    if (MN) {  // chunk = two consecutive rows at one k
+      k = c / 64;
+      r = 2 * (c % 64);
+      nr = nrows - (r0 + r);
+      nk = K - (k0 + k);
+      const int bytes = (nk > 0 && nr > 0) ? (nr >= 2 ? 16 : 8) : 0;
+      const double* src = bytes ? P + static_cast<long long>(k0 + k) * ld + r0 + r : P;
+      cp_async16(S + k * (128 + 4) + r, src, bytes);
+    } else {   // chunk = two consecutive k of one row
+      r = c / 8;
+      k = 2 * (c % 8);
+      nr = nrows - (r0 + r);
+      nk = K - (k0 + k);
+      const int bytes = (nk > 0 && nr > 0) ? (nk >= 2 ? 16 : 8) : 0;
+      const double* src = bytes ? P + static_cast<long long>(r0 + r) * ld + k0 + k : P;
+      cp_async16(S + r * (DBK + 4) + k, src, bytes);
+    }
+  }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(DTHREADS, 1) dgemm_pipe_kernel(const DgemmArgs a) {
+  constexpr int DBM = 128, DBN = 128;
+  constexpr int WM = DBM / 2, WN = DBN / 4;
+  constexpr int BI = WM / 16, BJ = WN / 8;
+  extern __shared__ __align__(16) double psm[];
+  int tm, tn;
+  {
+    const int tiles_n = (a.N + DBN - 1) / DBN;
+    tm = blockIdx.x / tiles_n;
+    tn = blockIdx.x % tiles_n;
+    if (a.tri && tn > tm) return;
+  }
+  const int m0 = tm * DBM, n0 = tn * DBN;
+  int k_begin = 0, k_end = a.K;
+  if (a.krange & KR_A_LOWER) k_end = min(k_end, m0 + DBM);
+  if (a.krange & KR_B_LOWER) k_end = min(k_end, n0 + DBN);
+  if (a.krange & KR_A_UPPER) k_begin = max(k_begin, m0);
+  if (a.krange & KR_B_UPPER) k_begin = max(k_begin, n0);
+  k_begin = (k_begin / DBK) * DBK;
+  const int nkb = (k_end > k_begin) ? (k_end - k_begin + DBK - 1) / DBK : 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wr = (warp >> 2) * WM, wc = (warp & 3) * WN;
+  const int fg = lane >> 2, ft = lane & 3;
+  double acc[BI][BJ][4];
+#pragma unroll
+  for (int i = 0; i < BI; ++i)
+#pragma unroll
+    for (int j = 0; j < BJ; ++j)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[i][j][u] = 0.0;
+
+  auto stage_a = [&](int s) { return psm + s * PSTAGE_DOUBLES; };
+  auto stage_b = [&](int s) { return psm + s * PSTAGE_DOUBLES + 128 * (DBK + 4); };
+  // prologue: stages 0 .. PSTAGES-2 (one commit group per k-block, empty groups keep the count uniform)
+#pragma unroll
+  for (int s = 0; s < PSTAGES - 1; ++s) {
+    if (s < nkb) {
+      pipe_load<A_MN>(stage_a(s), a.A, a.lda, a.M, a.K, m0, k_begin + s * DBK);
+      pipe_load<B_MN>(stage_b(s), a.B, a.ldb, a.N, a.K, n0, k_begin + s * DBK);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kb = 0; kb < nkb; ++kb) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(PSTAGES - 2) : "memory");  // k-block kb has landed
+    __syncthreads();  // ... for every thread, and everyone is done with the stage that is refilled next
+    {
+      const int nx = kb + PSTAGES - 1;
+      if (nx < nkb) {
+        pipe_load<A_MN>(stage_a(nx % PSTAGES), a.A, a.lda, a.M, a.K, m0, k_begin + nx * DBK);
+        pipe_load<B_MN>(stage_b(nx % PSTAGES), a.B, a.ldb, a.N, a.K, n0, k_begin + nx * DBK);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const double* As = stage_a(kb % PSTAGES);
+    const double* Bs = stage_b(kb % PSTAGES);
+    double af[BI][8], bf[BJ][4];
+#pragma unroll
+    for (int i = 0; i < BI; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) af[i][e] = As[sidx<DBM, A_MN>(wr + 16 * i + fg + 8 * (e & 1), ft + 4 * (e >> 1))];
+#pragma unroll
+    for (int j = 0; j < BJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) bf[j][e] = Bs[sidx<DBN, B_MN>(wc + 8 * j + fg, ft + 4 * e)];
+#pragma unroll
+    for (int i = 0; i < BI; ++i)
+#pragma unroll
+      for (int j = 0; j < BJ; ++j) dmma16816(acc[i][j], af[i], bf[j]);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < BI; ++i)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = m0 + wr + 16 * i + fg + 8 * h;
+      if (m >= a.M) continue;
+#pragma unroll
+      for (int j = 0; j < BJ; ++j)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int n = n0 + wc + 8 * j + 2 * ft + u;
+          if (n >= a.N) continue;
+          if (a.tri && n > m) continue;
+          double v = a.alpha * acc[i][j][2 * h + u];
+          if (a.beta != 0.0) v += a.beta * a.Cin[static_cast<long long>(m) * a.ldcin + n];
+          if (m == n) v += a.diag_add;
+          a.C[static_cast<long long>(m) * a.ldc + n] = v;
+          if (a.mirror && n != m) a.C[static_cast<long long>(n) * a.ldc + m] = v;
+        }
+    }
+}
+
 static int dgemm_variant() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("GSMVI_DGEMM");  // fma: DFMA kernel; mma8: m8n8k4; default: m16n8k16
-    v = (e && e[0] == 'f') ? 0 : ((e && e[0] == 'm' && e[3] == '8') ? 1 : 2);
+    const char* e = getenv("GSMVI_DGEMM");  // fma: DFMA kernel; mma8: m8n8k4; mma16: m16n8k16; default: pipelined m16n8k16
+    v = !e ? 3 : (e[0] == 'f' ? 0 : ((e[0] == 'm' && e[3] == '8') ? 1 : ((e[0] == 'm') ? 2 : 3)));
   }
   return v;
 }
@@ -391,7 +527,23 @@ int launch_dgemm(cudaStream_t stream, int M, int N, int K, const double* A, long
     else if (!a_mn && b_mn) KERN<BMV, false, true><<<grid, DTHREADS, 0, stream>>>(a);     \
     else KERN<BMV, true, true><<<grid, DTHREADS, 0, stream>>>(a);                         \
   }
-  if (dgemm_variant() == 2) {
+  const bool aligned = ((lda | ldb) & 1) == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
+  if (dgemm_variant() == 3 && big && aligned && K > 0) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t ae = cudaFuncSetAttribute(dgemm_pipe_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES);
+      if (ae == cudaSuccess) ae = cudaFuncSetAttribute(dgemm_pipe_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES);
+      if (ae == cudaSuccess) ae = cudaFuncSetAttribute(dgemm_pipe_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES);
+      if (ae == cudaSuccess) ae = cudaFuncSetAttribute(dgemm_pipe_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES);
+      if (ae != cudaSuccess) return static_cast<int>(ae);
+      attr_set = true;
+    }
+    const int grid = ((M + 127) / 128) * ((N + 127) / 128);
+    if (!a_mn && !b_mn) dgemm_pipe_kernel<false, false><<<grid, DTHREADS, PIPE_SMEM_BYTES, stream>>>(a);
+    else if (a_mn && !b_mn) dgemm_pipe_kernel<true, false><<<grid, DTHREADS, PIPE_SMEM_BYTES, stream>>>(a);
+    else if (!a_mn && b_mn) dgemm_pipe_kernel<false, true><<<grid, DTHREADS, PIPE_SMEM_BYTES, stream>>>(a);
+    else dgemm_pipe_kernel<true, true><<<grid, DTHREADS, PIPE_SMEM_BYTES, stream>>>(a);
+  } else if (dgemm_variant() >= 2) {
     if (big) GSMVI_DG(dgemm_mma16_kernel, 128) else GSMVI_DG(dgemm_mma16_kernel, 64)
   } else if (dgemm_variant() == 1) {
     if (big) GSMVI_DG(dgemm_mma_kernel, 128) else GSMVI_DG(dgemm_mma_kernel, 64)

@@ -189,6 +189,140 @@ __global__ void __launch_bounds__(RP_THREADS) gsm_rowpass_kernel(const float* __
   }
 }
 
+// ---- the same row pass for the h3 engine, split in two so that T = [E; U; D] is written ONCE, directly as the fp16 pair:
+// (1) per-sample scalars alpha_b, beta_b and a bound on |e|, |u|, |d| over the whole batch (|u_b| <= alpha |w|max +
+//     |beta| |d|max per row, |e_b| <= |d|max + that; loose by at most 2x, i.e. one bit of fp16 range) - a warp per row;
+// (2) e, u, d from X, W and the scalars, split with the scale of that bound, plus the column sums of u.
+// 22 B D bytes of traffic instead of 24 B D (pass) + 24 B D (separate split of an fp32 T).
+__global__ void __launch_bounds__(256) gsm_rowscal_kernel(const float* __restrict__ X, long long ldx,
+                                                          const float* __restrict__ G, long long ldg,
+                                                          const float* __restrict__ W, long long ldw,
+                                                          const float* __restrict__ mu, float* __restrict__ ab, int B, int D,
+                                                          unsigned* __restrict__ tbound) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + warp;
+  if (b >= B) return;
+  const float* x = X + static_cast<long long>(b) * ldx;
+  const float* g = G + static_cast<long long>(b) * ldg;
+  const float* w = W + static_cast<long long>(b) * ldw;
+  const bool vec = ((D & 3) == 0) && ((ldx & 3) == 0) && ((ldg & 3) == 0) && ((ldw & 3) == 0) &&
+                   (((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(W) |
+                      reinterpret_cast<uintptr_t>(mu)) & 15) == 0);
+  float vSv = 0.0f, mu_v = 0.0f, wmax = 0.0f, dmax = 0.0f;
+  if (vec) {
+    for (int j = lane * 4; j < D; j += 128) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + j);
+      const float4 gv = *reinterpret_cast<const float4*>(g + j);
+      const float4 wv = *reinterpret_cast<const float4*>(w + j);
+      const float4 mv = *reinterpret_cast<const float4*>(mu + j);
+      const float d0 = mv.x - xv.x, d1 = mv.y - xv.y, d2 = mv.z - xv.z, d3 = mv.w - xv.w;
+      vSv += wv.x * gv.x + wv.y * gv.y + wv.z * gv.z + wv.w * gv.w;
+      mu_v += d0 * gv.x + d1 * gv.y + d2 * gv.z + d3 * gv.w;
+      wmax = fmaxf(wmax, fmaxf(fmaxf(fabsf(wv.x), fabsf(wv.y)), fmaxf(fabsf(wv.z), fabsf(wv.w))));
+      dmax = fmaxf(dmax, fmaxf(fmaxf(fabsf(d0), fabsf(d1)), fmaxf(fabsf(d2), fabsf(d3))));
+    }
+  } else {
+    for (int j = lane; j < D; j += 32) {
+      const float d = mu[j] - x[j];
+      vSv += w[j] * g[j];
+      mu_v += d * g[j];
+      wmax = fmaxf(wmax, fabsf(w[j]));
+      dmax = fmaxf(dmax, fabsf(d));
+    }
+  }
+  vSv = warp_sum(vSv);
+  mu_v = warp_sum(mu_v);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  }
+  if (lane == 0) {
+    const float rho = 0.5f * sqrtf(1.0f + 4.0f * (vSv + mu_v * mu_v)) - 0.5f;
+    const float alpha = 1.0f / (1.0f + rho);
+    const float beta = -alpha * (1.0f + (vSv - mu_v) / (1.0f + rho + mu_v));
+    ab[b] = alpha;
+    ab[B + b] = beta;
+    // NaN / Inf anywhere in the row makes the bound NaN / Inf, which (as a bit pattern) outranks every finite value
+    const float bound = dmax + fabsf(alpha) * wmax + fabsf(beta) * dmax;
+    atomicMax(tbound, __float_as_uint(fabsf(bound)));
+  }
+}
+
+__global__ void __launch_bounds__(RP_THREADS) gsm_rowwrite_h3_kernel(const float* __restrict__ X, long long ldx,
+                                                                     const float* __restrict__ W, long long ldw,
+                                                                     const float* __restrict__ mu, const float* __restrict__ ab,
+                                                                     const unsigned* __restrict__ tbound,
+                                                                     float* __restrict__ scale_out, __half* __restrict__ Thi,
+                                                                     __half* __restrict__ Tlo, long long ldt,
+                                                                     float* __restrict__ usum, int B, int D, int rows_per_cta) {
+  const float sc = h3_scale_from_absmax(*tbound, 0);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *scale_out = sc;
+  const int row0 = blockIdx.x * rows_per_cta;
+  const int nrows = min(rows_per_cta, B - row0);
+  const bool vec = ((D & 3) == 0) && ((ldx & 3) == 0) && ((ldw & 3) == 0) && ((ldt & 3) == 0) &&
+                   (((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(mu)) & 15) == 0) &&
+                   (((reinterpret_cast<uintptr_t>(Thi) | reinterpret_cast<uintptr_t>(Tlo)) & 7) == 0);
+  auto put4 = [&](long long row, int j, const float4 v) {
+    __half h[4], l[4];
+    h3_split1(v.x, sc, h[0], l[0]);
+    h3_split1(v.y, sc, h[1], l[1]);
+    h3_split1(v.z, sc, h[2], l[2]);
+    h3_split1(v.w, sc, h[3], l[3]);
+    *reinterpret_cast<uint2*>(Thi + row * ldt + j) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(Tlo + row * ldt + j) = *reinterpret_cast<const uint2*>(l);
+  };
+  if (vec) {
+    for (int j = threadIdx.x * 4; j < D; j += RP_THREADS * 4) {
+      const float4 mv = *reinterpret_cast<const float4*>(mu + j);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r0 = 0; r0 < nrows; r0 += 4) {
+        float4 xv[4], wv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const long long b = row0 + min(r0 + q, nrows - 1);
+          xv[q] = *reinterpret_cast<const float4*>(X + b * ldx + j);
+          wv[q] = *reinterpret_cast<const float4*>(W + b * ldw + j);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = r0 + q;
+          if (r >= nrows) break;
+          const long long b = row0 + r;
+          const float al = ab[b], be = ab[B + b];
+          float4 d, u, e;
+          d.x = mv.x - xv[q].x; d.y = mv.y - xv[q].y; d.z = mv.z - xv[q].z; d.w = mv.w - xv[q].w;
+          u.x = al * wv[q].x + be * d.x; u.y = al * wv[q].y + be * d.y; u.z = al * wv[q].z + be * d.z; u.w = al * wv[q].w + be * d.w;
+          e.x = d.x + u.x; e.y = d.y + u.y; e.z = d.z + u.z; e.w = d.w + u.w;
+          acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
+          put4(b, j, e);
+          put4(b + B, j, u);
+          put4(b + 2LL * B, j, d);
+        }
+      }
+      atomicAdd(usum + j + 0, acc.x);
+      atomicAdd(usum + j + 1, acc.y);
+      atomicAdd(usum + j + 2, acc.z);
+      atomicAdd(usum + j + 3, acc.w);
+    }
+  } else {
+    for (int j = threadIdx.x; j < D; j += RP_THREADS) {
+      const float m = mu[j];
+      float acc = 0.0f;
+      for (int r = 0; r < nrows; ++r) {
+        const long long b = row0 + r;
+        const float d = m - X[b * ldx + j];
+        const float u = ab[b] * W[b * ldw + j] + ab[B + b] * d;
+        acc += u;
+        h3_split1(d + u, sc, Thi[b * ldt + j], Tlo[b * ldt + j]);
+        h3_split1(u, sc, Thi[(b + B) * ldt + j], Tlo[(b + B) * ldt + j]);
+        h3_split1(d, sc, Thi[(b + 2LL * B) * ldt + j], Tlo[(b + 2LL * B) * ldt + j]);
+      }
+      atomicAdd(usum + j, acc);
+    }
+  }
+}
+
 // 16 rows per CTA amortise the column-sum atomics; batch shards too small to give every SM a few CTAs that way use fewer
 static inline int rowpass_rows_per_cta(int B) {
   int r = RP_ROWS;
@@ -529,15 +663,18 @@ static int gsm_update_h3_impl(cudaStream_t stream, const float* X, long long ldx
     if ((rc = launch_gemm_h3(stream, B, D, D, hview(Gh, B, D), hview(Sh, D, D), W, ldw, o)) != GSMVI_OK) return rc;
   }
   tmr.mark("W");
-  // (ii) row pass -> T = [E; U; D] (fp32), |T| max, column sums of U; then the fp16 split of T
-  const int rpc = rowpass_rows_per_cta(B);
-  gsm_rowpass_kernel<1><<<(B + rpc - 1) / rpc, RP_THREADS, 0, stream>>>(X, ldx, G, ldg, W, ldw, mu, T, nullptr, ldw, usum, B, D,
-                                                                        reinterpret_cast<unsigned*>(scal), rpc);
-  if ((e = cudaGetLastError()) != cudaSuccess) return static_cast<int>(e);
-  tmr.mark("rowpass");
-  if ((rc = h3_split(stream, T, ldw, 3 * B, D, reinterpret_cast<const unsigned*>(scal), 0, scal + 1, Thi, Tlo, ldw)) != GSMVI_OK)
-    return rc;
-  tmr.mark("splitT");
+  // (ii) row pass in two launches: per-sample scalars + a bound on |T|, then T = [E; U; D] written once as the fp16 pair
+  //      (the fp32 T area only holds the 2B scalars), with the column sums of U
+  {
+    float* ab = T;
+    gsm_rowscal_kernel<<<(B + 7) / 8, 256, 0, stream>>>(X, ldx, G, ldg, W, ldw, mu, ab, B, D, reinterpret_cast<unsigned*>(scal));
+    tmr.mark("rowscal");
+    const int rpc = rowpass_rows_per_cta(B);
+    gsm_rowwrite_h3_kernel<<<(B + rpc - 1) / rpc, RP_THREADS, 0, stream>>>(X, ldx, W, ldw, mu, ab, reinterpret_cast<const unsigned*>(scal),
+                                                                         scal + 1, Thi, Tlo, ldw, usum, B, D, rpc);
+    if ((e = cudaGetLastError()) != cudaSuccess) return static_cast<int>(e);
+    tmr.mark("rowwrite");
+  }
   // (iii) Sigma_out = [Sigma0] - (E^T U + U^T D) / B_total : rows of T are K, so both operands are MN-major views
   {
     H3Opts o;

@@ -62,18 +62,103 @@ __device__ __forceinline__ void tile4x4_mac(const float* __restrict__ Arows, int
 // per column is one multiply and one FMA:  x_j = v_j / l_jj;  v_k -= x_j l_kj (k > j).  dT holds the block TRANSPOSED
 // (dT[j * DT + k] = l_kj) so the column below the pivot is read as broadcast float4s.  Fully unrolled (a rolled variant
 // with rotated registers measured 40% slower); the solved row is written to out_row[0..31].
-// Warp Cholesky of the 32 x 32 block whose row `lane` starts at myrow (shared memory).
-__device__ __forceinline__ void chol32_smem(float* __restrict__ myrow, int lane, float* __restrict__ dT,
-                                         float* __restrict__ dinv_out, int* __restrict__ bad) {
-  float row[32];
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Cholesky of the 32 x 32 block at `blk` (shared memory, leading dimension DS, lower triangle valid, zeros above) by
+// warps 0..3 of the CTA (128 threads; call with warp < 4), eight columns at a time:
+//   warp 0: reads the 8 x 8 pivot block (broadcast loads), factors it in registers - software-pipelined so that the next
+//           pivot's rsqrt is issued as soon as its entry is final and the rest of the column update fills its latency -
+//           solves every row's eight entries against it and writes them back (also transposed into dT, 1/l_jj into dinv);
+//   all four warps: rank-8 update of the remaining columns, a quarter of the columns each, rows below the diagonal only.
+// A single warp retires ~1 instruction per 2.5 cycles (nothing hides its latencies), so the 24-column rank-8 update done
+// by one warp with shuffles cost more than the eight dependent pivots; split over four warps through shared memory it
+// is ~4x shorter.  A non-positive / non-finite pivot poisons its column; *bad is set if any diagonal entry is not finite > 0.
+__device__ __forceinline__ void chol32_coop(float* __restrict__ blk, float* __restrict__ dT, float* __restrict__ dinv,
+                                            int* __restrict__ bad) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float mydiag = 1.0f;
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    const int cq = 8 * q;
+    if (warp == 0) {
+      float a[8], d[8][8];
+      {
+        const float4 t0 = *reinterpret_cast<const float4*>(blk + lane * DS + cq);
+        const float4 t1 = *reinterpret_cast<const float4*>(blk + lane * DS + cq + 4);
+        a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
+      }
 #pragma unroll
-  for (int k = 0; k < 32; k += 4) {
-    const float4 t = *reinterpret_cast<const float4*>(myrow + k);
-    row[k] = t.x; row[k + 1] = t.y; row[k + 2] = t.z; row[k + 3] = t.w;
+      for (int r = 0; r < 8; ++r) {
+        const float4 t0 = *reinterpret_cast<const float4*>(blk + (cq + r) * DS + cq);
+        const float4 t1 = *reinterpret_cast<const float4*>(blk + (cq + r) * DS + cq + 4);
+        d[r][0] = t0.x; d[r][1] = t0.y; d[r][2] = t0.z; d[r][3] = t0.w; d[r][4] = t1.x; d[r][5] = t1.y; d[r][6] = t1.z; d[r][7] = t1.w;
+      }
+      float rinv[8];
+      float r;
+      asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d[0][0]));
+      r = r * fmaf(-0.5f * d[0][0], r * r, 1.5f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        rinv[j] = r;
+        float rn = 0.0f;
+        if (j < 7) {  // the entries the next pivot depends on first, and its rsqrt right behind them
+          d[j + 1][j] *= r;
+          d[j + 1][j + 1] -= d[j + 1][j] * d[j + 1][j];
+          const float dn = d[j + 1][j + 1];
+          asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(dn));
+          rn = rn * fmaf(-0.5f * dn, rn * rn, 1.5f);
+        }
+#pragma unroll
+        for (int i = j + 2; i < 8; ++i) d[i][j] *= r;
+#pragma unroll
+        for (int i = j + 2; i < 8; ++i)
+#pragma unroll
+          for (int k = j + 1; k <= i; ++k) d[i][k] -= d[i][j] * d[k][j];
+        r = rn;
+      }
+      // this row against the pivot block, right-looking: x_j = a_j / l_jj, a_k -= x_j l_kj
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x = a[j] * rinv[j];
+        a[j] = x;
+#pragma unroll
+        for (int k = j + 1; k < 8; ++k) a[k] -= x * d[k][j];
+      }
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = (cq + j <= lane) ? a[j] : 0.0f;
+        dT[(cq + j) * DT + lane] = o[j];
+        if (lane == cq + j) {
+          dinv[cq + j] = rinv[j];
+          mydiag = a[j];
+        }
+      }
+      *reinterpret_cast<float4*>(blk + lane * DS + cq) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(blk + lane * DS + cq + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    if (q == 3) break;
+    named_bar_sync(10, 128);
+    {
+      // rank-8 update of columns cq+8 .. 31: thread (row i = lane, column group = warp) takes columns cq+8+warp, +4, ...
+      const float4 x0 = *reinterpret_cast<const float4*>(blk + lane * DS + cq);
+      const float4 x1 = *reinterpret_cast<const float4*>(blk + lane * DS + cq + 4);
+#pragma unroll 2
+      for (int k = cq + 8 + warp; k < 32; k += 4) {
+        if (k > lane) continue;  // above the diagonal
+        const float4 l0 = *reinterpret_cast<const float4*>(blk + k * DS + cq);
+        const float4 l1 = *reinterpret_cast<const float4*>(blk + k * DS + cq + 4);
+        float acc0 = blk[lane * DS + k], acc1 = 0.0f;
+        acc0 -= x0.x * l0.x; acc1 -= x0.y * l0.y; acc0 -= x0.z * l0.z; acc1 -= x0.w * l0.w;
+        acc0 -= x1.x * l1.x; acc1 -= x1.y * l1.y; acc0 -= x1.z * l1.z; acc1 -= x1.w * l1.w;
+        blk[lane * DS + k] = acc0 + acc1;
+      }
+    }
+    named_bar_sync(10, 128);
   }
-  int isbad = 0;
-  chol32_rolled(row, lane, myrow, dT, DT, dinv_out, isbad);
-  if (isbad && lane == 0) *bad = 1;
+  if (warp == 0 && __any_sync(0xffffffffu, !(mydiag > 0.0f) || !(mydiag < 3.0e38f)) && lane == 0) *bad = 1;
 }
 
 // Inlined on purpose: every CTA runs this code once per launch from a cold instruction cache, and fall-through code is
@@ -195,10 +280,6 @@ struct PanelArgs {
   unsigned helper_target;
   int helpers;
 };
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // spin (thread 0) until the panel's epoch word reaches `target`, then release the whole CTA
 __device__ __forceinline__ void wait_epoch(const unsigned* ready, unsigned target, int j0) {
@@ -391,7 +472,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_h3_kernel(const PanelArgs 
       for (int p = 0; p < NB / 32; ++p) {
         const int c0 = 32 * p;
         // ---- (1) 32 x 32 diagonal block: warp 0, row `lane` in registers; leaves it in s and, transposed, in dT
-        if (warp == 0) chol32_smem(s + (c0 + lane) * DS + c0, lane, dT, dinv, &bad);
+        if (warp < 4) chol32_coop(s + c0 * DS + c0, dT, dinv, &bad);
         named_bar_sync(2, NCOMP);
         asm volatile("bar.arrive %0, %1;" ::"r"(3 + 2 * p), "r"(256) : "memory");
         PT3(2 + 4 * p);

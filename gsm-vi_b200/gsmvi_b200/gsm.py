@@ -97,6 +97,15 @@ class GSMEngine:
         if z_tape is not None:
             assert z_tape.shape[1] == batch_size and z_tape.shape[2] == D
         self.z_tape = z_tape
+        self._tape_async = bool(z_tape is not None and npass == 4 and not z_tape.is_cuda and z_tape.is_pinned())
+        if self._tape_async:
+            self.copy_stream = torch.cuda.Stream()
+            self.Zbufs = [self.Z, new_mat(B, D, dev)[1]]
+            self.z_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self.z_free = [torch.cuda.Event(), torch.cuda.Event()]
+            for e in self.z_free:
+                e.record()
+            self._tape_copied, self._z_buf_in_use = -1, 0
         self.target = getattr(getattr(lp_g, "__self__", None), "_gsmvi_builtin_target", None)
         self.n_reverts = 0
         if self.h3:
@@ -175,6 +184,33 @@ class GSMEngine:
                                 npass=npass, A_lo=Tlo[: 2 * B, :D], B_lo=Tlo[B:, :D]),
         ]
 
+    def _tape_copy(self, j):
+        """Queue the host -> device copy of this rank's draws of iteration j on the copy stream (pinned tape only)."""
+        B, buf = self.B, j & 1
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.z_free[buf])  # the split that last read this buffer has run
+            self.Zbufs[buf].copy_(self.z_tape[j, self.rank * B:(self.rank + 1) * B], non_blocking=True)
+            self.z_ready[buf].record()
+        self._tape_copied = j
+
+    def _tape_slice(self, i):
+        """This rank's [B, D] draws of iteration i as a device matrix.  A pinned host tape is streamed: the slice of
+        iteration i + 1 is copied on a second stream while iteration i computes (the reference draws its samples on the
+        host every iteration, gsmvi/gsm.py:117-119; this is that hand-over without the stall)."""
+        B = self.B
+        if not self._tape_async:
+            self.Z.copy_(self.z_tape[i, self.rank * B:(self.rank + 1) * B], non_blocking=True)
+            return self.Z
+        if self._tape_copied < i:
+            self._tape_copy(i)
+        buf = i & 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.z_ready[buf])
+        if i + 1 < self.z_tape.shape[0]:
+            self._tape_copy(i + 1)
+        self._z_buf_in_use = buf
+        return self.Zbufs[buf]
+
     def _launch_body_h3(self, i, graph):
         """Every launch of one h3 iteration up to (and including) the copy of the accept flag to pinned host memory and the
         NEXT iteration's Philox draws.  graph=True: the form that is captured into a CUDA graph (Philox counter read from
@@ -186,8 +222,9 @@ class GSMEngine:
         sl.zero_()
         # ---- sample (gsm.py:117-119)
         if self.z_tape is not None:
-            self.Z.copy_(self.z_tape[i, self.rank * B:(self.rank + 1) * B], non_blocking=True)
-            self.Zh.split_from(self.Z)
+            self.Zh.split_from(self._tape_slice(i))
+            if self._tape_async:
+                self.z_free[self._z_buf_in_use].record()
         elif not graph and self.z_drawn_for != i:
             L.philox_normal_h3(self.Zh, B, D, self.seed, i * self.world + self.rank)
         tgt = self.target

@@ -279,6 +279,20 @@ def test_gsm_graph_replay_matches_eager_launches(lib, monkeypatch, D, B):
     assert relF(c1, c0.cpu().double().numpy()) < 1e-5 and relF(m1, m0.cpu().double().numpy()) < 1e-5
 
 
+def test_gsm_pinned_tape_is_streamed_and_matches_pageable_tape(lib):
+    """A pinned host z-tape is copied one iteration ahead on a second stream; the fit must equal the one with the same
+    tape in pageable memory (synchronous copies) up to the summation order of the column-sum atomics."""
+    from gsmvi_b200.gsm import GSM
+    from gsmvi_b200.targets import DenseGaussianTarget
+    D, B, niter = 200, 48, 25
+    mean_t, cov_t = orc.dense_gaussian_target(D, 4)
+    tgt = DenseGaussianTarget(mean_t, cov_t)
+    Z = torch.randn(niter + 1, B, D, generator=torch.Generator().manual_seed(3))
+    m0, c0 = GSM(D, tgt.lp, tgt.lp_g).fit(0, niter=niter, batch_size=B, z_tape=Z, verbose=False)
+    m1, c1 = GSM(D, tgt.lp, tgt.lp_g).fit(0, niter=niter, batch_size=B, z_tape=Z.pin_memory(), verbose=False)
+    assert relF(c1, c0.cpu().double().numpy()) < 1e-5 and relF(m1, m0.cpu().double().numpy()) < 1e-5
+
+
 def test_gsm_large_trajectory_parity(lib):
     """D = B = 2048, 4 iterations, identical z-tape: device loop vs fp64 oracle loop."""
     from gsmvi_b200.gsm import GSM

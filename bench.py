@@ -312,33 +312,36 @@ def run_ours(args):
     # ---- BaM leg of the BASELINE metric (same shape, example_bam.py schedule reg_i = 100/(1+i)); reported beside GSM
     bam = None
     if not args.no_bam:
-        from gsmvi_b200.bam import BaMEngine
-        torch.cuda.empty_cache()
-        beng = BaMEngine(D, B, tgt.lp_g, key=99, npass=min(npass, 3), process_group=group)
-        nb = max(2, min(args.steps, 4))
-        beng.step(0, 100.0)
-        barrier()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        for i in range(1, nb + 1):
-            beng.step(i, 100.0 / (1 + i))
-        b1.record()
-        barrier()
-        bms = b0.elapsed_time(b1)
-        if world > 1:
-            t = torch.tensor([bms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            bms = float(t.item())
-        k = float(np.mean(beng.ns_iters[1:]))
-        K = Bl + 1
-        solve_flops = (6.0 * k + 7.0) * D**3  # (6k+7) D^3 with k Newton-Schulz iterations
-        bam = {"metric": "VI iterations/sec (BaM, dense-Gaussian target, D=%d, B=%d)" % (D, B), "value": nb / (bms * 1e-3),
-               "unit": UNIT, "steps": nb, "ms_per_step": bms / nb, "ns_iters_mean": k, "reverts": beng.n_reverts,
-               "solve_algorithmic_tflops_fp64": solve_flops * nb / (bms * 1e-3) / 1e12,
-               "note": "fp32 tensor-core sampling/score + fp64 statistics and QME solve (dgemm_kernel, FP64 pipe; cuBLAS "
-                       "DGEMM on this part measures ~36 TFLOP/s)"}
-        del beng
-        torch.cuda.empty_cache()
+        try:
+            from gsmvi_b200.bam import BaMEngine
+            torch.cuda.empty_cache()
+            beng = BaMEngine(D, B, tgt.lp_g, key=99, npass=min(npass, 3), process_group=group)
+            nb = max(2, min(args.steps, 4))
+            beng.step(0, 100.0)
+            barrier()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for i in range(1, nb + 1):
+                beng.step(i, 100.0 / (1 + i))
+            b1.record()
+            barrier()
+            bms = b0.elapsed_time(b1)
+            if world > 1:
+                t = torch.tensor([bms], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                bms = float(t.item())
+            k = float(np.mean(beng.ns_iters[1:]))
+            K = Bl + 1
+            solve_flops = (6.0 * k + 7.0) * D**3  # (6k+7) D^3 with k Newton-Schulz iterations
+            bam = {"metric": "VI iterations/sec (BaM, dense-Gaussian target, D=%d, B=%d)" % (D, B), "value": nb / (bms * 1e-3),
+                   "unit": UNIT, "steps": nb, "ms_per_step": bms / nb, "ns_iters_mean": k, "reverts": beng.n_reverts,
+                   "solve_algorithmic_tflops_fp64": solve_flops * nb / (bms * 1e-3) / 1e12,
+                   "note": "fp32 tensor-core sampling/score + fp64 statistics and QME solve (dgemm_pipe_kernel: FP64 tensor-core "
+                           "path, 30.8 TFLOP/s at 4096^3; cuBLAS DGEMM on this part measures 35.4)"}
+            del beng
+            torch.cuda.empty_cache()
+        except Exception as exc:  # the BaM leg must never take the GSM line down with it
+            bam = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

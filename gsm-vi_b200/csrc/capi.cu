@@ -253,8 +253,8 @@ int gsmvi_gauss_logq_reduce(const float* Z_or_X, long long ld, int N, int D, con
 }
 
 int gsmvi_gsm_ensemble_fit(const float* P, const float* c, float* mu, float* Sigma, int F, int D, int B, int niter,
-                           unsigned long long seed, const float* z_tape, int* reverts, void* stream) {
-  return gsm_ensemble_fit(S(stream), P, c, mu, Sigma, F, D, B, niter, seed, z_tape, reverts);
+                           unsigned long long seed, const float* z_tape, int* reverts, int first_fit, void* stream) {
+  return gsm_ensemble_fit(S(stream), P, c, mu, Sigma, F, D, B, niter, seed, z_tape, reverts, first_fit);
 }
 
 }  // extern "C"

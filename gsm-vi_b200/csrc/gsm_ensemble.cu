@@ -125,7 +125,7 @@ __device__ __forceinline__ bool chol64(float* s, float* dinv, int* bad_smem) {
 
 __global__ void __launch_bounds__(ETHREADS, 2)
 gsm_ensemble_kernel(const float* __restrict__ Pg, const float* __restrict__ cg, float* __restrict__ mug,
-                    float* __restrict__ Sg, int F, int D, int B, int niter, unsigned long long seed,
+                    float* __restrict__ Sg, int F, int D, int B, int niter, unsigned long long seed, int first_fit,
                     const float* __restrict__ ztape, long long z_fit_stride, int* __restrict__ reverts) {
   extern __shared__ __align__(16) float sm[];
   float* S = sm;                      // current Sigma
@@ -179,7 +179,7 @@ gsm_ensemble_kernel(const float* __restrict__ Pg, const float* __restrict__ cg, 
     } else {
       for (int g4 = tid; g4 < EB * ED / 4; g4 += ETHREADS) {
         const int b = g4 >> 4, j = (g4 & 15) * 4;
-        uint32_t c[4] = {static_cast<uint32_t>(g4), static_cast<uint32_t>(f), static_cast<uint32_t>(it), 0x454e53u};
+        uint32_t c[4] = {static_cast<uint32_t>(g4), static_cast<uint32_t>(first_fit + f), static_cast<uint32_t>(it), 0x454e53u};  // global fit index
         philox4(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
         const float u0 = (static_cast<float>(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
         const float u1 = (static_cast<float>(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
@@ -309,7 +309,7 @@ gsm_ensemble_kernel(const float* __restrict__ Pg, const float* __restrict__ cg, 
 }
 
 int gsm_ensemble_fit(cudaStream_t st, const float* P, const float* c, float* mu, float* Sigma, int F, int D, int B,
-                     int niter, unsigned long long seed, const float* ztape, int* reverts) {
+                     int niter, unsigned long long seed, const float* ztape, int* reverts, int first_fit) {
   if (!P || !c || !mu || !Sigma || !reverts || F <= 0 || D <= 0 || D > ED || B <= 0 || B > EB || niter < 0) return GSMVI_EINVAL;
   const int smem = (4 * ED * ELD + 3 * EB * ELD + 4 * ED + 2 * EB) * sizeof(float);
   static bool attr_set = false;
@@ -318,7 +318,7 @@ int gsm_ensemble_fit(cudaStream_t st, const float* P, const float* c, float* mu,
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  gsm_ensemble_kernel<<<F, ETHREADS, smem, st>>>(P, c, mu, Sigma, F, D, B, niter, seed, ztape,
+  gsm_ensemble_kernel<<<F, ETHREADS, smem, st>>>(P, c, mu, Sigma, F, D, B, niter, seed, first_fit, ztape,
                                                  static_cast<long long>(niter + 1) * B * D, reverts);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);

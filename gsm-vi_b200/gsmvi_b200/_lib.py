@@ -228,7 +228,7 @@ def gauss_logq_reduce(Z_or_X, N, D, mu, L_, out, from_z):
 # ------------------------------------------------------------------------------------------------ ensemble
 def _declare_ens(L):
     L.gsmvi_gsm_ensemble_fit.restype = c_i
-    L.gsmvi_gsm_ensemble_fit.argtypes = [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_ull, c_p, c_p, c_p]
+    L.gsmvi_gsm_ensemble_fit.argtypes = [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_ull, c_p, c_p, c_i, c_p]
 
 
 _declare_mon_level = _declare
@@ -239,9 +239,9 @@ def _declare(L):  # noqa: F811
     _declare_ens(L)
 
 
-def gsm_ensemble_fit_raw(P, c, mu, Sigma, F, D, B, niter, seed, z_tape, reverts):
+def gsm_ensemble_fit_raw(P, c, mu, Sigma, F, D, B, niter, seed, z_tape, reverts, first_fit=0):
     check(lib().gsmvi_gsm_ensemble_fit(ptr(P), ptr(c), ptr(mu), ptr(Sigma), F, D, B, niter, seed & (2**64 - 1), ptr(z_tape),
-                                       ptr(reverts), stream_ptr()), "gsmvi_gsm_ensemble_fit")
+                                       ptr(reverts), first_fit, stream_ptr()), "gsmvi_gsm_ensemble_fit")
 
 
 # ------------------------------------------------------------------------------------------------ scaled 3xFP16 engine

@@ -240,9 +240,11 @@ int gsmvi_gauss_logq_reduce(const float* Z_or_X, long long ld, int N, int D, con
  * (gsmvi/gsm.py:107-129: sample, score -(x - m) P, gsm_update gsmvi/gsm.py:31-58, Cholesky check gsmvi/gsm.py:136-150,
  * accept/revert) for niter + 1 iterations inside one kernel, one CTA per fit, state in shared memory.
  * P [F,D,D], c [F,D] (c_f = P_f m_f), mu [F,D] and Sigma [F,D,D] in/out, dense row-major.  z_tape: optional
- * [F, niter+1, B, D] draws (else Philox(seed)).  reverts [F] <- rejected updates (-1: initial Sigma not PD). */
+ * [F, niter+1, B, D] draws (else Philox(seed)).  reverts [F] <- rejected updates (-1: initial Sigma not PD).
+ * first_fit: global index of fit 0 (ensembles split across GPUs - replicas only, no communication - keep the Philox
+ * streams of the unsharded run). */
 int gsmvi_gsm_ensemble_fit(const float* P, const float* c, float* mu, float* Sigma, int F, int D, int B, int niter,
-                           unsigned long long seed, const float* z_tape, int* reverts, void* stream);
+                           unsigned long long seed, const float* z_tape, int* reverts, int first_fit, void* stream);
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,17 @@ def test_h3_and_comm_host_queries_match_the_header_structs():
     assert lib.gsmvi_dgemm_oz_workspace_bytes(4096, 4096, 4096, 8) >= 2 * 8 * 4096 * 4096 + 8 * 4096 * 4096
 
 
+def test_ensemble_shard_ranges_partition_the_fits():
+    from gsmvi_b200.ensemble import shard_range
+    for F in (1, 7, 1024, 1025):
+        for world in (1, 2, 3, 8):
+            r = [shard_range(F, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == F
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            sizes = [hi - lo for lo, hi in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
 def test_header_cites_reference_for_each_hot_path_entry():
     with open(os.path.join(ROOT, "include", "gsmvi_b200.h")) as f:
         src = f.read()

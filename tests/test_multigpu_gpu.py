@@ -42,6 +42,15 @@ for (D, B, niter) in [(96, 32, 20), (512, 256, 6)]:
     assert e[0] < 2e-5 and e[1] < 2e-5, e
     # both ranks hold identical replicated state
     t = b2c.clone(); dist.broadcast(t, 0); assert torch.equal(t, b2c)
+# ensemble of independent fits: each rank fits its slice (no communication), the gathered result equals the unsharded run
+from gsmvi_b200.ensemble import gsm_ensemble_fit, shard_range
+F, D, B, niter = 10, 24, 8, 30
+rng = np.random.RandomState(0)
+means = rng.random_sample((F, D)); A = rng.normal(size=(F, D, D)); covs = A @ np.swapaxes(A, 1, 2) / D + 1e-2 * np.eye(D)
+mu_all, S_all, rev_all = gsm_ensemble_fit(means, covs, key=3, batch_size=B, niter=niter)
+mu_loc, S_loc, rev_loc = gsm_ensemble_fit(means, covs, key=3, batch_size=B, niter=niter, process_group=dist.group.WORLD)
+lo, hi = shard_range(F, rank, dist.get_world_size())
+assert torch.equal(S_loc, S_all[lo:hi]) and torch.equal(mu_loc, mu_all[lo:hi]) and torch.equal(rev_loc, rev_all[lo:hi])
 dist.destroy_process_group()
 print("rank", rank, "ok", flush=True)
 '''

@@ -55,13 +55,13 @@ static int launch_h3_one(cudaStream_t stream, const H3Args& args, const CUtensor
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
 }
 
-int launch_gemm_h3(cudaStream_t stream, int M, int N, int K, const HView& A, const HView& B, float* C, long long ldc,
-                   const H3Opts& o) {
+int h3_prepare(int M, int N, int K, const HView& A, const HView& B, float* C, long long ldc, const H3Opts& o, H3Args* out,
+               CUtensorMap* maps, dim3* grid_out) {
   if (M <= 0 || N <= 0 || K <= 0 || (!C && !o.push_base) || !A.hi || !A.lo || !B.hi || !B.lo || !A.scale || !B.scale) return GSMVI_EINVAL;
   if (o.tri && M != N) return GSMVI_EINVAL;
   if (o.beta != 0.0f && !o.Cin) return GSMVI_EINVAL;
   if (o.splits < 1 || (o.splits > 1 && (o.beta != 0.0f || o.bias_n || o.mirror))) return GSMVI_EINVAL;
-  H3Args a;
+  H3Args& a = *out;
   a.M = M; a.N = N; a.K = K;
   a.alpha = o.alpha; a.beta = o.beta;
   a.Cin = o.Cin; a.ldcin = o.ldcin;
@@ -89,21 +89,29 @@ int launch_gemm_h3(cudaStream_t stream, int M, int N, int K, const HView& A, con
   if (o.split_hi && (!o.split_lo || !o.split_scale || (o.split_ld & 3) != 0 || o.tri || o.splits != 1 || o.push_base)) return GSMVI_EINVAL;
   if (o.push_base && (!o.tri || o.splits != 1 || o.mirror || o.beta != 0.0f || o.bias_n)) return GSMVI_EINVAL;
   const int tiles = o.tri ? a.tiles_m * (a.tiles_m + 1) / 2 : a.tiles_m * a.tiles_n;
-  const dim3 grid(tiles, o.splits);
+  *grid_out = dim3(tiles, o.splits);
 
-  CUtensorMap tah, tbh, tal, tbl;
   int rc;
   // K-major: box = 64 K-elements (128 B) x 128 rows.  MN-major: box = 64 MN-elements (128 B) x 64 K-rows, two per tile.
   const int abc = 64, abr = o.a_mn ? H3_BK : H3_BM, bbr = o.b_mn ? H3_BK : H3_BN;
-  if ((rc = make_tmap_h(&tah, A.hi, A.rows, A.cols, A.ld, abc, abr)) != GSMVI_OK) return rc;
-  if ((rc = make_tmap_h(&tal, A.lo, A.rows, A.cols, A.ld, abc, abr)) != GSMVI_OK) return rc;
-  if ((rc = make_tmap_h(&tbh, B.hi, B.rows, B.cols, B.ld, abc, bbr)) != GSMVI_OK) return rc;
-  if ((rc = make_tmap_h(&tbl, B.lo, B.rows, B.cols, B.ld, abc, bbr)) != GSMVI_OK) return rc;
+  if ((rc = make_tmap_h(&maps[0], A.hi, A.rows, A.cols, A.ld, abc, abr)) != GSMVI_OK) return rc;
+  if ((rc = make_tmap_h(&maps[1], B.hi, B.rows, B.cols, B.ld, abc, bbr)) != GSMVI_OK) return rc;
+  if ((rc = make_tmap_h(&maps[2], A.lo, A.rows, A.cols, A.ld, abc, abr)) != GSMVI_OK) return rc;
+  if ((rc = make_tmap_h(&maps[3], B.lo, B.rows, B.cols, B.ld, abc, bbr)) != GSMVI_OK) return rc;
+  return GSMVI_OK;
+}
 
-  if (!o.a_mn && !o.b_mn) return launch_h3_one<false, false>(stream, a, tah, tbh, tal, tbl, grid, o.pdl);
-  if (o.a_mn && !o.b_mn) return launch_h3_one<true, false>(stream, a, tah, tbh, tal, tbl, grid, o.pdl);
-  if (!o.a_mn && o.b_mn) return launch_h3_one<false, true>(stream, a, tah, tbh, tal, tbl, grid, o.pdl);
-  return launch_h3_one<true, true>(stream, a, tah, tbh, tal, tbl, grid, o.pdl);
+int launch_gemm_h3(cudaStream_t stream, int M, int N, int K, const HView& A, const HView& B, float* C, long long ldc,
+                   const H3Opts& o) {
+  H3Args a;
+  CUtensorMap tm[4];  // A_hi, B_hi, A_lo, B_lo
+  dim3 grid;
+  const int rc = h3_prepare(M, N, K, A, B, C, ldc, o, &a, tm, &grid);
+  if (rc != GSMVI_OK) return rc;
+  if (!o.a_mn && !o.b_mn) return launch_h3_one<false, false>(stream, a, tm[0], tm[1], tm[2], tm[3], grid, o.pdl);
+  if (o.a_mn && !o.b_mn) return launch_h3_one<true, false>(stream, a, tm[0], tm[1], tm[2], tm[3], grid, o.pdl);
+  if (!o.a_mn && o.b_mn) return launch_h3_one<false, true>(stream, a, tm[0], tm[1], tm[2], tm[3], grid, o.pdl);
+  return launch_h3_one<true, true>(stream, a, tm[0], tm[1], tm[2], tm[3], grid, o.pdl);
 }
 
 // ------------------------------------------------------------------------------------------------ operand split

@@ -96,12 +96,15 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 
 __device__ __forceinline__ void h3_split1(float v, float s, __half& hi, __half& lo);
 
+// The whole CTA program of one (tile, split) work item: bx = tile index, by = split index (the x / y block indices of a
+// plain launch).  A device function so that the Cholesky's fused panel kernel (potrf_h3.cu) can run it in its otherwise
+// idle CTAs; every one of the CTA's H3_THREADS threads must call it.  The tensor maps must live in kernel parameter
+// space (__grid_constant__).
 template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(H3_THREADS, 1)
-gemm_h3_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmBhi,
-               const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo) {
+__device__ __forceinline__ void gemm_h3_body(const H3Args& args, const CUtensorMap& tmAhi, const CUtensorMap& tmBhi,
+                                             const CUtensorMap& tmAlo, const CUtensorMap& tmBlo, uint8_t* smem_raw,
+                                             const int bx, const int by) {
   constexpr int STAGES = H3_STAGES;
-  extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   const uint32_t bar_base = ptx::smem_u32(smem);
@@ -117,7 +120,7 @@ gemm_h3_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, con
   // ---- tile coordinates
   int tm, tn;
   if (args.tri) {
-    const int t = blockIdx.x;
+    const int t = bx;
     int i = static_cast<int>((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
     while ((i + 1) * (i + 2) / 2 <= t) ++i;
     while (i * (i + 1) / 2 > t) --i;
@@ -125,7 +128,7 @@ gemm_h3_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, con
     tn = t - i * (i + 1) / 2;
   } else {
     constexpr int GROUP = 8;  // tile-rows per group: concurrently resident CTAs share operand tiles in L2
-    const int t = blockIdx.x;
+    const int t = bx;
     const int per_group = GROUP * args.tiles_n;
     const int g = t / per_group;
     const int first_m = g * GROUP;
@@ -147,7 +150,7 @@ gemm_h3_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, con
   if (args.krange & KR_B_UPPER) k_begin = max(k_begin, n0);
   int kb_begin = k_begin / H3_BK;
   int kb_end = (k_end > k_begin) ? (k_end + H3_BK - 1) / H3_BK : kb_begin;
-  const int split = blockIdx.y;
+  const int split = by;
   if (args.splits > 1) {
     const int total = kb_end - kb_begin;
     const int per = (total + args.splits - 1) / args.splits;
@@ -367,7 +370,7 @@ gemm_h3_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, con
       // the tile is complete in shared memory: 128 threads send one row each (cp.async.bulk, shared -> peer global:
       // full-size NVLink packets instead of 16-byte scattered stores), wait for their copies, then one thread
       // publishes the tile to its owner
-      const int t = blockIdx.x, owner = t % args.push_world;
+      const int t = bx, owner = t % args.push_world;
       ptx::fence_proxy_async_smem();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int prow = threadIdx.x - 64;
@@ -395,6 +398,14 @@ gemm_h3_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, con
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, H3_TMEM_COLS);
   }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(H3_THREADS, 1)
+gemm_h3_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmBhi,
+               const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo) {
+  extern __shared__ uint8_t h3_smem_raw[];
+  gemm_h3_body<A_MN, B_MN>(args, tmAhi, tmBhi, tmAlo, tmBlo, h3_smem_raw, blockIdx.x, blockIdx.y);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -431,6 +442,10 @@ struct H3Opts {
 
 int launch_gemm_h3(cudaStream_t stream, int M, int N, int K, const HView& A, const HView& B, float* C, long long ldc,
                    const H3Opts& o);
+// The argument block, the four tensor maps (A_hi, B_hi, A_lo, B_lo) and the grid (tiles, splits) of that launch, for
+// callers that run gemm_h3_body inside a kernel of their own (potrf_h3.cu).
+int h3_prepare(int M, int N, int K, const HView& A, const HView& B, float* C, long long ldc, const H3Opts& o, H3Args* out,
+               CUtensorMap* maps, dim3* grid_out);
 
 // scale <- power of two with absmax * scale in [2^13, 2^14) (absmax given as the bit pattern of a non-negative float,
 // or of its square when sqrt_mode: |L_ij| <= sqrt(max Sigma_ii)); Hi = rn_f16(A scale), Lo = rn_f16((A scale - Hi) 2^11).

@@ -65,6 +65,9 @@ __device__ __forceinline__ void tile4x4_mac(const float* __restrict__ Arows, int
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// Barrier over the 256 threads that run the panel program.  Not __syncthreads(): in the fused kernel the CTA has 320
+// threads (the GEMM role's shape) and the last two warps of a panel-role CTA have exited.
+__device__ __forceinline__ void cta_sync() { named_bar_sync(0, 256); }
 
 // Cholesky of the 32 x 32 block at `blk` (shared memory, leading dimension DS, lower triangle valid, zeros above) by
 // warps 0..3 of the CTA (128 threads; call with warp < 4), eight columns at a time:
@@ -254,7 +257,7 @@ __global__ void potrf_zero_upper_kernel(float* __restrict__ L, long long ldl, __
 
 // optional phase timing of one panel (GSMVI_POTRF_TIMING=1): clock64 stamps of CTA 0 / CTA 1, read back by the host
 __device__ long long g_pt3[64];
-#define PT3(i) do { if (TIMING && threadIdx.x == 0) g_pt3[i] = clock64(); } while (0)
+#define PT3(i) do { if (TIMING && threadIdx.x == 0 && a.j0 == 8 * NB) g_pt3[i] = clock64(); } while (0)
 
 struct PanelArgs {
   const float* A;
@@ -279,6 +282,11 @@ struct PanelArgs {
   unsigned* helper_count;
   unsigned helper_target;
   int helpers;
+  int trsm_ctas;  // CTAs 1 .. trsm_ctas own the rows below the diagonal block (the fused kernel's grid is larger)
+  // look-ahead: `partials` holds the update with the panels before the previous one only (computed by GEMM-role CTAs of
+  // the previous launch, concurrently with that panel); the previous panel's K = 128 contribution
+  // L[rows, j0-128 : j0) L[j0 : j0+128, j0-128 : j0)^T is subtracted here, by the CTAs that own the rows
+  int late;
 };
 
 // spin (thread 0) until the panel's epoch word reaches `target`, then release the whole CTA
@@ -290,7 +298,7 @@ __device__ __forceinline__ void wait_epoch(const unsigned* ready, unsigned targe
       if (clock64() - t0 > 4000000000LL) { printf("gsmvi: potrf panel watchdog (j0=%d epoch %u)\n", j0, target); __trap(); }
     }
   }
-  __syncthreads();
+  cta_sync();
 }
 
 // Epochs of one panel (relative to epoch_base): 2p+1 = diagonal block p factored and stored, 2p+2 = the rows below it in
@@ -300,8 +308,7 @@ __device__ __forceinline__ void wait_epoch(const unsigned* ready, unsigned targe
 // The straight-line parts are kept small on purpose: each CTA runs this code once per launch with a cold instruction
 // cache, and an earlier fully unrolled version (10.8k SASS instructions) spent more time fetching than computing.
 template <bool FULL, bool TIMING>
-__global__ void __launch_bounds__(256, 1) potrf_panel_h3_kernel(const PanelArgs a) {
-  extern __shared__ __align__(16) uint8_t sm_raw[];
+__device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw) {
   // [1 KiB-aligned: tf32 hi | lo operand tiles of CTA 0's tensor-core update, 96 x 128 B each] then the fp32 arrays.  The
   // MMA (M = 128) reads 32 rows past each 96-row tile: those land in the lo tile / in s (ignored accumulator rows).
   const uint32_t pt_addr = (ptx::smem_u32(sm_raw) + 1023u) & ~1023u;
@@ -309,6 +316,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_h3_kernel(const PanelArgs 
   float* s = sm;                   // [NB][DS]   diagonal block (CTA 0) / published block-rows of L11 (TRSM CTAs)
   float* at = sm + NB * DS;        // [RPC][DS]  TRSM CTAs: their rows of the panel
   float* dT = at + RPC * DS;       // [32][DT]   current 32 x 32 diagonal block, transposed
+  float* la = dT + 32 * DT;        // [RPC][DS]  TRSM CTAs, look-ahead: their rows of the previous panel's block-column
   __shared__ float dinv[32];
   __shared__ int bad;
   __shared__ __align__(8) unsigned long long mma_bar;
@@ -359,7 +367,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_h3_kernel(const PanelArgs 
             if (clock64() - t0 > 4000000000LL) { printf("gsmvi: potrf helper watchdog (j0=%d)\n", j0); __trap(); }
           }
         }
-        __syncthreads();
+        cta_sync();
 #pragma unroll
         for (int e = 0; e < PER; ++e) {
           v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -414,7 +422,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_h3_kernel(const PanelArgs 
       }
     }
     ptx::tc_fence_before_sync();
-    __syncthreads();
+    cta_sync();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
     PT3(1);
@@ -546,7 +554,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_h3_kernel(const PanelArgs 
         PT3(5 + 4 * p);
       }
     }
-    __syncthreads();
+    cta_sync();
     if (warp == 0) {
       ptx::tc_fence_after_sync();
       ptx::tmem_dealloc(tmem_base, 128);
@@ -559,32 +567,78 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_h3_kernel(const PanelArgs 
   if (!FULL) return;
   // -------------------------------------------------------------------- TRSM rows (only full panels have rows below)
   if (blockIdx.x == 1) PT3(20);
-  if (static_cast<int>(blockIdx.x) <= a.helpers) {
-    // helper: rows 8 (blockIdx.x - 1) .. +7 of the diagonal block, A11 - sum P, one 16-byte group per thread, all loads in flight
-    const int i = 8 * (blockIdx.x - 1) + (tid >> 5), j4 = (tid & 31) * 4;
-    if (j4 <= i) {
-      float4 v = *reinterpret_cast<const float4*>(a.A + static_cast<long long>(j0 + i) * a.lda + j0 + j4);
-      float4 pv[MAX_SPLITS];
+  bool lp_staged = false;  // s holds the previous panel's rows L[j0 .. j0+127][j0-128 .. j0) (look-ahead operand)
+  // the previous panel's block-column of the 128 rows of this panel's diagonal block -> s (64 KiB, L2-resident)
+  auto stage_lp = [&]() {
+    const float* lp = a.L + static_cast<long long>(j0) * a.ldl + (j0 - NB);
+    float4 t[16];  // all sixteen loads of a thread in flight: one L2 round trip instead of four
 #pragma unroll
-      for (int sp = 0; sp < MAX_SPLITS; ++sp) {
-        pv[sp] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (sp < a.splits) pv[sp] = *reinterpret_cast<const float4*>(a.partials + sp * a.split_stride + static_cast<long long>(i) * NB + j4);
-      }
-#pragma unroll
-      for (int sp = 0; sp < MAX_SPLITS; ++sp) { v.x -= pv[sp].x; v.y -= pv[sp].y; v.z -= pv[sp].z; v.w -= pv[sp].w; }
-      *reinterpret_cast<float4*>(a.d0 + i * NB + j4) = v;
+    for (int e = 0; e < 16; ++e) {
+      const int q = tid + e * 256;
+      t[e] = __ldcg(reinterpret_cast<const float4*>(lp + static_cast<long long>(q >> 5) * a.ldl + (q & 31) * 4));
     }
-    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int q = tid + e * 256;
+      *reinterpret_cast<float4*>(s + (q >> 5) * DS + (q & 31) * 4) = t[e];
+    }
+  };
+  if (static_cast<int>(blockIdx.x) <= a.helpers) {
+    // helper: rows 8 (blockIdx.x - 1) .. +7 of the diagonal block, A11 - sum P (- the look-ahead term): thread = one
+    // column x four rows, so that a warp reads 32 consecutive rows of s (conflict-free float4) and broadcasts its own rows
+    const int col = tid & 127, ih = 8 * (blockIdx.x - 1) + 4 * (tid >> 7);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // A11 and its look-ahead partials first: their latency hides behind the staging and the FMA loop
+    float hv[4], hp[4][MAX_SPLITS];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = ih + r;
+      hv[r] = (col <= i) ? a.A[static_cast<long long>(j0 + i) * a.lda + j0 + col] : 0.0f;
+#pragma unroll
+      for (int sp = 0; sp < MAX_SPLITS; ++sp)
+        hp[r][sp] = (col <= i && sp < a.splits) ? a.partials[sp * a.split_stride + static_cast<long long>(i) * NB + col] : 0.0f;
+    }
+    if (a.late) {
+      stage_lp();
+      lp_staged = true;
+      cta_sync();
+      if (blockIdx.x == 1) PT3(30);
+      if (col <= ih + 3) {
+#pragma unroll 4
+        for (int k = 0; k < NB; k += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(s + col * DS + k);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float4 x = *reinterpret_cast<const float4*>(s + (ih + r) * DS + k);
+            acc[r] = fmaf(x.x, b.x, fmaf(x.y, b.y, fmaf(x.z, b.z, fmaf(x.w, b.w, acc[r]))));
+          }
+        }
+      }
+    }
+    if (blockIdx.x == 1) PT3(31);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = ih + r;
+      if (col <= i) {
+        float v = hv[r];
+#pragma unroll
+        for (int sp = 0; sp < MAX_SPLITS; ++sp) v -= hp[r][sp];
+        a.d0[i * NB + col] = v - acc[r];
+      }
+    }
+    cta_sync();
     if (tid == 0) {
       __threadfence();
       atomicAdd(a.helper_count, 1u);
     }
+    if (blockIdx.x == 1) PT3(32);
   }
+  if (blockIdx.x == 17) PT3(40);
   // one CTA per SM (the spin-waits need every CTA resident): a CTA takes row blocks blockIdx.x - 1, + gridDim.x - 1, ...
   // of 32 rows; from its second block on the epochs it waits for have already been published
   const int nblocks = (n - j0 - NB + RPC - 1) / RPC;
 #pragma unroll 1
-  for (int rb = blockIdx.x - 1; rb < nblocks; rb += gridDim.x - 1) {
+  for (int rb = blockIdx.x - 1; rb < nblocks; rb += a.trsm_ctas) {
   const int r0 = j0 + NB + rb * RPC;
   const int rows = min(RPC, n - r0);
   {
@@ -619,7 +673,41 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_h3_kernel(const PanelArgs 
       *reinterpret_cast<float4*>(at + i * DS + j4) = v[e];
     }
   }
+  if (blockIdx.x == 17 && rb == 16) PT3(41);
+  if (a.late) {
+    // look-ahead term: at -= L[r0 .., j0-128 : j0) L[j0 : j0+128, j0-128 : j0)^T  (32 x 128, K = 128, fp32 FMAs; thread =
+    // one column x 16 rows: a warp reads 32 consecutive rows of s and broadcasts the rows of la)
+    if (!lp_staged) stage_lp();
+    {
+      const float* lr = a.L + static_cast<long long>(r0) * a.ldl + (j0 - NB);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int q = tid + e * 256, i = q >> 5, j4 = (q & 31) * 4;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < rows) t = __ldcg(reinterpret_cast<const float4*>(lr + static_cast<long long>(i) * a.ldl + j4));
+        *reinterpret_cast<float4*>(la + i * DS + j4) = t;
+      }
+    }
+    cta_sync();
+    const int col = tid & 127, rg = 16 * (tid >> 7);
+    float acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = 0.0f;
+#pragma unroll 2
+    for (int k = 0; k < NB; k += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(s + col * DS + k);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float4 x = *reinterpret_cast<const float4*>(la + (rg + r) * DS + k);
+        acc[r] = fmaf(x.x, b.x, fmaf(x.y, b.y, fmaf(x.z, b.z, fmaf(x.w, b.w, acc[r]))));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) at[(rg + r) * DS + col] -= acc[r];
+    lp_staged = false;  // the stages below overwrite s
+  }
   if (blockIdx.x == 1) PT3(21);
+  if (blockIdx.x == 17 && rb == 16) PT3(42);
   const float* l11 = a.L + static_cast<long long>(j0) * a.ldl + j0;
   constexpr int CPT = 32 / TPR;  // columns per thread in the block-update phase
   const int row = tid % RPC, part = tid / RPC;
@@ -635,7 +723,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_h3_kernel(const PanelArgs 
         const int i = 32 * J + q / ncol4, j4 = (q % ncol4) * 4;
         *reinterpret_cast<float4*>(s + i * DS + j4) = __ldcg(reinterpret_cast<const float4*>(l11 + static_cast<long long>(i) * a.ldl + j4));
       }
-      __syncthreads();
+      cta_sync();
       // v -= X_I L11[J][I]^T: thread (row, part) owns CPT of the 32 columns of block J
       float v[CPT];
       {
@@ -677,9 +765,9 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_h3_kernel(const PanelArgs 
       dT[(jj + 3) * DT + k] = t.w;
       if (jj <= k && k < jj + 4) dinv[k] = 1.0f / (k == jj ? t.x : k == jj + 1 ? t.y : k == jj + 2 ? t.z : t.w);
     }
-    __syncthreads();
+    cta_sync();
     if (tid < RPC) row_solve32<1>(at + tid * DS + 32 * J, dT, dinv);  // in-block forward substitution, one thread per row
-    __syncthreads();
+    cta_sync();
   }
   if (blockIdx.x == 1) PT3(23);
   float* l21 = a.L + static_cast<long long>(r0) * a.ldl + j0;
@@ -692,29 +780,85 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_h3_kernel(const PanelArgs 
       store_l4(l21 + static_cast<long long>(i) * a.ldl, h21 + static_cast<long long>(i) * a.ldh,
                o21 + static_cast<long long>(i) * a.ldh, j4, *reinterpret_cast<const float4*>(at + i * DS + j4), sl);
   }
-  __syncthreads();
+  cta_sync();
   }  // row blocks
   if (blockIdx.x == 1) PT3(24);
+  if (blockIdx.x == 17) PT3(43);
 }
 
 // fp32 arrays + the two 96 x 128 B swizzled tf32 operand tiles of CTA 0's tensor-core update (1 KiB alignment slack)
-constexpr int PANEL_SMEM = (NB * DS + RPC * DS + 32 * DT) * static_cast<int>(sizeof(float)) + 2 * 12288 + 1024;
+constexpr int PANEL_SMEM = (NB * DS + 2 * RPC * DS + 32 * DT) * static_cast<int>(sizeof(float)) + 2 * 12288 + 1024;
+constexpr int FUSED_SMEM = PANEL_SMEM > H3_SMEM_BYTES ? PANEL_SMEM : H3_SMEM_BYTES;
+
+template <bool FULL, bool TIMING>
+__global__ void __launch_bounds__(256, 1) potrf_panel_h3_kernel(const PanelArgs a) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  panel_body<FULL, TIMING>(a, sm_raw);
+}
+
+// Look-ahead launch of panel k: CTAs [0, panel_ctas) run the panel program above (CTA 0 = diagonal block, then the row
+// owners), CTAs [panel_ctas, gridDim.x) each run one (tile, split) work item of the NEXT panel's update GEMM restricted to
+// the block-columns before panel k (final since the previous launch) - the tensor-core work that used to sit between two
+// panel kernels now fills the SMs the panel leaves idle, and nothing in one role waits for the other.  One CTA per SM
+// (the GEMM role's shared-memory footprint), grid <= number of SMs.
+template <bool TIMING>
+__global__ void __launch_bounds__(H3_THREADS, 1)
+potrf_fused_h3_kernel(const PanelArgs a, const H3Args g, const __grid_constant__ CUtensorMap tmAhi,
+                      const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmAlo,
+                      const __grid_constant__ CUtensorMap tmBlo, const int panel_ctas, const int gemm_tiles) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  if (static_cast<int>(blockIdx.x) < panel_ctas) {
+    if (threadIdx.x < 256) panel_body<true, TIMING>(a, sm_raw);
+    return;
+  }
+  const int w = blockIdx.x - panel_ctas;
+  gemm_h3_body<false, false>(g, tmAhi, tmBhi, tmAlo, tmBlo, sm_raw, w % gemm_tiles, w / gemm_tiles);
+}
+
+template <typename Kern, typename... Args>
+cudaError_t launch_maybe_pdl(Kern kern, int grid, int block, int smem, cudaStream_t stream, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+int env_flag(const char* name, int dflt) {
+  const char* e = getenv(name);
+  if (!e || !e[0]) return dflt;
+  return e[0] == '0' ? 0 : 1;
+}
+
+// split-K factor of an update GEMM with `tiles` row tiles and kb k-blocks when `ctas` CTAs are available
+int pick_splits(int tiles, int kb, int ctas) {
+  int S = ctas / tiles;
+  if (S < 1) S = 1;
+  if (S > MAX_SPLITS) S = MAX_SPLITS;
+  if (S > kb) S = kb;
+  return S;
+}
 
 }  // namespace
 
 size_t potrf_h3_workspace_bytes(int n) {
-  // 256 bytes of scalars (epoch word, helper counter) + the helpers' reduced diagonal block [128][128] + split-K partials: at most MAX_SPLITS x rows x 128 with splits*tiles <= ~148+8
+  // 256 bytes of scalars (epoch word, helper counter) + the helpers' reduced diagonal block [128][128] + two buffers of
+  // split-K partials (the look-ahead GEMM of panel k+1 writes one while panel k reads the other): at most
+  // MAX_SPLITS x rows x 128 each, with splits * tiles bounded by the SM count
   const long long rows = n > 0 ? n : 1;
   long long worst = 0;
   for (long long j0 = NB; j0 < rows; j0 += NB) {
     const long long M = rows - j0, tiles = (M + NB - 1) / NB;
-    long long S = 148 / tiles;
-    if (S < 1) S = 1;
-    if (S > MAX_SPLITS) S = MAX_SPLITS;
-    if (S > j0 / H3_BK) S = j0 / H3_BK;
+    const long long S = pick_splits(static_cast<int>(tiles), static_cast<int>(j0 / H3_BK), 148);
     if (S * M > worst) worst = S * M;
   }
-  return 256 + static_cast<size_t>(NB) * NB * sizeof(float) + static_cast<size_t>(worst) * NB * sizeof(float);
+  return 256 + static_cast<size_t>(NB) * NB * sizeof(float) + 2 * static_cast<size_t>(worst) * NB * sizeof(float);
 }
 
 int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long long ldl, const gsmvi_h3_operand& Lh, int n,
@@ -727,12 +871,20 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
     cudaError_t e = cudaFuncSetAttribute(potrf_panel_h3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_panel_h3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_panel_h3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_fused_h3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_fused_h3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
+  long long worst = 0;
+  for (long long j0 = NB; j0 < n; j0 += NB) {
+    const long long M = n - j0, tiles = (M + NB - 1) / NB;
+    const long long S = pick_splits(static_cast<int>(tiles), static_cast<int>(j0 / H3_BK), 148);
+    if (S * M > worst) worst = S * M;
+  }
   unsigned* ready = static_cast<unsigned*>(workspace);
   float* d0 = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
-  float* partials = d0 + NB * NB;
+  float* pbuf[2] = {d0 + NB * NB, d0 + NB * NB + worst * NB};
   unsigned helper_target = 0;
   __half* Lhi = static_cast<__half*>(Lh.hi);
   __half* Llo = static_cast<__half*>(Lh.lo);
@@ -748,27 +900,74 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
     max_ctas = sms > 17 ? sms : 148;  // one CTA per SM; helpers need 16 TRSM CTAs
   }
   const bool timing = getenv("GSMVI_POTRF_TIMING") != nullptr;
-  static int pdl_env = -1;
-  if (pdl_env < 0) {
-    const char* e = getenv("GSMVI_POTRF_PDL");
-    pdl_env = (e && e[0] == '0') ? 0 : 1;
-  }
-  const bool pdl = pdl_env == 1 && !timing;
-  for (int j0 = 0; j0 < n; j0 += NB) {
+  static int pdl_env = -1, look_env = -1;
+  if (pdl_env < 0) pdl_env = env_flag("GSMVI_POTRF_PDL", 1);
+  if (look_env < 0) look_env = env_flag("GSMVI_POTRF_LOOKAHEAD", 1);
+  const bool pdl = pdl_env == 1;
+  // Look-ahead (GSMVI_POTRF_LOOKAHEAD=0 disables): every full panel k >= 1 is one fused launch whose spare CTAs run the
+  // update GEMM of panel k+1 over the block-columns before panel k; panel k+1 then adds the K = 128 term of panel k itself.
+  const bool look = look_env == 1 && n >= 4 * NB && max_ctas >= 64;
+  int next_splits = 0;  // split count of the look-ahead partials the NEXT panel will find in pbuf[(k + 1) & 1]
+  for (int j0 = 0, k = 0; j0 < n; j0 += NB, ++k) {
     const int nb = min(NB, n - j0);
     const int M = n - j0, rest = M - nb;
+    const int nblocks = (rest + RPC - 1) / RPC;
     PanelArgs pa;
     pa.A = A; pa.lda = lda; pa.L = L; pa.ldl = ldl; pa.Lhi = Lhi; pa.Llo = Llo; pa.ldh = Lh.ld; pa.scale_l = Lh.scale;
-    pa.n = n; pa.j0 = j0; pa.nb = nb; pa.partials = partials; pa.splits = 0; pa.split_stride = static_cast<long long>(M) * NB;
+    pa.n = n; pa.j0 = j0; pa.nb = nb; pa.partials = pbuf[k & 1]; pa.splits = 0; pa.split_stride = static_cast<long long>(M) * NB;
     pa.flag = flag; pa.ready = ready; pa.epoch_base = epoch;
-    pa.d0 = d0; pa.helper_count = ready + 1; pa.helpers = 0; pa.helper_target = 0;
+    pa.d0 = d0; pa.helper_count = ready + 1; pa.helpers = 0; pa.helper_target = 0; pa.late = 0;
     epoch += 8;
+    const bool fused = look && nb == NB;
+    if (fused) {
+      // ---- this panel: look-ahead partials (from the previous launch, if any) + the late term
+      if (k >= 1) {
+        pa.splits = next_splits;
+        pa.late = 1;
+        pa.helpers = 16;
+        helper_target += 16;
+        pa.helper_target = helper_target;
+      }
+      // ---- hosted work: update of panel k+1 (if it is a full panel) with block-columns [0, j0)
+      const int nj0 = j0 + NB;
+      const bool host_next = k >= 1 && nj0 < n && n - nj0 >= NB;
+      int G = 0, gtiles = 1, S = 0;
+      H3Args ga = {};
+      CUtensorMap tm[4] = {};
+      if (host_next) {
+        const int Mn = n - nj0;
+        gtiles = (Mn + NB - 1) / NB;
+        S = pick_splits(gtiles, j0 / H3_BK, max_ctas - 1 - (nblocks > 16 ? nblocks : 16));
+        while (S > 1 && 1 + 16 + gtiles * S > max_ctas) --S;
+        G = gtiles * S;
+        HView va{Lhi + static_cast<long long>(nj0) * Lh.ld, Llo + static_cast<long long>(nj0) * Lh.ld, Mn, j0, Lh.ld, Lh.scale};
+        HView vb{Lhi + static_cast<long long>(nj0) * Lh.ld, Llo + static_cast<long long>(nj0) * Lh.ld, NB, j0, Lh.ld, Lh.scale};
+        H3Opts o;
+        o.splits = S;
+        o.split_stride = static_cast<long long>(Mn) * NB;
+        dim3 ggrid;
+        int rc = h3_prepare(Mn, NB, j0, va, vb, pbuf[(k + 1) & 1], NB, o, &ga, tm, &ggrid);
+        if (rc != GSMVI_OK) return rc;
+      }
+      next_splits = S;
+      int T = nblocks;
+      if (pa.helpers > 0 && T < 16) T = 16;
+      if (T > max_ctas - 1 - G) T = max_ctas - 1 - G;
+      if (T < (pa.helpers > 0 ? 16 : 0)) return GSMVI_EINVAL;  // cannot happen: G <= max_ctas - 17 by construction
+      pa.trsm_ctas = T > 0 ? T : 1;
+      const int grid = 1 + T + G;
+      cudaError_t le;
+      if (timing)
+        le = launch_maybe_pdl(potrf_fused_h3_kernel<true>, grid, H3_THREADS, FUSED_SMEM, stream, pdl, pa, ga, tm[0], tm[1], tm[2], tm[3], 1 + T, gtiles);
+      else
+        le = launch_maybe_pdl(potrf_fused_h3_kernel<false>, grid, H3_THREADS, FUSED_SMEM, stream, pdl, pa, ga, tm[0], tm[1], tm[2], tm[3], 1 + T, gtiles);
+      if (le != cudaSuccess) return static_cast<int>(le);
+      continue;
+    }
+    next_splits = 0;
     if (j0 > 0) {
       const int tiles = (M + NB - 1) / NB;
-      int S = 148 / tiles;
-      if (S < 1) S = 1;
-      if (S > MAX_SPLITS) S = MAX_SPLITS;
-      if (S > j0 / H3_BK) S = j0 / H3_BK;
+      const int S = pick_splits(tiles, j0 / H3_BK, 148);
       pa.splits = S;
       HView va{Lhi + static_cast<long long>(j0) * Lh.ld, Llo + static_cast<long long>(j0) * Lh.ld, M, j0, Lh.ld, Lh.scale};
       HView vb{Lhi + static_cast<long long>(j0) * Lh.ld, Llo + static_cast<long long>(j0) * Lh.ld, nb, j0, Lh.ld, Lh.scale};
@@ -776,32 +975,22 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
       o.splits = S;
       o.split_stride = pa.split_stride;
       o.pdl = pdl;
-      int rc = launch_gemm_h3(stream, M, nb, j0, va, vb, partials, NB, o);
+      int rc = launch_gemm_h3(stream, M, nb, j0, va, vb, pbuf[k & 1], NB, o);
       if (rc != GSMVI_OK) return rc;
     }
-    int grid = 1 + (rest + RPC - 1) / RPC;
+    int grid = 1 + nblocks;
     if (grid > max_ctas) grid = max_ctas;
+    pa.trsm_ctas = grid > 1 ? grid - 1 : 1;
     if (pa.splits > 0 && grid - 1 >= 16) {
       pa.helpers = 16;
       helper_target += 16;
       pa.helper_target = helper_target;
     }
-    if (nb < NB) potrf_panel_h3_kernel<false, false><<<1, 256, PANEL_SMEM, stream>>>(pa);
-    else if (timing && j0 == NB * 8) potrf_panel_h3_kernel<true, true><<<grid, 256, PANEL_SMEM, stream>>>(pa);
-    else if (pdl) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(grid);
-      cfg.blockDim = dim3(256);
-      cfg.dynamicSmemBytes = PANEL_SMEM;
-      cfg.stream = stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      cudaError_t le = cudaLaunchKernelEx(&cfg, potrf_panel_h3_kernel<true, false>, pa);
-      if (le != cudaSuccess) return static_cast<int>(le);
-    } else potrf_panel_h3_kernel<true, false><<<grid, 256, PANEL_SMEM, stream>>>(pa);
+    cudaError_t le;
+    if (nb < NB) le = launch_maybe_pdl(potrf_panel_h3_kernel<false, false>, 1, 256, PANEL_SMEM, stream, false, pa);
+    else if (timing) le = launch_maybe_pdl(potrf_panel_h3_kernel<true, true>, grid, 256, PANEL_SMEM, stream, pdl, pa);
+    else le = launch_maybe_pdl(potrf_panel_h3_kernel<true, false>, grid, 256, PANEL_SMEM, stream, pdl, pa);
+    if (le != cudaSuccess) return static_cast<int>(le);
   }
   if (timing && n > NB * 9) {
     long long h[64];
@@ -813,6 +1002,9 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
               h[3 + 4 * p] - h[2 + 4 * p], p < 3 ? h[4 + 4 * p] - h[3 + 4 * p] : 0LL, p < 3 ? h[5 + 4 * p] - h[4 + 4 * p] : 0LL);
     fprintf(stderr, " total %lld || CTA1: prefetch %lld, stage-3 start at %lld, solve end %lld, store %lld (since CTA0 start)\n",
             h[18] - h[0], h[21] - h[20], h[22] - h[0], h[23] - h[0], h[24] - h[0]);
+    fprintf(stderr, "[potrf_h3 panel 8] since CTA0 start: helper(CTA1) start %lld staged %lld fma %lld counted %lld | row CTA 17: released %lld "
+            "prefetched %lld late-term %lld end %lld\n", h[20] - h[0], h[30] - h[0], h[31] - h[0], h[32] - h[0], h[40] - h[0],
+            h[41] - h[0], h[42] - h[0], h[43] - h[0]);
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);

@@ -86,7 +86,7 @@ def test_potrf_flags_bad_matrices(lib, D, kind):
     assert int(bad.item()) == 1
 
 
-@pytest.mark.parametrize("D", [1, 5, 10, 64, 128, 129, 200, 512, 1000, 2048, 4096])
+@pytest.mark.parametrize("D", [1, 5, 10, 64, 128, 129, 200, 512, 640, 1000, 2048, 2200, 4096])
 def test_potrf_h3_matches_cholesky(lib, D):
     """Left-looking Cholesky on the scaled 3xFP16 engine: fp32 factor, its fp16 (hi, lo) split, zeroed upper blocks."""
     rng = np.random.RandomState(D)

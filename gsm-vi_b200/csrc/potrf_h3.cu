@@ -906,7 +906,8 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
   const bool pdl = pdl_env == 1;
   // Look-ahead (GSMVI_POTRF_LOOKAHEAD=0 disables): every full panel k >= 1 is one fused launch whose spare CTAs run the
   // update GEMM of panel k+1 over the block-columns before panel k; panel k+1 then adds the K = 128 term of panel k itself.
-  const bool look = look_env == 1 && n >= 4 * NB && max_ctas >= 64;
+  // (one GEMM work item per spare CTA: the next panel's row tiles must fit beside CTA 0 and the 16 helpers)
+  const bool look = look_env == 1 && n >= 4 * NB && max_ctas >= 64 && (n + NB - 1) / NB - 2 <= max_ctas - 17;
   int next_splits = 0;  // split count of the look-ahead partials the NEXT panel will find in pbuf[(k + 1) & 1]
   for (int j0 = 0, k = 0; j0 < n; j0 += NB, ++k) {
     const int nb = min(NB, n - j0);

@@ -140,6 +140,11 @@ class GSMEngine:
         panels = (self.D + 127) // 128
         if self.h3:
             potrf = 1 + panels + (panels - 1)  # prepare, panel kernels, left-looking update GEMMs
+            look = __import__("os").environ.get("GSMVI_POTRF_LOOKAHEAD", "1")[:1] != "0"
+            if look and 512 <= self.D <= 128 * 133:
+                # look-ahead (csrc/potrf_h3.cu): the update GEMMs run inside the fused panel launches; only a ragged last
+                # panel still has a GEMM launch of its own
+                potrf = 1 + panels + (1 if self.D % 128 else 0)
             draw = 2 if self.z_tape is not None else 1  # |Z| max + split of a tape slice, or Philox written split
             score = 4 if self.target is not None else 3  # sample, split X, score GEMM, split G | sample, |G| max, split G
             upd = 5 + 2  # W GEMM, row pass, split T, covariance GEMM, axpy + split Sigma_new, its max|.| word copied

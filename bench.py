@@ -264,11 +264,12 @@ def run_ours(args):
     n_launches = eng.launches_per_step() * args.steps
     eng.close()
     del eng, calls  # the fit below gets its workspaces from the caching allocator instead of fresh cudaMallocs
+    mean_h = torch.zeros(D).pin_memory()
+    cov_h = torch.eye(D).pin_memory()
+    m_host, c_host = torch.empty(D).pin_memory(), torch.empty(D, D).pin_memory()
+    g = GSM(D, tgt.lp, tgt.lp_g)
+    state_bytes = (D * D + D) * 4.0
     if world == 1:
-        mean_h = torch.zeros(D).pin_memory()
-        cov_h = torch.eye(D).pin_memory()
-        m_host, c_host = torch.empty(D).pin_memory(), torch.empty(D, D).pin_memory()
-        g = GSM(D, tgt.lp, tgt.lp_g)
         # (a) host-fed draws, as the reference works (it samples on the host every iteration, gsmvi/gsm.py:117-119): each
         #     step's B x D standard-normal draws come from pinned host memory (H2D inside the timed region, streamed one
         #     iteration ahead on a copy stream), each step's accept flag goes back (D2H), and (mean, cov) cross at both ends
@@ -293,7 +294,6 @@ def run_ours(args):
         c_host.copy_(c_fit, non_blocking=True)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        state_bytes = (D * D + D) * 4.0
         e2e = {"value": ke / dt_host, "unit": UNIT, "steps": ke,
                "h2d_bytes_per_step": B * D * 4.0 + state_bytes / ke, "d2h_bytes_per_step": 4 + state_bytes / ke,
                "note": "GSM.fit(key, mean=pinned host, cov=pinned host, niter=steps-1, z_tape=pinned host draws): every "
@@ -306,8 +306,40 @@ def run_ours(args):
                               "note": "same call with the library's own Philox sampler (the default): only (mean, cov) and the "
                                       "accept flags cross the bus"}}
     else:
-        e2e = {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
-               "note": "multi-rank: state is device-resident per rank; only the accept flag crosses per step"}
+        # the same two calls on every rank (batch-sharded fit): each rank feeds ITS B / world draws per step from its own
+        # pinned host tape and reads its accept flag back; time = max over ranks of the wall clock around the call,
+        # bracketed by barriers; bytes are whole-job (all ranks)
+        def timed_fit(niter, tape):
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            m_fit, c_fit = g.fit(99, mean=mean_h, cov=cov_h, batch_size=B, niter=niter, verbose=False, npass=npass,
+                                 z_tape=tape, process_group=group)
+            m_host.copy_(m_fit, non_blocking=True)
+            c_host.copy_(c_fit, non_blocking=True)
+            torch.cuda.synchronize()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        ke = max(4, min(args.steps, 32))
+        tape = torch.empty(ke, Bl, D, dtype=torch.float32).pin_memory()
+        tape.normal_(generator=torch.Generator().manual_seed(1 + rank))
+        timed_fit(2, tape)  # untimed warm-up
+        dt_host = timed_fit(ke - 1, tape)
+        del tape
+        timed_fit(2, None)
+        dt = timed_fit(args.steps - 1, None)
+        e2e = {"value": ke / dt_host, "unit": UNIT, "steps": ke,
+               "h2d_bytes_per_step": world * (Bl * D * 4.0 + state_bytes / ke),
+               "d2h_bytes_per_step": world * (4 + state_bytes / ke),
+               "note": "GSM.fit(..., process_group=WORLD, z_tape=this rank's pinned host draws) on every rank: each step's "
+                       "B/world x D draws per rank are copied host->device inside the timed region, every rank reads its "
+                       "accept flag back; the timed region also holds workspace + NVLink exchange-buffer set-up (IPC handle "
+                       "exchange), H2D of (mean, cov), the initial Cholesky and the final D2H of (mean, cov); max over ranks",
+               "device_rng": {"value": args.steps / dt, "unit": UNIT, "steps": args.steps,
+                              "h2d_bytes_per_step": world * state_bytes / args.steps,
+                              "d2h_bytes_per_step": world * (4 + state_bytes / args.steps),
+                              "note": "same call with the library's own Philox sampler (the default)"}}
 
     # ---- BaM leg of the BASELINE metric (same shape, example_bam.py schedule reg_i = 100/(1+i)); reported beside GSM
     bam = None

@@ -94,8 +94,15 @@ class GSMEngine:
             self.dmu = new_vec(D, dev)
         if z_tape is not None and not isinstance(z_tape, torch.Tensor):
             z_tape = torch.as_tensor(z_tape, dtype=torch.float32)
+        self._tape_off = self.rank * B
         if z_tape is not None:
-            assert z_tape.shape[1] == batch_size and z_tape.shape[2] == D
+            # [n, batch_size, D]: the global draws, every rank reads its slice; [n, batch_size / world, D] on a sharded
+            # fit: this rank's own draws (a rank then only holds - and pins - what it copies)
+            if self.world > 1 and z_tape.shape[1] == B:
+                self._tape_off = 0
+            else:
+                assert z_tape.shape[1] == batch_size
+            assert z_tape.shape[2] == D
         self.z_tape = z_tape
         self._tape_async = bool(z_tape is not None and npass == 4 and not z_tape.is_cuda and z_tape.is_pinned())
         if self._tape_async:
@@ -194,7 +201,7 @@ class GSMEngine:
         B, buf = self.B, j & 1
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.z_free[buf])  # the split that last read this buffer has run
-            self.Zbufs[buf].copy_(self.z_tape[j, self.rank * B:(self.rank + 1) * B], non_blocking=True)
+            self.Zbufs[buf].copy_(self.z_tape[j, self._tape_off:self._tape_off + B], non_blocking=True)
             self.z_ready[buf].record()
         self._tape_copied = j
 
@@ -204,7 +211,7 @@ class GSMEngine:
         host every iteration, gsmvi/gsm.py:117-119; this is that hand-over without the stall)."""
         B = self.B
         if not self._tape_async:
-            self.Z.copy_(self.z_tape[i, self.rank * B:(self.rank + 1) * B], non_blocking=True)
+            self.Z.copy_(self.z_tape[i, self._tape_off:self._tape_off + B], non_blocking=True)
             return self.Z
         if self._tape_copied < i:
             self._tape_copy(i)
@@ -359,7 +366,7 @@ class GSMEngine:
         D, B, npass = self.D, self.B, self.npass
         # ---- sample (gsm.py:117-119)
         if self.z_tape is not None:
-            self.Z.copy_(self.z_tape[i, self.rank * B:(self.rank + 1) * B], non_blocking=True)
+            self.Z.copy_(self.z_tape[i, self._tape_off:self._tape_off + B], non_blocking=True)
         else:
             L.philox_normal(self.Zb, B, D, self.seed, i * self.world + self.rank)
         L.sample(self.mu, self.Lhi, self.Zb, self.Xb, B, D, npass, L_lo=self.Llo)
@@ -421,7 +428,8 @@ class GSM:
         is always checked; unlike the reference, niter < nprint does not raise ZeroDivisionError).  Extra keyword-only
         arguments:
           z_tape: optional [niter+1, batch_size, D] standard-normal draws used instead of the Philox stream
-                  (parity runs: the same tape is fed to the oracle)
+                  (parity runs: the same tape is fed to the oracle); with a process_group a
+                  rank may pass only its own [niter+1, batch_size / world, D] slice
           npass: tensor-core precision: 4 = scaled 3xFP16 split (default; 22-bit significands like 3xTF32 at twice the
                   pipe rate), 3 = 3xTF32 round-to-nearest split, 2 = 3xTF32 truncation split, 1 = single TF32 pass
           process_group: torch.distributed group; the batch is sharded across its ranks and the D x D statistics are

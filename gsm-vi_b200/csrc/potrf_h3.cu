@@ -13,6 +13,11 @@
 //       as the fp16 pair, which is what the next panels' update GEMMs (and the sampler) load by TMA.
 // Left-looking means the trailing matrix is never rewritten: total update traffic is ~D^3/(3*128) operand bytes read
 // once instead of a D^2 read-modify-write per panel, and each update is one long-K GEMM instead of a K=128 sliver.
+// Look-ahead form (default for 512 <= n <= ~17k, GSMVI_POTRF_LOOKAHEAD=0 disables): ONE launch per panel.  The fused
+// kernel's first CTAs run the panel program (2); its remaining CTAs each run one (row tile, split) work item of the
+// NEXT panel's update (1) restricted to the block-columns before the current panel - final at launch time, so neither
+// role waits for the other - and the next panel subtracts the current panel's own K = 128 term in fp32 on the CUDA cores
+// (row owners and helper CTAs, operands staged from L2 into shared memory).  See DESIGN.md section 3.2.
 #include "potrf.cuh"
 #include "chol_block.cuh"
 #include "h3_gemm.cuh"

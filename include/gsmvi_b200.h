@@ -138,7 +138,8 @@ int gsmvi_potrf_check(const float* Sigma, long long lds, float* L, long long ldl
                       void* workspace, int npass, void* stream);
 
 /* Same contract as gsmvi_potrf_check on the scaled 3xFP16 engine: left-looking panels (one long-K split-K update GEMM +
- * one panel kernel each), L also written as the fp16 pair *L_split (scale from max |Sigma_ii|) for the sampler's and the
+ * one panel kernel each; for 512 <= D <= ~17k one fused launch per panel whose spare CTAs run the next panel's update
+ * GEMM - environment GSMVI_POTRF_LOOKAHEAD=0 selects the two-launch form), L also written as the fp16 pair *L_split (scale from max |Sigma_ii|) for the sampler's and the
  * later panels' TMA loads.  zero_upper = 0: the blocks above the diagonal are left untouched (valid for a buffer that
  * was zeroed once).  workspace: gsmvi_workspace_bytes(GSMVI_WS_POTRF_H3, 0, D). */
 int gsmvi_potrf_h3(const float* Sigma, long long lds, float* L, long long ldl, const gsmvi_h3_operand* L_split, int D,

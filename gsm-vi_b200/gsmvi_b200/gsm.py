@@ -33,6 +33,24 @@ def gsm_update(samples, vs, mu0, S0, npass=3):
     return mu_out[:D].clone(), O.clone()
 
 
+def launch_count(D, h3=True, tape=False, builtin_target=True, world=1, lookahead=True):
+    """Library kernels launched by one GSM iteration (GSMEngine.step), by engine and options."""
+    panels = (D + 127) // 128
+    if h3:
+        potrf = 1 + panels + (panels - 1)  # prepare, panel kernels, left-looking update GEMMs
+        if lookahead and 512 <= D <= 128 * 133:
+            # look-ahead (csrc/potrf_h3.cu): the update GEMMs run inside the fused panel launches; only a ragged last
+            # panel still has a GEMM launch of its own
+            potrf = 1 + panels + (1 if D % 128 else 0)
+        draw = 2 if tape else 1  # |Z| max + split of a tape slice, or Philox written split
+        score = 4 if builtin_target else 3  # sample, split X, score GEMM, split G | sample, |G| max, split G
+        upd = 5 + 2  # W GEMM, row pass, split T, covariance GEMM, axpy + split Sigma_new, its max|.| word copied
+        return draw + score + upd + potrf + (3 if world > 1 else 0)
+    potrf = 1 + panels + (panels - 1)  # tril copy, panel kernels, SYRK GEMMs
+    upd = 4 + 2  # W GEMM, row pass, covariance GEMM, axpy + the two tf32_split launches (Sigma_new, L_new)
+    return (0 if tape else 1) + 1 + (1 if builtin_target else 0) + upd + potrf + (2 if world > 1 else 0)
+
+
 class GSMEngine:
     """Device-resident state and workspaces of one GSM fit; `step(i)` is one loop body of gsmvi/gsm.py:107-129
     (sample -> score -> update -> goodness check -> accept/revert).  GSM.fit drives it; bench.py times it."""
@@ -144,22 +162,8 @@ class GSMEngine:
 
     def launches_per_step(self):
         """Kernels of libgsmvi_b200.so launched by one step (bench.py reports it as gpu_launches)."""
-        panels = (self.D + 127) // 128
-        if self.h3:
-            potrf = 1 + panels + (panels - 1)  # prepare, panel kernels, left-looking update GEMMs
-            look = __import__("os").environ.get("GSMVI_POTRF_LOOKAHEAD", "1")[:1] != "0"
-            if look and 512 <= self.D <= 128 * 133:
-                # look-ahead (csrc/potrf_h3.cu): the update GEMMs run inside the fused panel launches; only a ragged last
-                # panel still has a GEMM launch of its own
-                potrf = 1 + panels + (1 if self.D % 128 else 0)
-            draw = 2 if self.z_tape is not None else 1  # |Z| max + split of a tape slice, or Philox written split
-            score = 4 if self.target is not None else 3  # sample, split X, score GEMM, split G | sample, |G| max, split G
-            upd = 5 + 2  # W GEMM, row pass, split T, covariance GEMM, axpy + split Sigma_new, its max|.| word copied
-            return draw + score + upd + potrf + (3 if self.world > 1 else 0)
-        potrf = 1 + panels + (panels - 1)  # tril copy, panel kernels, SYRK GEMMs
-        upd = 4 + 2  # W GEMM, row pass, covariance GEMM, axpy + the two tf32_split launches (Sigma_new, L_new)
-        return (0 if self.z_tape is not None else 1) + 1 + (1 if self.target is not None else 0) + upd + potrf + \
-            (2 if self.world > 1 else 0)
+        look = __import__("os").environ.get("GSMVI_POTRF_LOOKAHEAD", "1")[:1] != "0"
+        return launch_count(self.D, self.h3, self.z_tape is not None, self.target is not None, self.world, look)
 
     def gemm_calls(self):
         """The four batch-sized tensor-core launches of one step (sampler, score, W = G Sigma, covariance update) as

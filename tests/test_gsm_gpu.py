@@ -67,7 +67,7 @@ def test_potrf_matches_cholesky(lib, D):
     assert np.linalg.norm(rec @ rec.T - Sv.cpu().double().numpy()) / np.linalg.norm(S) < 5e-6
 
 
-@pytest.mark.parametrize("D,kind", [(64, "indef"), (300, "indef"), (300, "nan"), (130, "late")])
+@pytest.mark.parametrize("D,kind", [(64, "indef"), (300, "indef"), (300, "nan"), (130, "late"), (640, "indef"), (1000, "nan"), (768, "late")])
 def test_potrf_flags_bad_matrices(lib, D, kind):
     rng = np.random.RandomState(1)
     A = rng.normal(size=(D, D))
@@ -113,7 +113,7 @@ def test_potrf_h3_matches_cholesky(lib, D):
     record("potrf_h3", dict(D=D, relF_L=relF(Lv, Lref)))
 
 
-@pytest.mark.parametrize("D,kind", [(64, "indef"), (300, "indef"), (300, "nan"), (130, "late")])
+@pytest.mark.parametrize("D,kind", [(64, "indef"), (300, "indef"), (300, "nan"), (130, "late"), (640, "indef"), (1000, "nan"), (768, "late")])
 def test_potrf_h3_flags_bad_matrices(lib, D, kind):
     rng = np.random.RandomState(1)
     A = rng.normal(size=(D, D))

@@ -46,27 +46,6 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// acc[r][c] += sum_k Arows[r * lda_][k] * Brows[c * ldb_][k]   (both row-major over k; kbeg, kend multiples of 4)
-__device__ __forceinline__ void tile4x4_mac(const float* __restrict__ Arows, int lda_, const float* __restrict__ Brows,
-                                            int ldb_, int kbeg, int kend, float (&acc)[4][4]) {
-  for (int k = kbeg; k < kend; k += 4) {
-    float4 a[4], b[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(Arows + r * lda_ + k);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) b[c] = *reinterpret_cast<const float4*>(Brows + c * ldb_ + k);
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        acc[r][c] += a[r].x * b[c].x + a[r].y * b[c].y + a[r].z * b[c].z + a[r].w * b[c].w;
-  }
-}
-
-// Forward substitution of one row against a 32 x 32 lower-triangular block, right-looking so that the dependent chain
-// per column is one multiply and one FMA:  x_j = v_j / l_jj;  v_k -= x_j l_kj (k > j).  dT holds the block TRANSPOSED
-// (dT[j * DT + k] = l_kj) so the column below the pivot is read as broadcast float4s.  Fully unrolled (a rolled variant
-// with rotated registers measured 40% slower); the solved row is written to out_row[0..31].
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -169,6 +148,10 @@ __device__ __forceinline__ void chol32_coop(float* __restrict__ blk, float* __re
   if (warp == 0 && __any_sync(0xffffffffu, !(mydiag > 0.0f) || !(mydiag < 3.0e38f)) && lane == 0) *bad = 1;
 }
 
+// Forward substitution of one row against a 32 x 32 lower-triangular block, right-looking so that the dependent chain
+// per column is one multiply and one FMA:  x_j = v_j / l_jj;  v_k -= x_j l_kj (k > j).  dT holds the block TRANSPOSED
+// (dT[j * DT + k] = l_kj) so the column below the pivot is read as broadcast float4s.  Fully unrolled (a rolled variant
+// with rotated registers measured 40% slower); the solved row replaces row_io[0..31].
 // Inlined on purpose: every CTA runs this code once per launch from a cold instruction cache, and fall-through code is
 // prefetched while the first call of an out-of-line copy measured 11-12k cycles (one full miss per 128-byte line).
 template <int COPY>

@@ -149,6 +149,8 @@ int gsmvi_potrf_h3(const float* Sigma, long long lds, float* L, long long ldl, c
   return potrf_h3(S(stream), Sigma, lds, L, ldl, *L_split, D, bad_flag, workspace, zero_upper);
 }
 
+int gsmvi_potrf_h3_plan(int D, int sms, int* rows, int max_rows) { return potrf_h3_plan(D, sms, rows, max_rows); }
+
 int gsmvi_philox_normal(float* Z, long long ldz, int B, int D, unsigned long long seed, unsigned long long offset,
                         void* stream) {
   return philox_normal(S(stream), Z, ldz, B, D, seed, offset);

@@ -849,13 +849,26 @@ size_t potrf_h3_workspace_bytes(int n) {
   return 256 + static_cast<size_t>(NB) * NB * sizeof(float) + 2 * static_cast<size_t>(worst) * NB * sizeof(float);
 }
 
-int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long long ldl, const gsmvi_h3_operand& Lh, int n,
-             int* flag, void* workspace, int zero_upper) {
-  if (n <= 0 || !A || !L || !flag || !workspace || !Lh.hi || !Lh.lo || !Lh.scale) return GSMVI_EINVAL;
-  if ((lda & 3) != 0 || (ldl & 3) != 0 || (Lh.ld & 7) != 0 || ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(L)) & 15) != 0)
-    return GSMVI_EALIGN;
+// The launch plan of a factorisation (one row of eight ints per panel), recorded instead of launched when `plan` is set:
+// the grid arithmetic below is what keeps every spin-wait's partner resident, so it is testable without a GPU.
+struct PlanSink {
+  int sms;       // number of SMs to plan for
+  int* rows;     // [max_rows][8]: j0, fused, panel CTAs (1 + row owners), GEMM CTAs, GEMM row tiles, GEMM splits,
+                 //                partial planes this panel reads, helpers
+  int max_rows, count;
+};
+
+static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, float* L, long long ldl, const gsmvi_h3_operand& Lh,
+                         int n, int* flag, void* workspace, int zero_upper, PlanSink* plan) {
+  if (!plan) {
+    if (n <= 0 || !A || !L || !flag || !workspace || !Lh.hi || !Lh.lo || !Lh.scale) return GSMVI_EINVAL;
+    if ((lda & 3) != 0 || (ldl & 3) != 0 || (Lh.ld & 7) != 0 || ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(L)) & 15) != 0)
+      return GSMVI_EALIGN;
+  } else if (n <= 0) {
+    return GSMVI_EINVAL;
+  }
   static bool attr_set = false;
-  if (!attr_set) {
+  if (!attr_set && !plan) {
     cudaError_t e = cudaFuncSetAttribute(potrf_panel_h3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_panel_h3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_panel_h3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
@@ -876,17 +889,27 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
   unsigned helper_target = 0;
   __half* Lhi = static_cast<__half*>(Lh.hi);
   __half* Llo = static_cast<__half*>(Lh.lo);
-  potrf_prepare_kernel<<<1, 256, 0, stream>>>(A, lda, n, Lh.scale, ready, flag);
-  if (zero_upper && n > NB)
-    potrf_zero_upper_kernel<<<dim3((n / 4 + 255) / 256, n), 256, 0, stream>>>(L, ldl, Lhi, Llo, Lh.ld, n);
+  if (!plan) {
+    potrf_prepare_kernel<<<1, 256, 0, stream>>>(A, lda, n, Lh.scale, ready, flag);
+    if (zero_upper && n > NB)
+      potrf_zero_upper_kernel<<<dim3((n / 4 + 255) / 256, n), 256, 0, stream>>>(L, ldl, Lhi, Llo, Lh.ld, n);
+  }
   unsigned epoch = 0;
-  static int max_ctas = 0;
-  if (max_ctas == 0) {
+  static int dev_ctas = 0;
+  if (dev_ctas == 0 && !plan) {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    max_ctas = sms > 17 ? sms : 148;  // one CTA per SM; helpers need 16 TRSM CTAs
+    dev_ctas = sms > 17 ? sms : 148;  // one CTA per SM; helpers need 16 TRSM CTAs
   }
+  const int max_ctas = plan ? (plan->sms > 17 ? plan->sms : 148) : dev_ctas;
+  auto record = [&](int j0_, int fused_, int panel_ctas_, int gemm_ctas_, int gemm_tiles_, int gemm_splits_, int splits_in_, int helpers_) {
+    if (plan->count < plan->max_rows) {
+      int* r = plan->rows + 8 * plan->count;
+      r[0] = j0_; r[1] = fused_; r[2] = panel_ctas_; r[3] = gemm_ctas_; r[4] = gemm_tiles_; r[5] = gemm_splits_; r[6] = splits_in_; r[7] = helpers_;
+    }
+    ++plan->count;
+  };
   const bool timing = getenv("GSMVI_POTRF_TIMING") != nullptr;
   static int pdl_env = -1, look_env = -1;
   if (pdl_env < 0) pdl_env = env_flag("GSMVI_POTRF_PDL", 1);
@@ -928,6 +951,10 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
         gtiles = (Mn + NB - 1) / NB;
         S = pick_splits(gtiles, j0 / H3_BK, max_ctas - 1 - (nblocks > 16 ? nblocks : 16));
         while (S > 1 && 1 + 16 + gtiles * S > max_ctas) --S;
+        {  // never more planes than potrf_h3_workspace_bytes sized the partial buffers for (a no-op up to 148 SMs)
+          const int s_ws = pick_splits(gtiles, j0 / H3_BK, 148);
+          if (S > s_ws) S = s_ws;
+        }
         G = gtiles * S;
         HView va{Lhi + static_cast<long long>(nj0) * Lh.ld, Llo + static_cast<long long>(nj0) * Lh.ld, Mn, j0, Lh.ld, Lh.scale};
         HView vb{Lhi + static_cast<long long>(nj0) * Lh.ld, Llo + static_cast<long long>(nj0) * Lh.ld, NB, j0, Lh.ld, Lh.scale};
@@ -935,8 +962,10 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
         o.splits = S;
         o.split_stride = static_cast<long long>(Mn) * NB;
         dim3 ggrid;
-        int rc = h3_prepare(Mn, NB, j0, va, vb, pbuf[(k + 1) & 1], NB, o, &ga, tm, &ggrid);
-        if (rc != GSMVI_OK) return rc;
+        if (!plan) {
+          int rc = h3_prepare(Mn, NB, j0, va, vb, pbuf[(k + 1) & 1], NB, o, &ga, tm, &ggrid);
+          if (rc != GSMVI_OK) return rc;
+        }
       }
       next_splits = S;
       int T = nblocks;
@@ -945,6 +974,10 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
       if (T < (pa.helpers > 0 ? 16 : 0)) return GSMVI_EINVAL;  // cannot happen: G <= max_ctas - 17 by construction
       pa.trsm_ctas = T > 0 ? T : 1;
       const int grid = 1 + T + G;
+      if (plan) {
+        record(j0, 1, 1 + T, G, host_next ? gtiles : 0, S, pa.splits, pa.helpers);
+        continue;
+      }
       cudaError_t le;
       if (timing)
         le = launch_maybe_pdl(potrf_fused_h3_kernel<true>, grid, H3_THREADS, FUSED_SMEM, stream, pdl, pa, ga, tm[0], tm[1], tm[2], tm[3], 1 + T, gtiles);
@@ -964,8 +997,10 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
       o.splits = S;
       o.split_stride = pa.split_stride;
       o.pdl = pdl;
-      int rc = launch_gemm_h3(stream, M, nb, j0, va, vb, pbuf[k & 1], NB, o);
-      if (rc != GSMVI_OK) return rc;
+      if (!plan) {
+        int rc = launch_gemm_h3(stream, M, nb, j0, va, vb, pbuf[k & 1], NB, o);
+        if (rc != GSMVI_OK) return rc;
+      }
     }
     int grid = 1 + nblocks;
     if (grid > max_ctas) grid = max_ctas;
@@ -975,12 +1010,18 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
       helper_target += 16;
       pa.helper_target = helper_target;
     }
+    if (plan) {
+      const int tiles = (M + NB - 1) / NB;
+      record(j0, 0, nb < NB ? 1 : grid, pa.splits > 0 ? tiles * pa.splits : 0, pa.splits > 0 ? tiles : 0, pa.splits, pa.splits, pa.helpers);
+      continue;
+    }
     cudaError_t le;
     if (nb < NB) le = launch_maybe_pdl(potrf_panel_h3_kernel<false, false>, 1, 256, PANEL_SMEM, stream, false, pa);
     else if (timing) le = launch_maybe_pdl(potrf_panel_h3_kernel<true, true>, grid, 256, PANEL_SMEM, stream, pdl, pa);
     else le = launch_maybe_pdl(potrf_panel_h3_kernel<true, false>, grid, 256, PANEL_SMEM, stream, pdl, pa);
     if (le != cudaSuccess) return static_cast<int>(le);
   }
+  if (plan) return GSMVI_OK;
   if (timing && n > NB * 9) {
     long long h[64];
     cudaStreamSynchronize(stream);
@@ -997,6 +1038,19 @@ int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long 
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
+}
+
+int potrf_h3(cudaStream_t stream, const float* A, long long lda, float* L, long long ldl, const gsmvi_h3_operand& Lh, int n,
+             int* flag, void* workspace, int zero_upper) {
+  return potrf_h3_impl(stream, A, lda, L, ldl, Lh, n, flag, workspace, zero_upper, nullptr);
+}
+
+int potrf_h3_plan(int n, int sms, int* rows, int max_rows) {
+  if (n <= 0 || sms <= 0 || (!rows && max_rows > 0)) return GSMVI_EINVAL;
+  PlanSink sink{sms, rows, max_rows, 0};
+  gsmvi_h3_operand none = {};
+  const int rc = potrf_h3_impl(nullptr, nullptr, 0, nullptr, 0, none, n, nullptr, nullptr, 0, &sink);
+  return rc == GSMVI_OK ? sink.count : (rc > 0 ? -rc : rc);
 }
 
 }  // namespace gsmvi

@@ -274,6 +274,8 @@ def _declare_h3(L):
     L.gsmvi_gauss_score_h3.argtypes = [hp, hp, c_p, c_p, c_ll, c_p, hp, c_i, c_i, c_p]
     L.gsmvi_h3_bound_scales.restype = c_i
     L.gsmvi_h3_bound_scales.argtypes = [c_p, c_i, c_p, c_p, c_f, c_f, c_f, c_p, c_p, c_p]
+    L.gsmvi_potrf_h3_plan.restype = c_i
+    L.gsmvi_potrf_h3_plan.argtypes = [c_i, c_i, c_p, c_i]
     L.gsmvi_potrf_h3.restype = c_i
     L.gsmvi_potrf_h3.argtypes = [c_p, c_ll, c_p, c_ll, hp, c_i, c_p, c_p, c_i, c_p]
     L.gsmvi_gsm_update_h3.restype = c_i
@@ -369,6 +371,18 @@ def gsm_update_h3(X, G, Gh, mu, Sigma, Sh, mu_out, Sigma_out, absmax_sout, B, D,
 
 def h3_absmax(A, rows, cols, absmax):
     check(lib().gsmvi_h3_absmax(ptr(A), A.stride(0), rows, cols, ptr(absmax), stream_ptr()), "gsmvi_h3_absmax")
+
+
+def potrf_h3_plan(D, sms=148):
+    """Launch plan of potrf_h3 for a D x D matrix on `sms` SMs (host-only dry run): list of dicts, one per panel."""
+    import ctypes
+    n = (D + 127) // 128
+    buf = (ctypes.c_int * (8 * n))()
+    got = lib().gsmvi_potrf_h3_plan(D, sms, ctypes.cast(buf, ctypes.c_void_p), n)
+    if got != n:
+        raise GsmviError("gsmvi_potrf_h3_plan returned %d for D=%d" % (got, D))
+    keys = ("j0", "fused", "panel_ctas", "gemm_ctas", "gemm_tiles", "gemm_splits", "splits_in", "helpers")
+    return [dict(zip(keys, buf[8 * i: 8 * i + 8])) for i in range(n)]
 
 
 def potrf_h3(Sigma, L_out, Lh, D, bad_flag, ws, zero_upper=True):

@@ -145,6 +145,13 @@ int gsmvi_potrf_check(const float* Sigma, long long lds, float* L, long long ldl
 int gsmvi_potrf_h3(const float* Sigma, long long lds, float* L, long long ldl, const gsmvi_h3_operand* L_split, int D,
                    int* bad_flag, void* workspace, int zero_upper, void* stream);
 
+/* Dry run of gsmvi_potrf_h3's launch loop (the goodness check of gsmvi/gsm.py:136-150) for a D x D matrix on a device
+ * with `sms` SMs; no CUDA call is made.  One row of eight ints per 128-column panel is written to rows[max_rows][8]:
+ * first column, fused launch (1/0), panel CTAs (diagonal block + row owners), GEMM CTAs, GEMM row tiles, GEMM split-K
+ * factor, partial planes the panel reads, helper CTAs.  Returns the number of panels (< 0: error).  The kernels spin
+ * on each other inside a launch, so panel CTAs + GEMM CTAs <= sms is the invariant that matters; tests check it here. */
+int gsmvi_potrf_h3_plan(int D, int sms, int* rows, int max_rows);
+
 /* Z[B,D] <- N(0,1), Philox4x32-10 keyed by seed, counter (element, offset).  Replaces the host RNG of
  * np.random.seed / np.random.multivariate_normal (gsmvi/gsm.py:117-119). */
 int gsmvi_philox_normal(float* Z, long long ldz, int B, int D, unsigned long long seed, unsigned long long offset,

@@ -145,6 +145,49 @@ def test_launch_count_formula():
     assert launch_count(4096, world=8) == 48 and launch_count(4096, tape=True) == 46
 
 
+def test_potrf_h3_launch_plan_keeps_every_spin_wait_partner_resident():
+    """The Cholesky's CTAs spin on each other inside a launch (row owners on CTA 0's epochs, CTA 0 on the helpers), so a
+    launch must fit the device at one CTA per SM; the look-ahead GEMM of the next panel may only take what is left.
+    Checked on the host through the dry run of the launch loop, for ragged and aligned sizes and other SM counts."""
+    from gsmvi_b200 import _lib
+    lib = _lib.lib()
+    for sms in (148, 132, 64, 160, 192):
+        for D in (1, 100, 128, 129, 384, 512, 640, 1000, 1024, 2048, 2200, 4000, 4096, 8192, 12000, 17024, 17025, 20000):
+            plan = _lib.potrf_h3_plan(D, sms)
+            assert [p["j0"] for p in plan] == list(range(0, D, 128))
+            ws_floats = lib.gsmvi_workspace_bytes(_lib.WS_POTRF_H3, 0, D) // 4
+            per_buffer = (ws_floats - 64 - 128 * 128) // 2  # floats per partial buffer
+            for k, p in enumerate(plan):
+                nb = min(128, D - p["j0"])
+                rest = D - p["j0"] - nb
+                if p["fused"]:
+                    assert nb == 128
+                    assert p["panel_ctas"] + p["gemm_ctas"] <= sms, (D, sms, p)
+                    assert p["gemm_ctas"] == p["gemm_tiles"] * p["gemm_splits"]
+                    row_ctas = p["panel_ctas"] - 1
+                    assert row_ctas >= p["helpers"] and row_ctas <= max((rest + 31) // 32, 16)
+                    assert (row_ctas >= 1) or rest == 0
+                    if k >= 1:
+                        assert p["helpers"] == 16  # CTA 0 always starts from the helpers' reduced diagonal block
+                    if p["gemm_ctas"]:
+                        # the hosted GEMM is the next panel's update: its row tiles and its partial planes fit the buffer
+                        Mn = D - p["j0"] - 128
+                        assert p["gemm_tiles"] == (Mn + 127) // 128 and 1 <= p["gemm_splits"] <= min(8, p["j0"] // 64)
+                        assert p["gemm_splits"] * Mn * 128 <= per_buffer
+                        assert plan[k + 1]["fused"] and plan[k + 1]["splits_in"] == p["gemm_splits"]
+                    elif k + 1 < len(plan) and plan[k + 1]["fused"]:
+                        assert k == 0 and plan[k + 1]["splits_in"] == 0  # panel 1 has only the K = 128 term
+                else:
+                    assert p["panel_ctas"] <= sms and p["helpers"] in (0, 16)
+                    if p["helpers"]:
+                        assert p["panel_ctas"] - 1 >= 16
+                    assert p["splits_in"] * (D - p["j0"]) * 128 <= per_buffer
+            if 512 <= D <= 128 * (sms - 17 + 2) and sms >= 64:
+                assert all(p["fused"] for p in plan if min(128, D - p["j0"]) == 128), (D, sms)
+            else:
+                assert not any(p["fused"] for p in plan)
+
+
 WORKER = r'''
 import os, sys
 import numpy as np

@@ -94,7 +94,11 @@ class CommBuffer:
         self.dist.barrier(group=self.group)  # nobody is still writing into a buffer that is about to be unmapped
         for p in self.opened:
             self.lib.gsmvi_comm_close(p)
+        self.opened = []
         self.flat = None
         self.S = None
+        # an exported allocation must outlive every importer's mapping (cudaFree before the peers' cudaIpcCloseMemHandle is
+        # undefined behaviour): free only after every rank has closed its mappings
+        self.dist.barrier(group=self.group)
         self.lib.gsmvi_comm_free(self.own)
         self.own = None

@@ -1,5 +1,6 @@
 // Multi-GPU exchange of the GSM batch statistics over NVLink peer memory, fused with the
-// covariance-update GEMM instead of an NCCL all-reduce after it.
+// covariance-update GEMM instead of an NCCL all-reduce after it.  What is exchanged are the two batch means of
+// gsm_update (gsmvi/gsm.py:53-54: mean over samples of mu_update and S_update), each rank holding B / world samples.
 //
 // One process per GPU; every rank owns a "comm buffer" (cudaMalloc + CUDA IPC, mapped by all peers):
 //     [ staging: world x tpo dense 128x128 tiles | Sigma buffer 0 | Sigma buffer 1 | dmu: world x ld | counters ]

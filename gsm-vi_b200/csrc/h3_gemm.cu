@@ -1,4 +1,6 @@
 // Host side of the scaled 3xFP16 GEMM (h3_gemm.cuh): fp16 tensor maps, dispatch, and the operand split kernels.
+// The contractions it serves: sampler x = mu + z L^T (gsmvi/gsm.py:119), dense-Gaussian score (examples/
+// example_gsm_numpy.py:24-29), W = G Sigma and the batch-mean covariance update of gsm_update (gsmvi/gsm.py:11-27, 53-54).
 #include "h3_gemm.cuh"
 
 namespace gsmvi {

@@ -145,6 +145,36 @@ def test_launch_count_formula():
     assert launch_count(4096, world=8) == 48 and launch_count(4096, tape=True) == 46
 
 
+def test_scaled_fp16_split_model_keeps_22_bits():
+    """numpy model of the operand format of the h3 GEMM engine (csrc/h3_gemm.cuh): per-tensor power-of-two scale,
+    hi = rn_f16(a s), lo = rn_f16((a s - hi) 2^11), three products hi hi + (lo hi + hi lo) 2^-11.  The pair reproduces an
+    fp32 operand to 2^-22 of the tensor's absmax and the three-term product is fp32-grade (the GPU tests check the
+    kernels against exactly this claim)."""
+    rng = np.random.RandomState(0)
+
+    def split(a):
+        e = np.frexp(np.abs(a).max())[1]
+        s = np.float32(2.0 ** (14 - e))
+        x = a * s
+        hi = x.astype(np.float16)
+        lo = ((x - hi.astype(np.float32)) * np.float32(2048.0)).astype(np.float16)
+        return hi, lo, s
+
+    A = (rng.normal(size=(48, 512)) * 10.0 ** rng.uniform(-2, 2, size=(48, 1))).astype(np.float32)
+    B = (rng.normal(size=(40, 512)) * 3.0).astype(np.float32)
+    ah, al, sa = split(A)
+    bh, bl, sb = split(B)
+    assert np.isfinite(ah.astype(np.float32)).all() and np.abs(ah.astype(np.float32)).max() < 2.0 ** 14
+    recon = (ah.astype(np.float64) + al.astype(np.float64) / 2048.0) / sa
+    assert np.abs(recon - A).max() <= 2.0 ** -22 * np.abs(A).max()
+    ah, al, bh, bl = (t.astype(np.float64) for t in (ah, al, bh, bl))
+    C = (ah @ bh.T + (al @ bh.T + ah @ bl.T) / 2048.0) / (float(sa) * float(sb))
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    assert np.linalg.norm(C - ref) / np.linalg.norm(ref) < 2e-7
+    # a single fp16 pass (hi only) is four orders of magnitude worse: the lo terms are what buys fp32 grade
+    assert np.linalg.norm(ah @ bh.T / (float(sa) * float(sb)) - ref) / np.linalg.norm(ref) > 1e-4
+
+
 def test_potrf_h3_launch_plan_keeps_every_spin_wait_partner_resident():
     """The Cholesky's CTAs spin on each other inside a launch (row owners on CTA 0's epochs, CTA 0 on the helpers), so a
     launch must fit the device at one CTA per SM; the look-ahead GEMM of the next panel may only take what is left.

@@ -1,11 +1,13 @@
 #!/usr/bin/env python
-"""bench.py - VI iterations/s of the B200-native GSM hot path (BASELINE.json metric) + roofline + CPU baseline.
+"""bench.py - VI iterations/s of the B200-native GSM and BaM hot paths (BASELINE.json metric) + parity + roofline + CPU baseline.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--algo gsm|bam] [--D 4096] [--B 4096]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--D 4096] [--B 4096]
 
 A "step" is one VI iteration (gsmvi/gsm.py:107-129: sample -> score -> update -> PD check -> accept/revert) on the
-BASELINE headline configuration: dense-Gaussian target, D = 4096, batch 4096 (sharded over N GPUs), from (0, I).
-Prints ONE JSON line on rank 0.  See DESIGN.md section "Measurement" for every field.
+BASELINE headline configuration (configs[3]): D = 4096, batch 4096 (sharded over N GPUs), from (0, I).  The line's own
+value / e2e / roofline are the GSM leg on the dense-Gaussian target; the BaM leg (gsmvi/bam.py:178-212, ill-conditioned
+target, kappa stated) is the `bam` object of the same line with the same keys.  Prints ONE JSON line on rank 0.
+See DESIGN.md section "Measurement" for every field.
 """
 import argparse
 import json
@@ -18,13 +20,24 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "gsm-vi_b200"))
 
-METRIC = "VI iterations/sec (GSM, dense-Gaussian target, D=4096, B=4096)"  # BASELINE.json metric, GSM leg
+METRIC = "VI iterations/sec (GSM, dense-Gaussian target, D=4096, B=4096)"  # BASELINE.json metric, GSM leg (headline shape)
+METRIC_BAM = "VI iterations/sec (BaM, ill-conditioned Gaussian target, D=4096, B=4096)"  # BASELINE.json metric, BaM leg
 UNIT = "iterations/s"
+BAM_KAPPA = 1e2   # condition number of the BaM leg's target (kappa in {1e2, 1e3})
+BAM_REG0 = 100.0  # example_bam.py:58-59 schedule reg_i = 100 / (1 + i)
 
 
 def gsm_flops(B, D):
     """Algorithmic flops per GSM iteration, dense-counted: 9 B D^2 + D^3 / 3."""
     return 9.0 * B * D * D + D**3 / 3.0
+
+
+def config_for(D, B, world):
+    """`config` of both arms (ours and --impl reference time the same workload)."""
+    return {"workload": "GSM D=%d B=%d dense-Gaussian target seed 0, init (0, I) (BASELINE configs[3]); "
+                        "BaM leg: ill-conditioned target kappa=%g seed 0, reg_i = %g/(1+i)" % (D, B, BAM_KAPPA, BAM_REG0),
+            "global_batch": B, "per_gpu_batch": B // world, "parallelism": "batch-sharded x%d" % world,
+            "l2": "per-step working set %.0f MB >> 126 MB L2 (no flush needed)" % (11 * D * D * 4 / 1e6)}
 
 
 def measured_peaks():
@@ -34,6 +47,20 @@ def measured_peaks():
             return json.load(f), "measured"
     # fallback stated in /opt/skills/guides/B200_PROFILING.md
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def measured_traffic(kernel, D, B, world):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of this shape, if one exists
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep; never a constant in this file)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        tab = json.load(f)
+    for row in tab.get("captures", []):
+        if row.get("kernel") == kernel and row.get("D") == D and row.get("B") == B and row.get("world", 1) == world:
+            return row.get("dram_bytes_per_launch"), row.get("source")
+    return None, None
 
 
 class ClockSampler:
@@ -92,9 +119,30 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_oracle_step_fn(D, B, dtype_name="float64"):
+# ---------------------------------------------------------------------------------------------------- CPU side (oracle)
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must use every host core.  Called BEFORE numpy is
+    imported (the BLAS reads its thread count at load time) and enforced again through threadpoolctl afterwards."""
+    cores = os.cpu_count() or 1
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[k] = str(cores)
+    return cores
+
+
+def blas_threads(cores):
+    """Pin every BLAS / OpenMP pool numpy uses to `cores` threads; returns the thread count actually in force."""
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=cores)
+        n = [p.get("num_threads", 1) for p in threadpoolctl.threadpool_info() if p.get("user_api") == "blas"]
+        return max(n) if n else cores
+    except Exception:
+        return cores
+
+
+def cpu_gsm_step_fn(D, B, dtype_name="float64"):
     """One GSM iteration of the CPU oracle (GEMM restatement of gsmvi/gsm.py, Cholesky sampler + host Cholesky check)
-    on a row sample of B rows; returns a closure running one step on persistent state."""
+    on the full batch; returns a closure running one step on persistent state."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import gsmvi_oracle as orc
@@ -117,61 +165,92 @@ def cpu_oracle_step_fn(D, B, dtype_name="float64"):
     return step
 
 
+def cpu_bam_step_fn(D, B):
+    """One BaM iteration of the CPU oracle (bam.py:188-212: Cholesky sampler, score, symmetrised bam_update - an eigh of
+    a D x D matrix -, jitter, symmetrise, host Cholesky check) on the ill-conditioned target, full batch."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import gsmvi_oracle as orc
+    mean_t, cov_t = orc.illcond_gaussian_target(D, BAM_KAPPA, 0)
+    P = np.linalg.inv(cov_t)
+    c = P @ mean_t
+    state = {"mean": np.zeros(D), "cov": np.identity(D), "i": 0}
+    rng = np.random.RandomState(1)
+
+    def step():
+        Lc = np.linalg.cholesky(state["cov"])
+        X = state["mean"] + rng.standard_normal((B, D)) @ Lc.T
+        G = -(X @ P) + c
+        m_new, c_new = orc.bam_update(X, G, state["mean"], state["cov"], BAM_REG0 / (1 + state["i"]))
+        c_new = c_new + np.eye(D) * 1e-6
+        c_new = (c_new + c_new.T) / 2
+        if orc.check_goodness(c_new):
+            state["mean"], state["cov"] = m_new, c_new
+        state["i"] += 1
+
+    return step
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python (nothing to
-    compile into oracle/_ref), its JAX path is not installable here, and its literal per-sample loop needs B*D^2
-    intermediates (256 GiB at the headline shape), so the arm runs the oracle port (proven equal to gsm_numpy.py on
-    the golden vectors) on all host cores."""
+    """--impl reference: the reference's CPU implementation of the path, on every host core.  The reference is pure
+    Python (nothing to compile into oracle/_ref), its JAX path is not installable here, and its literal per-sample loop
+    needs B*D^2 intermediates (256 GiB at the headline shape), so the arm runs the oracle port (proven equal to
+    gsm_numpy.py on the golden vectors) at the FULL batch: the Cholesky terms do not shrink with a row sample, so none is
+    taken.  Under torchrun only rank 0 works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = use_all_host_threads()
+    import numpy as np  # noqa: F401  (after the thread-count environment is set)
+    threads = blas_threads(cores)
     D, B = args.D, args.B
-    cores = os.cpu_count()
-    # bound the sample: a full-size oracle iteration is O(10 s); shrink the batch rows per step if the run would
-    # exceed ~4 minutes, and report iterations/s as (rows processed / B) per second.
-    Bs = B
-    step = cpu_oracle_step_fn(D, Bs)
+    step = cpu_gsm_step_fn(D, B)
     t0 = time.perf_counter()
-    step()
+    step()  # first step (also warm-up 1)
     t1 = time.perf_counter() - t0
-    budget = 200.0
-    total = args.steps + args.warmup
-    while Bs > 64 and t1 * total > budget:
-        Bs //= 2
-        step = cpu_oracle_step_fn(D, Bs)
-        t0 = time.perf_counter()
-        step()
-        t1 = time.perf_counter() - t0
+    # every step is a full-size iteration; if the requested count would not end within a few minutes, fewer timed steps
+    # are run (each still complete) and the line says so
+    budget = 240.0
+    steps = max(1, min(args.steps, int((budget - t1 * max(args.warmup, 1)) / max(t1, 1e-3))))
     for _ in range(max(args.warmup - 1, 0)):
         step()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    value = args.steps * (Bs / B) / dt
-    sample = ("%d full oracle iterations (numpy fp64 GEMM restatement of gsm.py + Cholesky sampler + host Cholesky check)"
-              % args.steps) if Bs == B else (
-        "%d oracle iterations on a %d-row sample of the %d-row batch (D^3 Cholesky terms at full size); "
-        "value = steps*(%d/%d)/time" % (args.steps, Bs, B, Bs, B))
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "GSM D=%d B=%d dense-Gaussian target (configs[3])" % (D, B)},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    value = steps / dt
+    sample = ("%d full-size oracle iterations (numpy fp64 GEMM restatement of gsm.py:8-58 + Cholesky sampler + host "
+              "Cholesky check, full batch %d, %d BLAS threads)" % (steps, B, threads))
+    bam = None
+    if not args.no_bam:
+        bstep = cpu_bam_step_fn(D, B)
+        t0 = time.perf_counter()
+        bstep()
+        bdt = time.perf_counter() - t0
+        bam = {"metric": METRIC_BAM, "value": 1.0 / bdt, "unit": UNIT, "steps": 1, "ms_per_step": 1e3 * bdt,
+               "sample": "1 full-size oracle BaM iteration (sampler, score, bam_update with a D x D eigh, host Cholesky check)"}
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_for(D, B, max(args.gpus, 1)),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "host_cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "bam": bam}
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------- GPU side
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import gsmvi_oracle as orc
     from gsmvi_b200 import _lib as L
+    from gsmvi_b200 import gsm as gsm_mod
     from gsmvi_b200.gsm import GSM, GSMEngine
-    from gsmvi_b200.targets import DenseGaussianTarget
+    from gsmvi_b200.targets import DenseGaussianTarget, dense_gaussian_target, illcond_gaussian_target
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -183,7 +262,7 @@ def run_ours(args):
         group = dist.group.WORLD
     D, B = args.D, args.B
     npass = args.npass
-    mean_t, cov_t = orc.dense_gaussian_target(D, 0)  # synthetic target generation is setup, not the timed path
+    mean_t, cov_t = dense_gaussian_target(D, 0)  # synthetic target generation is set-up, not the timed path
     tgt = DenseGaussianTarget(mean_t, cov_t)
     eng = GSMEngine(D, B, tgt.lp_g, key=99, npass=npass, process_group=group)
 
@@ -191,6 +270,13 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     clk = ClockSampler(local).start()
     it = 0
@@ -209,20 +295,17 @@ def run_ours(args):
     barrier()
     clk.mark_end()
     clk.stop()
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
     value = args.steps / (ms * 1e-3)
     reverts = eng.n_reverts
+    clocks = clk.summary()
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM: gemm_h3_kernel, or gemm_tf32_kernel for --npass <= 3): the
     # four batch-sized launches of a step, each bracketed by CUDA events on the launching stream, averaged over nrep
     # repetitions on the engine's own (L2-cold: 738 MB working set) buffers.
     Bl = eng.B
     h3 = npass == 4
-    gemm_ms, gemm_flops = 0.0, 0.0
+    gemm_flops = 0.0
     per_call = [0.0] * 4
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     nrep = max(args.steps, 3)
@@ -238,172 +321,316 @@ def run_ours(args):
         gemm_flops += 9.0 * Bl * D * D  # B D^2 (triangular sampler) + 2 + 2 + 4 B D^2, dense-counted
     gemm_ms = sum(per_call)
     peaks, peak_src = measured_peaks()
-    pipe_peak = peaks["bf16_tflops_sustained"] if h3 else peaks["bf16_tflops_sustained"] / 2.0
+    # The four launches are timed one by one between synchronisations, i.e. in isolation: the denominator is the BURST
+    # figure of MEASURED_PEAKS.json (a kernel timed alone), not the sustained one - unless the clock samples of the timed
+    # region show the part power-capped or running below its maximum clock.
+    at_max = (clocks.get("sm_mhz") is not None and clocks.get("sm_max_mhz") and
+              clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"] and "sw_power_cap" not in clocks.get("reasons", []))
+    peak_key = "bf16_tflops" if (at_max or clocks.get("sm_mhz") is None) else "bf16_tflops_sustained"
+    pipe_peak = peaks[peak_key] if h3 else peaks[peak_key] / 2.0
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     executed = 3 * achieved * (7.0 / 9.0) if npass >= 2 else achieved * (7.0 / 9.0)
+    kname = "gemm_h3_kernel" if h3 else "gemm_tf32_kernel"
+    traffic, traffic_src = measured_traffic(kname, D, B, world)
     roofline = {"bound": "tensor",
                 "kernel": ("gemm_h3_kernel (scaled 3xFP16 split, kind::f16)" if h3 else "gemm_tf32_kernel<3xTF32>") +
                           ": sample, score, W=G*Sigma, E^T U + U^T D",
                 "achieved": achieved, "peak": pipe_peak, "unit": "TFLOP/s", "frac": achieved / pipe_peak,
-                "traffic": (389.4e6 if (h3 and D == 4096 and B == 4096 and world == 1) else None), "traffic_note":
-                "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the four launches in the ncu --set full "
-                "capture profiles/r01_ncu_gemm_h3_summary.txt (195 / 369 / 386 / 606 MB; algorithmic operand + result "
-                "bytes 201 / 201 / 201 / 302 MB)",
+                "traffic": traffic, "traffic_source": traffic_src,
                 "executed_tflops": executed, "executed_frac": executed / pipe_peak,
                 "launches_per_step": 4, "avg_launch_ms": gemm_ms / (4 * nrep),
                 "launch_ms": {"sample": per_call[0] / nrep, "score": per_call[1] / nrep, "w": per_call[2] / nrep,
                               "cov_update": per_call[3] / nrep},
-                "peak_note": "%s dense = %s bf16_tflops_sustained in MEASURED_PEAKS.json (%s); achieved counts ALGORITHMIC "
-                             "fp32 flops (9 B D^2 per step over 4 launches); a 3-pass split launch executes 3 tensor-core "
-                             "flops per algorithmic flop and skips the structurally-zero half of the triangular / "
-                             "symmetric products (executed = 3 * 7/9 of algorithmic), so frac <= 0.43 by construction; "
-                             "executed_frac is the pipe utilisation" % ((("kind::f16", "1x") if h3 else ("TF32", "1/2 of")) + (peak_src,))}
-
-    # ---- end to end through the public API with HOST buffers: GSM.fit(key, mean=host, cov=host, niter=K-1)
-    e2e = None
+                "peak_note": "%s dense = %s %s of MEASURED_PEAKS.json (%s; launches timed in isolation, clocks %s); achieved "
+                             "counts ALGORITHMIC fp32 flops (9 B D^2 per step over 4 launches); a 3-pass split launch "
+                             "executes 3 tensor-core flops per algorithmic flop and skips the structurally-zero half of "
+                             "the triangular / symmetric products (executed = 3 * 7/9 of algorithmic), so frac <= 0.43 by "
+                             "construction; executed_frac is the pipe utilisation"
+                             % ((("kind::f16", "1x") if h3 else ("TF32", "1/2 of")) + (peak_key, peak_src, clocks.get("sm_mhz")))}
     n_launches = eng.launches_per_step() * args.steps
     eng.close()
-    del eng, calls  # the fit below gets its workspaces from the caching allocator instead of fresh cudaMallocs
+    del eng, calls
+
+    # ---- parity of what was just timed (printed every run so BENCH / SCALE carry correctness, not only speed)
+    parity = None
+    try:
+        parity = gsm_parity_block(D, B, npass, tgt, world, rank, group)
+    except Exception as exc:
+        parity = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
+    # ---- end to end through the public API with HOST buffers: GSM.fit(key, mean=host, cov=host, niter=K-1)
     mean_h = torch.zeros(D).pin_memory()
     cov_h = torch.eye(D).pin_memory()
     m_host, c_host = torch.empty(D).pin_memory(), torch.empty(D, D).pin_memory()
     g = GSM(D, tgt.lp, tgt.lp_g)
     state_bytes = (D * D + D) * 4.0
-    if world == 1:
-        # (a) host-fed draws, as the reference works (it samples on the host every iteration, gsmvi/gsm.py:117-119): each
-        #     step's B x D standard-normal draws come from pinned host memory (H2D inside the timed region, streamed one
-        #     iteration ahead on a copy stream), each step's accept flag goes back (D2H), and (mean, cov) cross at both ends
-        ke = max(4, min(args.steps, 32))  # 32 x 64 MiB of pinned draws at the headline shape
-        tape = torch.empty(ke, B, D, dtype=torch.float32).pin_memory()
-        tape.normal_(generator=torch.Generator().manual_seed(1))
-        g.fit(99, mean=mean_h, cov=cov_h, batch_size=B, niter=2, verbose=False, npass=npass, z_tape=tape)  # untimed warm-up
-        torch.cuda.synchronize()
+
+    def timed_fit(niter, tape):
+        """One call of the public API on every rank; wall clock around it (host buffers in, host buffers out), max over
+        ranks, bracketed by barriers."""
+        barrier()
         t0 = time.perf_counter()
-        m_fit, c_fit = g.fit(99, mean=mean_h, cov=cov_h, batch_size=B, niter=ke - 1, verbose=False, npass=npass, z_tape=tape)
-        m_host.copy_(m_fit, non_blocking=True)
-        c_host.copy_(c_fit, non_blocking=True)
-        torch.cuda.synchronize()
-        dt_host = time.perf_counter() - t0
-        del tape
-        # (b) the product's own sampler (device Philox): nothing but the key, (mean, cov) and the flags cross the bus
-        g.fit(99, mean=mean_h, cov=cov_h, batch_size=B, niter=2, verbose=False, npass=npass)  # untimed warm-up of the API path
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        m_fit, c_fit = g.fit(99, mean=mean_h, cov=cov_h, batch_size=B, niter=args.steps - 1, verbose=False, npass=npass)
+        m_fit, c_fit = g.fit(99, mean=mean_h, cov=cov_h, batch_size=B, niter=niter, verbose=False, npass=npass,
+                             z_tape=tape, process_group=group)
         m_host.copy_(m_fit, non_blocking=True)  # D2H into pinned host memory
         c_host.copy_(c_fit, non_blocking=True)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        e2e = {"value": ke / dt_host, "unit": UNIT, "steps": ke,
-               "h2d_bytes_per_step": B * D * 4.0 + state_bytes / ke, "d2h_bytes_per_step": 4 + state_bytes / ke,
-               "note": "GSM.fit(key, mean=pinned host, cov=pinned host, niter=steps-1, z_tape=pinned host draws): every "
-                       "iteration's B x D draws are copied host->device inside the timed region (a copy stream runs one "
-                       "iteration ahead of the compute stream), every iteration's 4-byte accept flag is read back, and "
-                       "the timed region also holds workspace set-up, H2D of (mean, cov), the initial Cholesky and the "
-                       "final D2H of (mean, cov) (amortised over the steps in the byte counts)",
-               "device_rng": {"value": args.steps / dt, "unit": UNIT, "steps": args.steps,
-                              "h2d_bytes_per_step": state_bytes / args.steps, "d2h_bytes_per_step": 4 + state_bytes / args.steps,
-                              "note": "same call with the library's own Philox sampler (the default): only (mean, cov) and the "
-                                      "accept flags cross the bus"}}
-    else:
-        # the same two calls on every rank (batch-sharded fit): each rank feeds ITS B / world draws per step from its own
-        # pinned host tape and reads its accept flag back; time = max over ranks of the wall clock around the call,
-        # bracketed by barriers; bytes are whole-job (all ranks)
-        def timed_fit(niter, tape):
-            torch.cuda.synchronize()
-            dist.barrier()
-            t0 = time.perf_counter()
-            m_fit, c_fit = g.fit(99, mean=mean_h, cov=cov_h, batch_size=B, niter=niter, verbose=False, npass=npass,
-                                 z_tape=tape, process_group=group)
-            m_host.copy_(m_fit, non_blocking=True)
-            c_host.copy_(c_fit, non_blocking=True)
-            torch.cuda.synchronize()
-            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        ke = max(4, min(args.steps, 32))
-        tape = torch.empty(ke, Bl, D, dtype=torch.float32).pin_memory()
-        tape.normal_(generator=torch.Generator().manual_seed(1 + rank))
-        timed_fit(2, tape)  # untimed warm-up
-        dt_host = timed_fit(ke - 1, tape)
-        del tape
-        timed_fit(2, None)
-        dt = timed_fit(args.steps - 1, None)
-        e2e = {"value": ke / dt_host, "unit": UNIT, "steps": ke,
-               "h2d_bytes_per_step": world * (Bl * D * 4.0 + state_bytes / ke),
-               "d2h_bytes_per_step": world * (4 + state_bytes / ke),
-               "note": "GSM.fit(..., process_group=WORLD, z_tape=this rank's pinned host draws) on every rank: each step's "
-                       "B/world x D draws per rank are copied host->device inside the timed region, every rank reads its "
-                       "accept flag back; the timed region also holds workspace + NVLink exchange-buffer set-up (IPC handle "
-                       "exchange), H2D of (mean, cov), the initial Cholesky and the final D2H of (mean, cov); max over ranks",
-               "device_rng": {"value": args.steps / dt, "unit": UNIT, "steps": args.steps,
-                              "h2d_bytes_per_step": world * state_bytes / args.steps,
-                              "d2h_bytes_per_step": world * (4 + state_bytes / args.steps),
-                              "note": "same call with the library's own Philox sampler (the default)"}}
+        return max_over_ranks(time.perf_counter() - t0)
 
-    # ---- BaM leg of the BASELINE metric (same shape, example_bam.py schedule reg_i = 100/(1+i)); reported beside GSM
+    # (a) host-fed draws, as the reference works (it samples on the host every iteration, gsmvi/gsm.py:117-119): each
+    #     step's draws come from pinned host memory (H2D inside the timed region, streamed one iteration ahead on a copy
+    #     stream); (mean, cov) cross at both ends.  On a sharded fit every rank feeds ITS B / world rows.
+    ke = max(4, min(args.steps, 32))  # up to 32 x 64 MiB of pinned draws at the headline shape
+    tape = torch.empty(ke, Bl, D, dtype=torch.float32).pin_memory()
+    tape.normal_(generator=torch.Generator().manual_seed(1 + rank))
+    timed_fit(2, tape)  # untimed warm-up of the API path (first call: engine set-up, cached afterwards)
+    dt_host = timed_fit(ke - 1, tape)
+    del tape
+    # (b) the product's own sampler (device Philox): nothing but the key and (mean, cov) cross the bus
+    timed_fit(2, None)
+    dt = timed_fit(args.steps - 1, None)
+    e2e = {"value": ke / dt_host, "unit": UNIT, "steps": ke,
+           "h2d_bytes_per_step": world * (Bl * D * 4.0 + state_bytes / ke), "d2h_bytes_per_step": world * state_bytes / ke,
+           "note": "GSM.fit(key, mean=pinned host, cov=pinned host, niter=steps-1, z_tape=pinned host draws%s): every "
+                   "iteration's draws are copied host->device inside the timed region (a copy stream runs one iteration "
+                   "ahead of the compute stream); the accept / revert is decided on the device (no per-step read-back); the "
+                   "timed region also holds H2D of (mean, cov), the initial Cholesky, and the final D2H of (mean, cov) + the "
+                   "revert counter (amortised over the steps in the byte counts); the engine (workspaces%s) is the one a "
+                   "previous fit of this shape left in GSM.fit's cache; wall clock, max over ranks"
+                   % ((", process_group=WORLD; this rank's rows" if world > 1 else ""),
+                      (", NVLink exchange buffers" if world > 1 else "")),
+           "device_rng": {"value": args.steps / dt, "unit": UNIT, "steps": args.steps,
+                          "h2d_bytes_per_step": world * state_bytes / args.steps,
+                          "d2h_bytes_per_step": world * state_bytes / args.steps,
+                          "note": "same call with the library's own Philox sampler (the default): only (mean, cov) cross the bus"}}
+    gsm_mod.release_engines()
+
+    # ---- BaM leg of the BASELINE metric: same shape, ill-conditioned target, example_bam.py schedule reg_i = 100/(1+i)
     bam = None
     if not args.no_bam:
         try:
-            from gsmvi_b200.bam import BaMEngine
-            torch.cuda.empty_cache()
-            beng = BaMEngine(D, B, tgt.lp_g, key=99, npass=min(npass, 3), process_group=group)
-            nb = max(2, min(args.steps, 4))
-            beng.step(0, 100.0)
-            barrier()
-            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            b0.record()
-            for i in range(1, nb + 1):
-                beng.step(i, 100.0 / (1 + i))
-            b1.record()
-            barrier()
-            bms = b0.elapsed_time(b1)
-            if world > 1:
-                t = torch.tensor([bms], device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                bms = float(t.item())
-            k = float(np.mean(beng.ns_iters[1:]))
-            K = Bl + 1
-            solve_flops = (6.0 * k + 7.0) * D**3  # (6k+7) D^3 with k Newton-Schulz iterations
-            bam = {"metric": "VI iterations/sec (BaM, dense-Gaussian target, D=%d, B=%d)" % (D, B), "value": nb / (bms * 1e-3),
-                   "unit": UNIT, "steps": nb, "ms_per_step": bms / nb, "ns_iters_mean": k, "reverts": beng.n_reverts,
-                   "solve_algorithmic_tflops_fp64": solve_flops * nb / (bms * 1e-3) / 1e12,
-                   "note": "fp32 tensor-core sampling/score + fp64 statistics and QME solve (dgemm_pipe_kernel: FP64 tensor-core "
-                           "path, 30.8 TFLOP/s at 4096^3; cuBLAS DGEMM on this part measures 35.4)"}
-            del beng
-            torch.cuda.empty_cache()
+            bam = bam_leg(args, D, B, Bl, npass, world, rank, group, barrier, max_over_ranks, peaks)
         except Exception as exc:  # the BaM leg must never take the GSM line down with it
             bam = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        step = cpu_oracle_step_fn(D, B)
+        threads = blas_threads(os.cpu_count() or 1)
+        step = cpu_gsm_step_fn(D, B)
         step()
         n = 0
         t0 = time.perf_counter()
         while n < 4 and (time.perf_counter() - t0) < 15.0:
             step()
             n += 1
-        dt = time.perf_counter() - t0
-        cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+        dtc = time.perf_counter() - t0
+        cpu_baseline = {"value": n / dtc, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": "%d full-size oracle iterations after one warm-up (numpy fp64 GEMM restatement of "
                                   "gsm.py + Cholesky sampler + host Cholesky check, all host cores)" % n}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": {4: "f16x3 (scaled fp16 hi/lo split, fp32 accumulate)", 3: "tf32x3", 2: "tf32x3"}.get(npass, "tf32"), "data": "synthetic",
-                "config": {"workload": "GSM D=%d B=%d dense-Gaussian target seed 0, init (0, I), Philox z (configs[3])" % (D, B),
-                           "global_batch": B, "per_gpu_batch": Bl, "parallelism": "batch-sharded x%d" % world,
-                           "l2": "per-step working set %.0f MB >> 126 MB L2 (no flush needed)" % (11 * D * D * 4 / 1e6)},
+                "vs_baseline": None,
+                "dtype": {4: "f16x3 (scaled fp16 hi/lo split, fp32 accumulate)", 3: "tf32x3", 2: "tf32x3"}.get(npass, "tf32"),
+                "data": "synthetic", "config": config_for(D, B, world),
                 "score_evals_per_s": value * B,
                 "algorithmic_tflops": gsm_flops(B, D) * value / 1e12,
-                "reverts": reverts,
-                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": n_launches,
+                "reverts": reverts, "parity": parity,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": n_launches,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "bam": bam}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def gsm_parity_block(D, B, npass, tgt, world, rank, group):
+    """Correctness of the timed configuration, measured in the same process: N = 1: two iterations of GSM.fit at the timed
+    shape against the fp64 oracle loop on the same draw tape (relF(Sigma), rel(mu); bar 1e-4, BASELINE north_star).
+    N > 1: the sharded fit against the unsharded fit of the same tape on this rank's own GPU, plus bit-identity of the
+    replicated state across ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import gsmvi_oracle as orc
+    from gsmvi_b200.gsm import GSM
+    niter = 1
+    Zt = torch.empty(niter + 1, B, D, dtype=torch.float32)
+    Zt.normal_(generator=torch.Generator().manual_seed(7))
+    g = GSM(D, tgt.lp, tgt.lp_g)
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    if world == 1:
+        m_d, c_d = g.fit(99, niter=niter, batch_size=B, z_tape=Zt, verbose=False, npass=npass)
+        P_dev = tgt.P.cpu().double().numpy()  # the oracle scores with the same fp32-rounded (P, c) the device holds
+        c_dev = tgt.c[:D].cpu().double().numpy()
+        o = orc.GSM(D, None, lambda x: -(x @ P_dev.T) + c_dev)
+        m_o, c_o = o.fit(99, niter=niter, batch_size=B, sampler=orc.CholeskyTapeSampler(Zt.numpy().astype(np.float64)))
+        e_c = rel(c_d.cpu(), torch.as_tensor(c_o))
+        e_m = rel(m_d.cpu(), torch.as_tensor(m_o))
+        return {"against": "fp64 oracle loop (oracle/gsmvi_oracle.py GSM.fit), same z-tape, %d iterations at the timed shape"
+                           % (niter + 1), "relF_cov": e_c, "rel_mean": e_m, "reverts": g.n_reverts,
+                "reverts_oracle": o.n_reverts, "tolerance": 1e-4, "ok": bool(e_c < 1e-4 and e_m < 1e-4 and
+                                                                          g.n_reverts == o.n_reverts)}
+    m_s, c_s = g.fit(99, niter=niter, batch_size=B, z_tape=Zt, verbose=False, npass=npass, process_group=group)
+    m_1, c_1 = g.fit(99, niter=niter, batch_size=B, z_tape=Zt, verbose=False, npass=npass)
+    e_c, e_m = rel(c_s, c_1), rel(m_s, m_1)
+    ref_c, ref_m = c_s.clone(), m_s.clone()
+    dist.broadcast(ref_c, 0)
+    dist.broadcast(ref_m, 0)
+    same = torch.tensor([1.0 if (torch.equal(ref_c, c_s) and torch.equal(ref_m, m_s)) else 0.0], device="cuda")
+    errs = torch.tensor([e_c, e_m], dtype=torch.float64, device="cuda")
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    return {"against": "unsharded GSM.fit of the same z-tape on each rank's own GPU, %d iterations at the timed shape; max "
+                       "over ranks" % (niter + 1), "relF_cov": float(errs[0]), "rel_mean": float(errs[1]),
+            "replicas_bit_identical": bool(same.item() == 1.0), "reverts": g.n_reverts, "tolerance": 2e-5,
+            "ok": bool(float(errs[0]) < 2e-5 and float(errs[1]) < 2e-5 and same.item() == 1.0)}
+
+
+def bam_leg(args, D, B, Bl, npass, world, rank, group, barrier, max_over_ranks, peaks):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import gsmvi_oracle as orc
+    from gsmvi_b200 import _lib as L
+    from gsmvi_b200.bam import BaM, BaMEngine, Regularizers
+    from gsmvi_b200.targets import DenseGaussianTarget, illcond_gaussian_target
+    torch.cuda.empty_cache()
+    mean_t, cov_t = illcond_gaussian_target(D, BAM_KAPPA, 0)
+    tgt = DenseGaussianTarget(mean_t, cov_t)
+    bnp = min(npass, 3)
+    beng = BaMEngine(D, B, tgt.lp_g, key=99, npass=bnp, process_group=group)
+    nb = max(2, min(args.steps, 6))
+    beng.step(0, BAM_REG0)  # warm-up iteration (the schedule's first, largest regulariser)
+    barrier()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0, s1 = [], []
+    b0.record()
+    for i in range(1, nb + 1):
+        beng.draw_and_score(i)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        beng.update(BAM_REG0 / (1 + i))
+        b.record()
+        s0.append(a)
+        s1.append(b)
+        beng.accept_or_revert()
+    b1.record()
+    barrier()
+    bms = max_over_ranks(b0.elapsed_time(b1))
+    upd_ms = sum(x.elapsed_time(y) for x, y in zip(s0, s1))
+    k = float(np.mean(beng.ns_iters[1:]))
+    solve_flops = (6.0 * k + 7.0) * D**3  # SURVEY section 8d: (6k+7) D^3 with k Newton-Schulz iterations
+    # roofline of the dominant kernel: the fp64 GEMM of the Newton-Schulz products (dgemm_pipe_kernel), one D^3 product
+    # timed in isolation with CUDA events, against a DGEMM peak measured in this run (torch.matmul fp64 = cuBLAS, a
+    # measurement aid only: nothing on the product path links or calls it)
+    A = torch.randn(D, D, dtype=torch.float64, device="cuda")
+    Bm = torch.randn(D, D, dtype=torch.float64, device="cuda")
+    C = torch.empty(D, D, dtype=torch.float64, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def best_ms(fn, n=5):
+        fn()
+        best = 1e30
+        for _ in range(n):
+            torch.cuda.synchronize()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    ours_ms = best_ms(lambda: L.dgemm(A, Bm, C, D, D, D, b_mn=True))
+    cublas_ms = best_ms(lambda: torch.matmul(A, Bm, out=C))
+    ours_tf, peak_tf = 2.0 * D**3 / (ours_ms * 1e-3) / 1e12, 2.0 * D**3 / (cublas_ms * 1e-3) / 1e12
+    del A, Bm, C
+    roofline = {"bound": "fp64 pipe", "kernel": "dgemm_pipe_kernel (mma.sync m16n8k16 f64; Newton-Schulz products of the QME solve)",
+                "achieved": ours_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ours_tf / peak_tf, "traffic": None,
+                "launch_ms": ours_ms,
+                "peak_note": "peak = cuBLAS DGEMM %d^3 measured in this run through torch.matmul (best of 5, CUDA events): "
+                             "tcgen05 has no f64 kind and MEASURED_PEAKS.json carries no fp64 figure" % D,
+                "solve_algorithmic_tflops": solve_flops * nb / (upd_ms * 1e-3) / 1e12,
+                "solve_note": "statistics + QME solve of the timed iterations: (6k+7) D^3 flops with k = %.1f Newton-Schulz "
+                              "iterations (SURVEY.md section 8d), over their CUDA-event time" % k}
+    value = nb / (bms * 1e-3)
+    out = {"metric": METRIC_BAM, "value": value, "unit": UNIT, "n_gpus": world, "steps": nb, "ms_per_step": bms / nb,
+           "update_ms_per_step": upd_ms / nb, "higher_is_better": True, "scaling": "strong",
+           "dtype": "f64 (statistics + solve; sampling / score on the 3xTF32 tensor-core path)",
+           "target": {"family": "ill-conditioned Gaussian", "kappa": BAM_KAPPA, "seed": 0, "reg": "%g/(1+i)" % BAM_REG0},
+           "ns_iters_mean": k, "reverts": beng.n_reverts, "score_evals_per_s": value * B, "roofline": roofline}
+    del beng
+    torch.cuda.empty_cache()
+
+    # parity at the timed shape: N = 1 one full-size update against the oracle's bam_update (a D x D eigh on the host);
+    # N > 1 the sharded fit against the unsharded one on the same tape + replica bit-identity
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    Zt = torch.empty(2, B, D, dtype=torch.float32)
+    Zt.normal_(generator=torch.Generator().manual_seed(11))
+    reg = lambda: Regularizers().custom(lambda i: BAM_REG0 / i)  # counter starts at 1: 100, 50, ...
+    bm = BaM(D, tgt.lp, tgt.lp_g)
+    if world == 1:
+        if not args.no_cpu_baseline:
+            m_d, c_d = bm.fit(99, reg(), niter=0, batch_size=B, z_tape=Zt, verbose=False, npass=bnp)
+            P_dev = tgt.P.cpu().double().numpy()
+            c_dev = tgt.c[:D].cpu().double().numpy()
+            o = orc.BaM(D, None, lambda x: -(x @ P_dev.T) + c_dev)
+            t0 = time.perf_counter()
+            m_o, c_o = o.fit(99, orc.Regularizers().custom(lambda i: BAM_REG0 / i), niter=0, batch_size=B,
+                             sampler=orc.CholeskyTapeSampler(Zt.numpy().astype(np.float64)), update=orc.bam_update)
+            t_oracle = time.perf_counter() - t0
+            e_c, e_m = rel(c_d.cpu(), torch.as_tensor(c_o)), rel(m_d.cpu(), torch.as_tensor(m_o))
+            out["parity"] = {"against": "fp64 oracle (oracle/gsmvi_oracle.py BaM.fit with bam_update), same z-tape, 1 iteration "
+                                        "at the timed shape, reg = %g" % BAM_REG0, "relF_cov": e_c, "rel_mean": e_m,
+                             "tolerance": 1e-4, "ok": bool(e_c < 1e-4 and e_m < 1e-4)}
+            out["cpu_baseline"] = {"value": 1.0 / t_oracle, "unit": UNIT, "cores": blas_threads(os.cpu_count() or 1),
+                                   "kind": "port", "sample": "1 full-size oracle BaM iteration (Cholesky sampler, score, "
+                                   "bam_update with a %d x %d eigh, jitter, host Cholesky check), all host cores" % (D, D)}
+    else:
+        m_s, c_s = bm.fit(99, reg(), niter=1, batch_size=B, z_tape=Zt, verbose=False, npass=bnp, process_group=group)
+        m_1, c_1 = bm.fit(99, reg(), niter=1, batch_size=B, z_tape=Zt, verbose=False, npass=bnp)
+        ref_c = c_s.clone()
+        dist.broadcast(ref_c, 0)
+        same = torch.tensor([1.0 if torch.equal(ref_c, c_s) else 0.0], device="cuda")
+        errs = torch.tensor([rel(c_s, c_1), rel(m_s, m_1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+        out["parity"] = {"against": "unsharded BaM.fit of the same z-tape on each rank's own GPU, 2 iterations; max over ranks",
+                         "relF_cov": float(errs[0]), "rel_mean": float(errs[1]),
+                         "replicas_bit_identical": bool(same.item() == 1.0), "tolerance": 2e-5,
+                         "ok": bool(float(errs[0]) < 2e-5 and float(errs[1]) < 2e-5 and same.item() == 1.0)}
+
+    # end to end through BaM.fit with HOST buffers (pinned draws in, (mean, cov) out), wall clock, max over ranks
+    ke = max(3, min(args.steps, 5))
+    tape = torch.empty(ke, Bl, D, dtype=torch.float32).pin_memory()
+    tape.normal_(generator=torch.Generator().manual_seed(21 + rank))
+    if world > 1:  # BaMEngine slices a global tape by rank: give every rank a global-shaped view of its own rows
+        full = torch.empty(ke, B, D, dtype=torch.float32).pin_memory()
+        full[:, rank * Bl:(rank + 1) * Bl] = tape
+        tape = full
+    mean_h, cov_h = torch.zeros(D).pin_memory(), torch.eye(D).pin_memory()
+    m_host, c_host = torch.empty(D).pin_memory(), torch.empty(D, D).pin_memory()
+
+    def timed(niter):
+        barrier()
+        t0 = time.perf_counter()
+        m_fit, c_fit = bm.fit(99, reg(), mean=mean_h, cov=cov_h, niter=niter, batch_size=B, z_tape=tape, verbose=False,
+                              npass=bnp, process_group=group)
+        m_host.copy_(m_fit, non_blocking=True)
+        c_host.copy_(c_fit, non_blocking=True)
+        torch.cuda.synchronize()
+        return max_over_ranks(time.perf_counter() - t0)
+
+    timed(0)
+    dt = timed(ke - 1)
+    state_bytes = (D * D + D) * 4.0
+    out["e2e"] = {"value": ke / dt, "unit": UNIT, "steps": ke,
+                  "h2d_bytes_per_step": world * (Bl * D * 4.0 + state_bytes / ke),
+                  "d2h_bytes_per_step": world * (8 + state_bytes / ke),
+                  "note": "BaM.fit(key, regf, mean=pinned host, cov=pinned host, niter=steps-1, z_tape=pinned host draws): each "
+                          "iteration's draws cross host->device inside the timed region, the two PD flags are read back per "
+                          "iteration, (mean, cov) cross at both ends, workspaces are allocated inside the call"}
+    return out
 
 
 def main():
@@ -418,6 +645,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bam", action="store_true")
     args = ap.parse_args()
+    global METRIC, METRIC_BAM
+    METRIC = METRIC.replace("D=4096, B=4096", "D=%d, B=%d" % (args.D, args.B))
+    METRIC_BAM = METRIC_BAM.replace("D=4096, B=4096", "D=%d, B=%d" % (args.D, args.B))
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
         run_reference(args)

@@ -9,6 +9,7 @@
 //   Q = [sqrt(reg/B) (G-gbar)^T, sqrt(reg/(1+reg)) gbar] of U instead of a truncated SVD (Q Q^T = U, S is invariant).
 // Samples and scores come from the fp32 tensor-core path; the statistics and everything D x D / K x K here are fp64
 // (dgemm.cu): V = S0 + reg*C amplifies C's rounding by reg, and the solve mixes scales of 1 and ~1e9.
+#include "dev_once.cuh"
 #include "bam_solve.cuh"
 #include "oz_gemm.cuh"
 
@@ -120,6 +121,8 @@ __global__ void scale_diag64_kernel(double* __restrict__ A, long long lda, int n
   const long long i = blockIdx.y;
   if (j < n) A[i * lda + j] = scale * A[i * lda + j] + ((i == j) ? diag_add : 0.0);
 }
+
+__global__ void or_flag_kernel(int* flag, int bits) { atomicOr(flag, bits); }
 
 __global__ void set_identity64_kernel(double* __restrict__ A, long long lda, int n) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -274,10 +277,10 @@ static int dgemm_big(cudaStream_t st, int M, int N, int K, const double* A, long
 // of every 64x64 diagonal block ([ceil(n/64)] x 64 x 64).  flag |= 1 on a bad pivot.
 static int potrf64_inplace(cudaStream_t st, double* A, long long lda, int n, double* dinv, int* flag) {
   const int smem = 2 * NB64 * L64S * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (!attr_set.get()) {
     GSMVI_CUDA(cudaFuncSetAttribute(potrf64_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_set.set();
   }
   tril64_kernel<<<grid2(n, n), 256, 0, st>>>(A, lda, n);
   for (int j0 = 0, blk = 0; j0 < n; j0 += NB64, ++blk) {
@@ -357,7 +360,8 @@ static void dbg_stage(cudaStream_t st, const char* name, const double* A, long l
 // at kappa ~ 1e11 (measured).  Needs 4 scratch n x n buffers.  Synchronises the stream once per iteration
 // to read the residual ||I - Z Y||_F.
 static int ns_sqrt64(cudaStream_t st, double* Y, long long ld, int n, double* Z, double* P, double* Y2, double* Z2,
-                     double* scal_dev, int max_iter, double tol, double lam_min, int* iters_out, const OzCtx& oz = OzCtx()) {
+                     double* scal_dev, int max_iter, double tol, double lam_min, int* iters_out, int* flag,
+                     const OzCtx& oz = OzCtx()) {
   double h[2];
   GSMVI_CUDA(cudaMemsetAsync(scal_dev, 0, 2 * sizeof(double), st));
   frob_inf64_kernel<<<n, 256, 0, st>>>(Y, ld, n, 0.0, scal_dev);
@@ -366,14 +370,16 @@ static int ns_sqrt64(cudaStream_t st, double* Y, long long ld, int n, double* Z,
   const double c = h[1];
   if (!(c > 0.0) || isinf(c) || isnan(c)) {
     *iters_out = -1;
-    return GSMVI_OK;  // caller sees NaNs downstream; the PD check rejects the update
+    or_flag_kernel<<<1, 1, 0, st>>>(flag, 2);  // not a matrix a square root exists for: the update must be rejected
+    return GSMVI_OK;
   }
   scale_diag64_kernel<<<grid2(n, n), 256, 0, st>>>(Y, ld, n, 1.0 / c, 0.0);
   set_identity64_kernel<<<grid2(n, n), 256, 0, st>>>(Z, ld, n);
   double lo = sqrt(fmin(fmax(lam_min / c, 1e-300), 1.0));
   int it = 0;
   bool last_round = false;
-  double prev_res = 1e300;
+  double prev_res = 1e300, exit_res = 1e300;
+  bool stagnated = false;
   for (; it < max_iter; ++it) {
     double a = 1.5, b = -0.5;
     if (lo < 0.9 && !last_round) {
@@ -404,18 +410,23 @@ static int ns_sqrt64(cudaStream_t st, double* Y, long long ld, int n, double* Z,
     }
     double* t = Y; Y = Y2; Y2 = t;
     t = Z; Z = Z2; Z2 = t;
-    if (last_round) { ++it; break; }
+    if (last_round) { ++it; if (!stagnated) exit_res = prev_res * prev_res; break; }  // one more quadratic step
     GSMVI_CUDA(cudaMemcpyAsync(h, scal_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     GSMVI_CUDA(cudaStreamSynchronize(st));
     const double res = sqrt(h[0]) / fabs(b);
     if (dbg_on()) fprintf(stderr, "[gsmvi debug]   NS it=%d a=%.4f b=%.4f res=%.6e\n", it, a, b, res);
+    exit_res = res;
     if (isnan(res) || isinf(res)) { ++it; break; }
     if (res < tol) { ++it; break; }            // this update already used P with ||I - ZY|| < tol: converged
     if (res < 1e-4 && a == 1.5) last_round = true;   // quadratic convergence: one more plain update reaches ~1e-9
-    if (res < 1e-2 && res > 0.5 * prev_res) last_round = true;  // stagnating at the rounding floor
+    if (res < 1e-2 && res > 0.5 * prev_res) last_round = stagnated = true;  // stagnating at the rounding floor
     prev_res = res;
   }
   *iters_out = it;
+  // Out of iterations, or a non-finite residual: Y is not M^(1/2), and S = 2 T T^T built from it would still pass the PD
+  // check (it is PSD by construction) - so the solve itself raises bit 1 of the flag and the update is rejected
+  // (the reference's sqrtm would have thrown, which BaM.fit's retry loop catches, bam.py:188-206).
+  if (!(exit_res < (stagnated ? 1e-4 : 1e-6))) or_flag_kernel<<<1, 1, 0, st>>>(flag, 2);
   // result lives in the current Y; if that is the caller's Y2 buffer, copy back (odd number of swaps)
   if (it % 2 == 1) GSMVI_CUDA(cudaMemcpy2DAsync(Y2, ld * sizeof(double), Y, ld * sizeof(double), n * sizeof(double), n,
                                                 cudaMemcpyDeviceToDevice, st));
@@ -530,7 +541,7 @@ int bam_solve_full(cudaStream_t st, const double* stats_ws, int B, int D, int Bt
     return GSMVI_OK;
   }
   int iters = 0;
-  GSMVI_TRY(ns_sqrt64(st, b3, ld, D, b2, b4, b5, b0, scal, max_ns, 1e-11, 1.0, &iters, oz));  // b3 = N = M^{1/2}
+  GSMVI_TRY(ns_sqrt64(st, b3, ld, D, b2, b4, b5, b0, scal, max_ns, 1e-11, 1.0, &iters, flag, oz));  // b3 = N = M^{1/2}
   if (ns_iters_host) *ns_iters_host = iters;
   dbg_stage(st, "N=sqrt(M)", b3, ld, D, scal, flag);
   scale_diag64_kernel<<<grid2(D, D), 256, 0, st>>>(b3, ld, D, 1.0, 1.0);          // I + N
@@ -585,7 +596,7 @@ int bam_solve_lowrank(cudaStream_t st, const double* stats_ws, int B, int D, int
   h.mirror = true;
   GSMVI_TRY(launch_dgemm(st, K, K, D, A, ldk, true, Q, ldk, true, k0, ldk, h));    // H = A^T Q + I/4
   int iters = 0;
-  GSMVI_TRY(ns_sqrt64(st, k0, ldk, K, k1, k2, k3, k4, scal, max_ns, 1e-11, 0.25, &iters));
+  GSMVI_TRY(ns_sqrt64(st, k0, ldk, K, k1, k2, k3, k4, scal, max_ns, 1e-11, 0.25, &iters, flag));
   if (ns_iters_host) *ns_iters_host = iters;
   scale_diag64_kernel<<<grid2(K, K), 256, 0, st>>>(k0, ldk, K, 1.0, 0.5);          // I/2 + H^{1/2}
   GSMVI_TRY(potrf64_inplace(st, k0, ldk, K, dinv, flag));                          // = R2 R2^T

@@ -6,6 +6,7 @@
 #include "dgemm.cuh"
 #include "gsm_ensemble.cuh"
 #include "gsm_kernels.cuh"
+#include "gsm_small64.cuh"
 #include "h3_gemm.cuh"
 #include "monitor.cuh"
 #include "oz_gemm.cuh"
@@ -257,6 +258,19 @@ int gsmvi_gauss_logq_reduce(const float* Z_or_X, long long ld, int N, int D, con
 int gsmvi_gsm_ensemble_fit(const float* P, const float* c, float* mu, float* Sigma, int F, int D, int B, int niter,
                            unsigned long long seed, const float* z_tape, int* reverts, int first_fit, void* stream) {
   return gsm_ensemble_fit(S(stream), P, c, mu, Sigma, F, D, B, niter, seed, z_tape, reverts, first_fit);
+}
+
+int gsmvi_gsm_commit(const int* bad_flag, const int* bad_flag2, int n, const void* const* src_host, void* const* dst_host,
+                     const long long* bytes_host, int* status, void* stream) {
+  return gsm_commit(S(stream), bad_flag, bad_flag2, n, src_host, dst_host, bytes_host, status);
+}
+
+long long gsmvi_gsm_small64_workspace_bytes(int B, int D) { return gsm_small64_workspace_bytes(B, D); }
+
+int gsmvi_gsm_small64(int mode, double* mu, double* Sigma, double* L, const float* z_tape, unsigned long long seed,
+                      unsigned long long iter0, double* X, const double* G, const double* P, const double* c, int B, int D,
+                      int iters, int* status, void* workspace, void* stream) {
+  return gsm_small64(S(stream), mode, mu, Sigma, L, z_tape, seed, iter0, X, G, P, c, B, D, iters, status, workspace);
 }
 
 }  // extern "C"

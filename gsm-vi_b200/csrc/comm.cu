@@ -21,6 +21,7 @@
 
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace gsmvi {
@@ -37,11 +38,14 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 __device__ __forceinline__ void red_release_sys(unsigned* p, unsigned v) {
   asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void spin_until(const unsigned* p, unsigned target, const char* what) {
+// Watchdog of the peer waits: a rank may legitimately be late by a long time (a slow host-side score callable, a first-call
+// JIT, a debugger), and a trap takes the CUDA context of every waiting rank down with it, so the limit is generous
+// (GSMVI_COMM_TIMEOUT_S seconds, default 300; 0 = wait forever) and exists only to turn a dead peer into an error.
+__device__ __forceinline__ void spin_until(const unsigned* p, unsigned target, const char* what, long long timeout_cycles) {
   const long long t0 = clock64();
   while (static_cast<int>(ld_acquire_sys(p) - target) < 0) {
     __nanosleep(100);
-    if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer never arrived
+    if (timeout_cycles > 0 && clock64() - t0 > timeout_cycles) {
       printf("gsmvi: comm watchdog (%s, block %d, have %u want %u)\n", what, blockIdx.x, ld_acquire_sys(p), target);
       __trap();
     }
@@ -55,6 +59,7 @@ struct ReduceArgs {
   unsigned step;
   const float* usum;  // this rank's sum_b u_b
   float inv_btotal;
+  long long timeout_cycles;
 };
 
 constexpr int RQ = 4;              // CTAs per owned tile
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(256) comm_reduce_kernel(const ReduceArgs a) {
   const int m0 = tm * TILE, n0 = tn * TILE;
   const bool diag = (tm == tn);
   if (tid == 0)
-    spin_until(reinterpret_cast<const unsigned*>(mine) + a.lay.cnt_off + li, static_cast<unsigned>(a.world) * (a.step + 1), "partial tiles");
+    spin_until(reinterpret_cast<const unsigned*>(mine) + a.lay.cnt_off + li, static_cast<unsigned>(a.world) * (a.step + 1), "partial tiles", a.timeout_cycles);
   __syncthreads();
   const float* stage = mine + a.lay.stage_off;
   const float* s0 = mine + a.lay.s_off[a.cur];
@@ -179,13 +184,14 @@ __global__ void __launch_bounds__(256) comm_mirror_kernel(float* __restrict__ S,
 }
 
 __global__ void __launch_bounds__(256) comm_finalize_kernel(float* const* base, gsmvi_comm_layout lay, int rank, int world, int D,
-                                                            unsigned step, const float* __restrict__ mu, float* __restrict__ mu_out) {
+                                                            unsigned step, const float* __restrict__ mu, float* __restrict__ mu_out,
+                                                            long long timeout_cycles) {
   const float* mine = base[rank];
   const unsigned* cnt = reinterpret_cast<const unsigned*>(mine) + lay.cnt_off;
   const int ntiles = lay.tiles_m * (lay.tiles_m + 1) / 2;
   if (threadIdx.x == 0) {
-    spin_until(cnt + lay.tpo, static_cast<unsigned>(ntiles) * RQ * (step + 1), "final tiles");
-    spin_until(cnt + lay.tpo + 1, static_cast<unsigned>(world) * (step + 1), "mean increments");
+    spin_until(cnt + lay.tpo, static_cast<unsigned>(ntiles) * RQ * (step + 1), "final tiles", timeout_cycles);
+    spin_until(cnt + lay.tpo + 1, static_cast<unsigned>(world) * (step + 1), "mean increments", timeout_cycles);
   }
   __syncthreads();
   for (int j = threadIdx.x; j < D; j += 256) {
@@ -196,6 +202,16 @@ __global__ void __launch_bounds__(256) comm_finalize_kernel(float* const* base, 
 }
 
 }  // namespace
+
+static long long comm_timeout_cycles() {
+  static long long v = -1;
+  if (v < 0) {
+    const char* e = getenv("GSMVI_COMM_TIMEOUT_S");
+    const double sec = e ? atof(e) : 300.0;
+    v = sec <= 0.0 ? 0 : static_cast<long long>(sec * 2.0e9);  // clock64 ticks at <= 1.965 GHz: at least `sec` seconds
+  }
+  return v;
+}
 
 long long comm_layout(int D, int world, gsmvi_comm_layout* lay) {
   if (D <= 0 || world <= 0 || !lay) return -1;
@@ -257,17 +273,16 @@ int comm_reduce_broadcast(cudaStream_t stream, float* const* base, float* own_ba
   ReduceArgs a;
   a.base = base; a.lay = lay; a.rank = rank; a.world = world; a.D = D; a.cur = cur; a.step = step;
   a.usum = usum; a.inv_btotal = inv_btotal;
+  a.timeout_cycles = comm_timeout_cycles();
   const int ntiles = lay.tiles_m * (lay.tiles_m + 1) / 2;
   const int mine = (ntiles - rank + world - 1) / world;  // tiles t = li * world + rank < ntiles
   constexpr int SMEM = TILE * (TILE + 1) * static_cast<int>(sizeof(float));
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per call: the attribute is per device, a process may drive more than one, and setting it is cheap
     cudaError_t e = cudaFuncSetAttribute(comm_mirror_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
   }
   comm_reduce_kernel<<<mine * RQ + 1, 256, 0, stream>>>(a);
-  comm_finalize_kernel<<<1, 256, 0, stream>>>(base, lay, rank, world, D, step, mu, mu_out);
+  comm_finalize_kernel<<<1, 256, 0, stream>>>(base, lay, rank, world, D, step, mu, mu_out, a.timeout_cycles);
   comm_mirror_kernel<<<ntiles, 256, SMEM, stream>>>(own_base + lay.s_off[1 - cur], lay.lds, D, lay.tiles_m);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);

@@ -10,6 +10,7 @@
 // 12 wavefronts per 64 DFMA (the first version, 8x4 tiles with 32-byte-strided reads, needed 0.85 per DFMA and ran the
 // FP64 pipe at 41%, profiles/r01_ncu_dgemm_summary.txt).
 // Operand conventions match tc_gemm.cuh: K-major operand = [rows, K] row-major, MN-major = [K, rows] row-major.
+#include "dev_once.cuh"
 #include "dgemm.cuh"
 
 #include <stdint.h>
@@ -529,14 +530,14 @@ int launch_dgemm(cudaStream_t stream, int M, int N, int K, const double* A, long
   }
   const bool aligned = ((lda | ldb) & 1) == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
   if (dgemm_variant() == 3 && big && aligned && K > 0) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (!attr_set.get()) {
       cudaError_t ae = cudaFuncSetAttribute(dgemm_pipe_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES);
       if (ae == cudaSuccess) ae = cudaFuncSetAttribute(dgemm_pipe_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES);
       if (ae == cudaSuccess) ae = cudaFuncSetAttribute(dgemm_pipe_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES);
       if (ae == cudaSuccess) ae = cudaFuncSetAttribute(dgemm_pipe_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES);
       if (ae != cudaSuccess) return static_cast<int>(ae);
-      attr_set = true;
+      attr_set.set();
     }
     const int grid = ((M + 127) / 128) * ((N + 127) / 128);
     if (!a_mn && !b_mn) dgemm_pipe_kernel<false, false><<<grid, DTHREADS, PIPE_SMEM_BYTES, stream>>>(a);

@@ -7,6 +7,7 @@
 // per SM).  D <= 64 and B <= 32 are far below a tensor-core tile, so everything is exact fp32 FMA arithmetic with
 // conflict-free float4 shared-memory tiles; the same Philox stream, row formulas and low-cancellation covariance
 // update as the large path (gsm_kernels.cu).
+#include "dev_once.cuh"
 #include "gsm_ensemble.cuh"
 
 #include <math.h>
@@ -312,11 +313,11 @@ int gsm_ensemble_fit(cudaStream_t st, const float* P, const float* c, float* mu,
                      int niter, unsigned long long seed, const float* ztape, int* reverts, int first_fit) {
   if (!P || !c || !mu || !Sigma || !reverts || F <= 0 || D <= 0 || D > ED || B <= 0 || B > EB || niter < 0) return GSMVI_EINVAL;
   const int smem = (4 * ED * ELD + 3 * EB * ELD + 4 * ED + 2 * EB) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (!attr_set.get()) {
     cudaError_t e = cudaFuncSetAttribute(gsm_ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
+    attr_set.set();
   }
   gsm_ensemble_kernel<<<F, ETHREADS, smem, st>>>(P, c, mu, Sigma, F, D, B, niter, seed, first_fit, ztape,
                                                  static_cast<long long>(niter + 1) * B * D, reverts);

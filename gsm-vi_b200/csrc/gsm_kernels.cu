@@ -716,6 +716,68 @@ static int gsm_update_h3_impl(cudaStream_t stream, const float* X, long long ldx
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
 }
 
+// ---- accept / revert on the device (gsmvi/gsm.py:125-129).  The host always flips its buffer pointers as if the update
+// had been accepted; when the goodness check raised *bad, this kernel copies the previous state over the rejected
+// proposal, so the flipped pointers again name the old (mu, Sigma, L) - a rejected update costs one state copy, an
+// accepted one a flag read per CTA, and no iteration waits for the host to read anything back.
+struct CommitArgs {
+  const int* bad;
+  const int* bad2;  // optional second flag (BaM: the solve's own PD flag)
+  int* status;      // [0] += 1 per rejected update, [1] <- 1 if accepted else 0
+  int n;
+  const void* src[GSMVI_COMMIT_MAX];
+  void* dst[GSMVI_COMMIT_MAX];
+  long long bytes[GSMVI_COMMIT_MAX];
+};
+
+__global__ void __launch_bounds__(256) gsm_commit_kernel(const CommitArgs a) {
+  const bool bad = (*a.bad != 0) || (a.bad2 != nullptr && *a.bad2 != 0);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (bad) a.status[0] += 1;
+    a.status[1] = bad ? 0 : 1;
+  }
+  if (!bad) return;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (int r = 0; r < a.n; ++r) {
+    const long long nb = a.bytes[r];
+    if (((reinterpret_cast<uintptr_t>(a.src[r]) | reinterpret_cast<uintptr_t>(a.dst[r]) | static_cast<uintptr_t>(nb)) & 15) == 0) {
+      const int4* s4 = static_cast<const int4*>(a.src[r]);
+      int4* d4 = static_cast<int4*>(a.dst[r]);
+      for (long long i = tid; i < nb / 16; i += nth) d4[i] = s4[i];
+    } else {
+      const unsigned* s1 = static_cast<const unsigned*>(a.src[r]);
+      unsigned* d1 = static_cast<unsigned*>(a.dst[r]);
+      for (long long i = tid; i < nb / 4; i += nth) d1[i] = s1[i];
+    }
+  }
+}
+
+int gsm_commit(cudaStream_t stream, const int* bad, const int* bad2, int n, const void* const* src, void* const* dst,
+               const long long* bytes, int* status) {
+  if (!bad || !status || n < 0 || n > GSMVI_COMMIT_MAX || (n > 0 && (!src || !dst || !bytes))) return GSMVI_EINVAL;
+  CommitArgs a;
+  a.bad = bad;
+  a.bad2 = bad2;
+  a.status = status;
+  a.n = n;
+  long long most = 0;
+  for (int r = 0; r < n; ++r) {
+    if (!src[r] || !dst[r] || bytes[r] < 0 || (bytes[r] & 3)) return GSMVI_EINVAL;
+    a.src[r] = src[r];
+    a.dst[r] = dst[r];
+    a.bytes[r] = bytes[r];
+    most = bytes[r] > most ? bytes[r] : most;
+  }
+  // the common (accepted) case is one flag read per CTA: a grid that is large enough to stream a 64 MiB state at HBM
+  // speed when it does copy, small enough to retire in a microsecond when it does not
+  int ctas = static_cast<int>((most / 16 + 255) / 256);
+  ctas = ctas < 1 ? 1 : (ctas > 592 ? 592 : ctas);
+  gsm_commit_kernel<<<ctas, 256, 0, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
+}
+
 int gsm_update_h3(cudaStream_t stream, const float* X, long long ldx, const float* G, long long ldg, const H3Operand& Gh,
                   const float* mu, const float* Sigma, long long lds, const H3Operand& Sh, float* mu_out, float* Sigma_out,
                   long long ldso, unsigned* absmax_sout, int B, int D, int B_total, int mode, void* workspace) {

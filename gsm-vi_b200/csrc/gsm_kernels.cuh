@@ -19,6 +19,10 @@ int gsm_update(cudaStream_t stream, const float* X, long long ldx, const float* 
 int gsm_apply_stats(cudaStream_t stream, const float* Sigma, long long lds, const float* dSigma, long long ldd,
                     const float* mu, const float* dmu, float* Sigma_out, long long ldso, float* mu_out, int D);
 
+// accept / revert on the device: if *bad (or *bad2) is set, copy src[r] -> dst[r] (bytes[r], multiples of 4) for r < n
+int gsm_commit(cudaStream_t stream, const int* bad, const int* bad2, int n, const void* const* src, void* const* dst,
+               const long long* bytes, int* status);
+
 // ---- scaled 3xFP16 path (h3_gemm.cuh): operands are gsmvi_h3_operand (fp16 hi / lo + device scale)
 typedef gsmvi_h3_operand H3Operand;
 int philox_normal_h3(cudaStream_t stream, const H3Operand& Z, int B, int D, unsigned long long seed,

@@ -1,6 +1,7 @@
 // Host side of the scaled 3xFP16 GEMM (h3_gemm.cuh): fp16 tensor maps, dispatch, and the operand split kernels.
 // The contractions it serves: sampler x = mu + z L^T (gsmvi/gsm.py:119), dense-Gaussian score (examples/
 // example_gsm_numpy.py:24-29), W = G Sigma and the batch-mean covariance update of gsm_update (gsmvi/gsm.py:11-27, 53-54).
+#include "dev_once.cuh"
 #include "h3_gemm.cuh"
 
 namespace gsmvi {
@@ -31,12 +32,12 @@ static int make_tmap_h(CUtensorMap* out, const __half* ptr, long long rows, long
 template <bool A_MN, bool B_MN>
 static int launch_h3_one(cudaStream_t stream, const H3Args& args, const CUtensorMap& tah, const CUtensorMap& tbh,
                          const CUtensorMap& tal, const CUtensorMap& tbl, dim3 grid, bool pdl) {
-  static bool attr_set = false;
+  static PerDeviceOnce attr_set;
   auto kern = gemm_h3_kernel<A_MN, B_MN>;
-  if (!attr_set) {
+  if (!attr_set.get()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
+    attr_set.set();
   }
   if (pdl) {
     cudaLaunchConfig_t cfg = {};

@@ -5,6 +5,7 @@
 //  * samples drawn from q as x = mu + L z  =>  L^{-1}(x - mu) = z: only |z|^2 and the log-determinant are needed
 //    (reverse KL; HBM-bound reduction over Z and diag(L));
 //  * arbitrary x (forward KL on reference samples): one CTA per sample does the forward substitution y = L^{-1}(x-mu).
+#include "dev_once.cuh"
 #include "monitor.cuh"
 
 #include <math.h>
@@ -87,11 +88,11 @@ int gauss_logq_from_x(cudaStream_t st, const float* X, long long ldx, int N, int
   if (!X || !mu || !L || !out || N <= 0 || D <= 0 || D > 48 * 1024) return GSMVI_EINVAL;
   cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double), st);
   if (e != cudaSuccess) return static_cast<int>(e);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (!attr_set.get()) {
     e = cudaFuncSetAttribute(logq_from_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024 * 4);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
+    attr_set.set();
   }
   logq_from_x_kernel<<<N, 256, D * sizeof(float), st>>>(X, ldx, D, mu, L, ldl, out);
   e = cudaGetLastError();

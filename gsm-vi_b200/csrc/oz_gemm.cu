@@ -1,4 +1,5 @@
 // FP64 GEMM on the int8 tensor cores (see oz_gemm.cuh): digit slicers, the tcgen05 kind::i8 kernel, the launcher.
+#include "dev_once.cuh"
 #include "oz_gemm.cuh"
 
 #include <cuda.h>
@@ -370,11 +371,11 @@ int launch_dgemm_oz(cudaStream_t stream, int M, int N, int K, const double* A, l
   int rc;
   if ((rc = make_tmap_u8(&ta, pa, static_cast<long long>(slices) * ra, Kp)) != GSMVI_OK) return rc;
   if ((rc = make_tmap_u8(&tb, pb, static_cast<long long>(slices) * (same ? ra : rb), Kp)) != GSMVI_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (!attr_set.get()) {
     e = cudaFuncSetAttribute(gemm_oz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
+    attr_set.set();
   }
   OzArgs a;
   a.M = M; a.N = N;

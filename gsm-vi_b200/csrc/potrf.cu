@@ -9,6 +9,7 @@
 // memory / registers and publishes it through a release flag, the other CTAs prefetch their rows of the panel, acquire
 // the flag and solve L21 L11^T = A21 one row per thread in registers;  (2) the SYRK trailing update
 // A22 -= L21 L21^T on lower tiles, on the tcgen05 3xTF32 GEMM.
+#include "dev_once.cuh"
 #include "potrf.cuh"
 #include "chol_block.cuh"
 
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(float* __restrict__
     const long long t0 = clock64();
     while (ld_acquire_u32(ready) != epoch) {
       __nanosleep(64);
-      if (clock64() - t0 > 4000000000LL) { printf("gsmvi: potrf panel watchdog (j0=%d)\n", j0); __trap(); }
+      if (clock64() - t0 > 60000000000LL) { printf("gsmvi: potrf panel watchdog (j0=%d)\n", j0); __trap(); }
     }
   }
   __syncthreads();
@@ -324,12 +325,12 @@ size_t potrf_workspace_bytes(int n) {
 int potrf_lower(cudaStream_t stream, const float* A, long long lda, float* L, long long ldl, int n, int* flag,
                 float* workspace, int npass) {
   if (n <= 0 || !A || !L || !flag || !workspace) return GSMVI_EINVAL;
-  static bool attr_set = false;
+  static PerDeviceOnce attr_set;
   const int smem = 2 * NB * DS * sizeof(float);
-  if (!attr_set) {
+  if (!attr_set.get()) {
     cudaError_t e = cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
+    attr_set.set();
   }
   unsigned* ready = reinterpret_cast<unsigned*>(workspace);
   cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), stream);

@@ -18,6 +18,7 @@
 // NEXT panel's update (1) restricted to the block-columns before the current panel - final at launch time, so neither
 // role waits for the other - and the next panel subtracts the current panel's own K = 128 term in fp32 on the CUDA cores
 // (row owners and helper CTAs, operands staged from L2 into shared memory).  See DESIGN.md section 3.2.
+#include "dev_once.cuh"
 #include "potrf.cuh"
 #include "chol_block.cuh"
 #include "h3_gemm.cuh"
@@ -283,7 +284,7 @@ __device__ __forceinline__ void wait_epoch(const unsigned* ready, unsigned targe
     const long long t0 = clock64();
     while (static_cast<int>(ld_acquire_u32(ready) - target) < 0) {
       __nanosleep(20);
-      if (clock64() - t0 > 4000000000LL) { printf("gsmvi: potrf panel watchdog (j0=%d epoch %u)\n", j0, target); __trap(); }
+      if (clock64() - t0 > 60000000000LL) { printf("gsmvi: potrf panel watchdog (j0=%d epoch %u)\n", j0, target); __trap(); }
     }
   }
   cta_sync();
@@ -352,7 +353,7 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw) 
         if (tid == 0) {
           const long long t0 = clock64();
           while (static_cast<int>(ld_acquire_u32(a.helper_count) - a.helper_target) < 0) {
-            if (clock64() - t0 > 4000000000LL) { printf("gsmvi: potrf helper watchdog (j0=%d)\n", j0); __trap(); }
+            if (clock64() - t0 > 60000000000LL) { printf("gsmvi: potrf helper watchdog (j0=%d)\n", j0); __trap(); }
           }
         }
         cta_sync();
@@ -867,15 +868,15 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
   } else if (n <= 0) {
     return GSMVI_EINVAL;
   }
-  static bool attr_set = false;
-  if (!attr_set && !plan) {
+  static PerDeviceOnce attr_set;
+  if (!plan && !attr_set.get()) {
     cudaError_t e = cudaFuncSetAttribute(potrf_panel_h3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_panel_h3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_panel_h3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_fused_h3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_fused_h3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
+    attr_set.set();
   }
   long long worst = 0;
   for (long long j0 = NB; j0 < n; j0 += NB) {
@@ -895,7 +896,8 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
       potrf_zero_upper_kernel<<<dim3((n / 4 + 255) / 256, n), 256, 0, stream>>>(L, ldl, Lhi, Llo, Lh.ld, n);
   }
   unsigned epoch = 0;
-  static int dev_ctas = 0;
+  static PerDeviceInt dev_ctas_pd;
+  int& dev_ctas = dev_ctas_pd.ref();
   if (dev_ctas == 0 && !plan) {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);

@@ -1,4 +1,5 @@
 // Host-side launcher for the tcgen05 TF32 GEMM (tc_gemm.cuh): tensor-map construction and dispatch.
+#include "dev_once.cuh"
 #include "tc_gemm.cuh"
 
 #include <mutex>
@@ -38,12 +39,12 @@ template <int NPASS, bool SPLIT_RN, bool A_MN, bool B_MN, int PRE>
 static int launch_one(cudaStream_t stream, const GemmArgs& args, const CUtensorMap& ta, const CUtensorMap& tb,
                       const CUtensorMap& tal, const CUtensorMap& tbl, int grid) {
   using Cfg = GemmCfg<NPASS>;
-  static bool attr_set = false;
+  static PerDeviceOnce attr_set;
   auto kern = gemm_tf32_kernel<NPASS, SPLIT_RN, A_MN, B_MN, PRE>;
-  if (!attr_set) {
+  if (!attr_set.get()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
+    attr_set.set();
   }
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(args, ta, tb, tal, tbl);
   cudaError_t e = cudaGetLastError();

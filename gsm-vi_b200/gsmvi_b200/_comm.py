@@ -87,11 +87,20 @@ class CommBuffer:
                 "gsmvi_gsm_update_h3_fused")
         self.step += 1
 
-    def close(self):
+    def close(self, collective=True):
+        """collective=True: every rank calls it (barriers order unmapping and free).  collective=False: emergency /
+        interpreter-exit teardown of this rank alone - unmap the peers' buffers and free the own one without waiting for
+        anybody (a peer that still has this buffer mapped keeps a valid mapping until it unmaps: CUDA IPC reference-counts
+        the allocation; what is lost is only the guarantee that nobody writes into it any more, which a dying fit has
+        given up anyway)."""
         if self.own is None:
             return
-        torch.cuda.synchronize()
-        self.dist.barrier(group=self.group)  # nobody is still writing into a buffer that is about to be unmapped
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+        if collective:
+            self.dist.barrier(group=self.group)  # nobody is still writing into a buffer that is about to be unmapped
         for p in self.opened:
             self.lib.gsmvi_comm_close(p)
         self.opened = []
@@ -99,6 +108,7 @@ class CommBuffer:
         self.S = None
         # an exported allocation must outlive every importer's mapping (cudaFree before the peers' cudaIpcCloseMemHandle is
         # undefined behaviour): free only after every rank has closed its mappings
-        self.dist.barrier(group=self.group)
+        if collective:
+            self.dist.barrier(group=self.group)
         self.lib.gsmvi_comm_free(self.own)
         self.own = None

@@ -419,3 +419,61 @@ def dgemm_oz(A, B, C, M, N, K, a_mn=False, b_mn=False, alpha=1.0, beta=0.0, Cin=
                                alpha, beta, ptr(Cin), Cin.stride(0) if Cin is not None else 0, diag_add, int(tri),
                                int(mirror), ctypes.c_void_p(base), slices, stream_ptr()), "gsmvi_dgemm_oz")
     return C
+
+
+# ------------------------------------------------------------------------------------------------ fp64 small-D GSM
+SMALL64_INIT, SMALL64_FULL, SMALL64_SAMPLE, SMALL64_UPDATE = 0, 1, 2, 3
+
+
+def _declare_small64(L):
+    L.gsmvi_gsm_commit.restype = c_i
+    L.gsmvi_gsm_commit.argtypes = [c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p]
+    L.gsmvi_gsm_small64_workspace_bytes.restype = c_ll
+    L.gsmvi_gsm_small64_workspace_bytes.argtypes = [c_i, c_i]
+    L.gsmvi_gsm_small64.restype = c_i
+    L.gsmvi_gsm_small64.argtypes = [c_i, c_p, c_p, c_p, c_p, c_ull, c_ull, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]
+
+
+_declare_oz_level = _declare
+
+
+def _declare(L):  # noqa: F811
+    _declare_oz_level(L)
+    _declare_small64(L)
+
+
+COMMIT_MAX = 12
+
+
+class CommitPlan:
+    """Host-side argument block of gsmvi_gsm_commit: the regions (previous state -> proposal buffers) that are copied on
+    the device when an update is rejected.  Built once per buffer parity and reused every iteration."""
+
+    def __init__(self, pairs):
+        pairs = [(s, d) for (s, d) in pairs if s is not None]
+        assert len(pairs) <= COMMIT_MAX
+        self.n = len(pairs)
+        self.keep = pairs  # the tensors own the memory the raw pointers below name
+        for s_, d_ in pairs:
+            assert s_.is_contiguous() and d_.is_contiguous() and s_.numel() * s_.element_size() == d_.numel() * d_.element_size()
+        self.src = (c_p * max(self.n, 1))(*[s_.data_ptr() for s_, _ in pairs])
+        self.dst = (c_p * max(self.n, 1))(*[d_.data_ptr() for _, d_ in pairs])
+        self.nbytes = (c_ll * max(self.n, 1))(*[s_.numel() * s_.element_size() for s_, _ in pairs])
+
+
+def gsm_commit(bad, plan, status, bad2=None):
+    check(lib().gsmvi_gsm_commit(ptr(bad), ptr(bad2), plan.n, plan.src, plan.dst, plan.nbytes, ptr(status), stream_ptr()),
+          "gsmvi_gsm_commit")
+
+
+def gsm_small64_workspace_bytes(B, D):
+    n = lib().gsmvi_gsm_small64_workspace_bytes(B, D)
+    if n < 0:
+        raise GsmviError("gsmvi_gsm_small64 supports 1 <= D <= 64 (got D=%d, B=%d)" % (D, B))
+    return n
+
+
+def gsm_small64(mode, mu, Sigma, L_, z_tape, seed, iter0, X, G, P, c, B, D, iters, status, ws):
+    check(lib().gsmvi_gsm_small64(mode, ptr(mu), ptr(Sigma), ptr(L_), ptr(z_tape), seed & (2**64 - 1), iter0 & (2**64 - 1),
+                                  ptr(X), ptr(G), ptr(P), ptr(c), B, D, iters, ptr(status), ptr(ws), stream_ptr()),
+          "gsmvi_gsm_small64")

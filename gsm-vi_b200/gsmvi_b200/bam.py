@@ -67,8 +67,8 @@ class BaMEngine:
         if batch_size % self.world != 0:
             raise ValueError("batch_size must be divisible by the number of ranks")
         B = self.B = batch_size // self.world
-        if use_lowrank and (self.world > 1 or batch_size + 1 >= D):
-            raise ValueError("the low-rank update needs batch_size + 1 < D and a single rank")
+        if use_lowrank and batch_size + 1 >= D:
+            raise ValueError("the low-rank update needs batch_size + 1 < D (the reference's svds(U, k=B) needs B < D)")
         self.seed = key_to_seed(key)
         self.score_input = score_input
         self.Sb, self.S = new_mat(D, D, dev)
@@ -88,7 +88,12 @@ class BaMEngine:
         self.ws_p = torch.empty(L.workspace_bytes(L.WS_POTRF, B, D) // 4, dtype=torch.float32, device=dev)
         self.ws_s = torch.empty(L.workspace_bytes(L.WS_BAM_STATS, B, D) // 8, dtype=torch.float64, device=dev)
         kind = L.WS_BAM_SOLVE_LOWRANK if use_lowrank else L.WS_BAM_SOLVE
-        self.ws_v = torch.empty(L.workspace_bytes(kind, B, D) // 8, dtype=torch.float64, device=dev)
+        self.ws_v = torch.empty(L.workspace_bytes(kind, batch_size if use_lowrank else B, D) // 8, dtype=torch.float64,
+                                device=dev)
+        if use_lowrank and self.world > 1:
+            # sharded low-rank update: the K = batch_size + 1 columns of U's exact factor Q come from every rank's centred
+            # scores, gathered into a full-batch statistics block; the O(D^2 K) solve is then replicated (bit-identical)
+            self.ws_full = torch.zeros(L.workspace_bytes(L.WS_BAM_STATS, batch_size, D) // 8, dtype=torch.float64, device=dev)
         self.bad = torch.zeros(1, dtype=torch.int32, device=dev)
         self.bad2 = torch.zeros(1, dtype=torch.int32, device=dev)
         if z_tape is not None and not isinstance(z_tape, torch.Tensor):
@@ -139,12 +144,27 @@ class BaMEngine:
                 self.bad2)
         if self.world == 1:
             it = L.bam_solve(*args, lowrank=self.use_lowrank, max_ns=self.max_ns)
+        elif self.use_lowrank:
+            # bam.py:72-114 on a sharded batch: C, xbar, gbar are already global; gather the centred score rows (rank order =
+            # sample order) so every rank holds Q = [sqrt(reg/B) Gc^T, sqrt(reg/(1+reg)) gbar] in full, then solve as one rank
+            ld = (D + 7) // 8 * 8
+            Bt = self.batch_size
+            gc_local = self.ws_s[B * ld: 2 * B * ld]
+            self.dist.all_gather_into_tensor(self.ws_full[Bt * ld: 2 * Bt * ld], gc_local, group=self.group)
+            self.ws_full[2 * Bt * ld: 2 * Bt * ld + (D + 2) * ld].copy_(self.ws_s[2 * B * ld: 2 * B * ld + (D + 2) * ld])
+            it = L.bam_solve(self.ws_full, Bt, D, Bt, self.mu, self.Sb, reg, self.jitter, self.mun, self.Snb, self.ws_v,
+                             self.bad2, lowrank=True, max_ns=self.max_ns)
         else:  # shard partials of M = I + 4 W W^T are summed between the two phases of the solve
             L.bam_solve(*args, max_ns=self.max_ns, world=self.world, phase=1)
             ld = (D + 7) // 8 * 8
             self.dist.all_reduce(self.ws_v[3 * D * ld: 4 * D * ld], group=self.group)
             it = L.bam_solve(*args, max_ns=self.max_ns, world=self.world, phase=2)
         self.ns_iters.append(it)
+        # bit 1 of the solve's flag: the Newton-Schulz square root did not converge (the reference's scipy sqrtm raises
+        # there, and BaM.fit's retry loop - bam.py:188-206 - draws fresh samples).  With a fixed draw tape a retry would see
+        # the same samples, so the proposal is left to the goodness check, which rejects it (flag != 0).
+        if self.z_tape is None and (int(self.bad2.item()) & 2):
+            raise FloatingPointError("BaM update: the Newton-Schulz square root did not converge")
         return it
 
     def propose(self, i, reg):

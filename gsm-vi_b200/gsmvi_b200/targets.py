@@ -11,6 +11,26 @@ from . import _lib as L
 from ._util import device, new_mat, new_vec
 
 
+def dense_gaussian_target(D, seed=0):
+    """(mean, cov) of the benchmark's dense-Gaussian family: the examples' generator (examples/example_gsm_numpy.py:11-14:
+    mean ~ U(0,1)^D, A ~ N(0,1)^{DxD}) on a seeded RandomState with cov = A A^T / D + 1e-3 I, so that the spectrum is O(1)
+    at any D.  numpy fp64."""
+    rng = np.random.RandomState(seed)
+    mean = rng.random_sample(D)
+    A = rng.normal(size=(D, D))
+    return mean, A @ A.T / D + np.eye(D) * 1e-3
+
+
+def illcond_gaussian_target(D, kappa=1e2, seed=0):
+    """(mean, cov) of the ill-conditioned family (BASELINE configs 3 / 4): cov = Q diag(logspace(0, -log10 kappa, D)) Q^T
+    with Q from the QR factorisation of a seeded Gaussian matrix.  numpy fp64."""
+    rng = np.random.RandomState(seed)
+    mean = rng.random_sample(D)
+    Q, _ = np.linalg.qr(rng.normal(size=(D, D)))
+    cov = (Q * np.logspace(0, -np.log10(kappa), D)) @ Q.T
+    return mean, (cov + cov.T) / 2
+
+
 class DenseGaussianTarget:
     def __init__(self, mean, cov, dev=None):
         dev = dev or device()
@@ -33,6 +53,14 @@ class DenseGaussianTarget:
         self.c[: self.D].copy_(torch.as_tensor(P @ mean, dtype=torch.float32))
         self.m = torch.as_tensor(mean, dtype=torch.float32, device=dev)
         self._gsmvi_builtin_target = self
+
+    def device_fp64(self):
+        """(P [D, D], c = P m [D]) as contiguous fp64 device tensors: the operands of the fp64 small-D path (D <= 64)."""
+        if getattr(self, "_P64d", None) is None:
+            dev = self.P.device
+            self._P64d = torch.as_tensor(self.P64, dtype=torch.float64).to(dev).contiguous()
+            self._c64d = torch.as_tensor(self.P64 @ self.mean64, dtype=torch.float64).to(dev).contiguous()
+        return self._P64d, self._c64d
 
     def lp_g(self, x):
         """Score -(x - m) P, [B, D] -> [B, D] (examples/example_gsm_numpy.py:24-29), via the device GEMM."""

@@ -254,6 +254,39 @@ int gsmvi_gauss_logq_reduce(const float* Z_or_X, long long ld, int N, int D, con
 int gsmvi_gsm_ensemble_fit(const float* P, const float* c, float* mu, float* Sigma, int F, int D, int B, int niter,
                            unsigned long long seed, const float* z_tape, int* reverts, int first_fit, void* stream);
 
+/* Accept / revert of an iteration's proposal on the device.  Replaces the host-side branch of gsmvi/gsm.py:125-129 and
+ * gsmvi/bam.py:208-212 (`if is_good: mean, cov = mean_new, cov_new else: revert`), which costs the reference a device ->
+ * host copy of the covariance and a host Cholesky per iteration.  The caller always exchanges its (current, proposal)
+ * buffer pointers; when *bad_flag (the Cholesky's PD flag; optionally also *bad_flag2) is non-zero this call copies the n
+ * regions src[r] -> dst[r] (the previous state over the rejected proposal; bytes[r] multiples of 4; src / dst / bytes are
+ * HOST arrays of n <= GSMVI_COMMIT_MAX entries holding device pointers), so the exchanged pointers name the old state
+ * again.  status (device int[2]): [0] += 1 per rejected update, [1] <- 1 if accepted else 0.  Nothing is read back. */
+#define GSMVI_COMMIT_MAX 12
+int gsmvi_gsm_commit(const int* bad_flag, const int* bad_flag2, int n, const void* const* src_host, void* const* dst_host,
+                     const long long* bytes_host, int* status, void* stream);
+
+/* fp64 GSM iteration for small problems (D <= 64), one CTA, state resident on the device, accept / revert predicated
+ * on the device (no host read between iterations).  Replaces the loop body of gsmvi/gsm_numpy.py:107-127 (numpy fp64:
+ * np.random.multivariate_normal, lp_g, gsm_update gsm_numpy.py:27-55, np.linalg.cholesky check gsm_numpy.py:131-145) -
+ * BASELINE configs[0], examples/example_gsm_numpy.py - and gsmvi/gsm.py:107-129 under jax_enable_x64.
+ * State (DOUBLES, dense row-major): mu [D], Sigma [D,D], L [D,D] = chol(Sigma).
+ * mode GSMVI_SMALL64_INIT:   L <- chol(Sigma); status[1] <- 1 if Sigma is not positive definite.
+ * mode GSMVI_SMALL64_FULL:   `iters` complete iterations with the built-in dense-Gaussian score g = -x P + c
+ *                            (P [D,D] symmetric precision, c = P m; examples/example_gsm_numpy.py:24-29).
+ * mode GSMVI_SMALL64_SAMPLE: X [B,D] <- mu + Z L^T (gsm.py:117-119) - then the caller evaluates its lp_g on X - and
+ * mode GSMVI_SMALL64_UPDATE: the update (gsm.py:122), check (gsm.py:125) and commit from X and the caller's G [B,D].
+ * Draws: z_tape [iters, B, D] (fp32, the slice for these iterations) or NULL for Philox4x32-10 (seed, counter iter0 + it).
+ * status (device int[3]): [0] += rejected updates, [1] see INIT, [2] <- 1 if the last update was accepted.
+ * workspace: gsmvi_gsm_small64_workspace_bytes(B, D) bytes, 8-byte aligned. */
+#define GSMVI_SMALL64_INIT 0
+#define GSMVI_SMALL64_FULL 1
+#define GSMVI_SMALL64_SAMPLE 2
+#define GSMVI_SMALL64_UPDATE 3
+long long gsmvi_gsm_small64_workspace_bytes(int B, int D);
+int gsmvi_gsm_small64(int mode, double* mu, double* Sigma, double* L, const float* z_tape, unsigned long long seed,
+                      unsigned long long iter0, double* X, const double* G, const double* P, const double* c, int B, int D,
+                      int iters, int* status, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

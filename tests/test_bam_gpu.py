@@ -128,6 +128,32 @@ def test_bam_update_matches_oracle_large(lib, D, B, reg, kappa):
         assert relF(S_l, S_o) < 1e-4 and relF(mu_l, mu_o) < 1e-4
 
 
+def test_bam_update_full_size(lib):
+    """BASELINE headline shape D = B = 4096 (configs[3]) on the ill-conditioned target, kappa = 1e2, reg = 100 (the first
+    value of the example's schedule, example_bam.py:58-59): one device update vs the oracle's bam_update (a 4096 eigh on the
+    host), plus the size-independent property that S solves S U S + S = V."""
+    from gsmvi_b200.bam import bam_update
+    D = B = 4096
+    reg, kappa = 100.0, 1e2
+    rng = np.random.RandomState(7)
+    mean_t, cov_t = orc.illcond_gaussian_target(D, kappa, 0)
+    P = np.linalg.inv(cov_t)
+    mu0 = f32(rng.normal(size=D) * 0.1)
+    S0 = np.eye(D)
+    X = f32(mu0 + rng.normal(size=(B, D)))
+    G = f32(-(X - mean_t) @ P)
+    mu, S = bam_update(X, G, mu0, S0, reg)
+    mu_o, S_o = orc.bam_update(X, G, mu0, S0, reg)
+    xbar, gbar, U, V = orc.bam_stats(X, G, mu0, S0, reg)
+    Sd = S.cpu().double().numpy()
+    res = np.linalg.norm(Sd @ U @ Sd + Sd - V) / (np.linalg.norm(Sd) ** 2 * np.linalg.norm(U) + np.linalg.norm(V))
+    record("bam_update_full_size", dict(D=D, B=B, reg=reg, kappa=kappa, relF_cov=relF(S, S_o), rel_mean=relF(mu, mu_o),
+                                        qme_residual=res))
+    assert relF(S, S_o) < 1e-4 and relF(mu, mu_o) < 1e-4
+    assert res < 1e-6
+    assert torch.equal(S, S.t())
+
+
 FIT_CASES = [
     # D, B, niter, target, kappa, lowrank
     (16, 4, 60, "illcond", 1e1, False),

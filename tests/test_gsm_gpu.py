@@ -168,19 +168,21 @@ def test_sample_and_score_match_oracle(lib, B, D):
     assert relF(G, lp_g(X.cpu().double().numpy())) < 2e-5  # precision matrix is ill-conditioned: P in fp32
 
 
+@pytest.mark.parametrize("npass", [4, 3])  # 4: gsmvi_gsm_update_h3 (the engine GSM.fit and bench.py run), 3: 3xTF32
 @pytest.mark.parametrize("D,B", [(5, 2), (10, 4), (64, 16), (12, 7)])
-def test_gsm_update_matches_reference_golden(lib, golden, D, B):
+def test_gsm_update_matches_reference_golden(lib, golden, D, B, npass):
     from gsmvi_b200.gsm import gsm_update
     k = f"gsm_update_D{D}_B{B}"
     X, G, mu0, S0 = (golden[k + s] for s in ("_X", "_G", "_mu0", "_S0"))
-    mu, S = gsm_update(X, G, mu0, S0)
+    mu, S = gsm_update(X, G, mu0, S0, npass=npass)
     assert relF(S, golden[k + "_S_numpy"]) < 5e-6
     assert relF(mu, golden[k + "_mu_numpy"]) < 5e-6
     assert torch.equal(S, S.t())
 
 
+@pytest.mark.parametrize("npass", [4, 3])
 @pytest.mark.parametrize("D,B", [(512, 64), (1000, 48), (1024, 1024)])
-def test_gsm_update_matches_oracle_large(lib, D, B):
+def test_gsm_update_matches_oracle_large(lib, D, B, npass):
     from gsmvi_b200.gsm import gsm_update
     rng = np.random.RandomState(D + B)
     mean_t, cov_t = orc.dense_gaussian_target(D, 1)
@@ -190,7 +192,7 @@ def test_gsm_update_matches_oracle_large(lib, D, B):
     S0 = A @ A.T / D + 0.5 * np.eye(D)
     X = mu0 + rng.normal(size=(B, D)) @ np.linalg.cholesky(S0).T
     G = lp_g(X)
-    mu, S = gsm_update(X, G, mu0, S0)
+    mu, S = gsm_update(X, G, mu0, S0, npass=npass)
     mu_o, S_o = orc.gsm_update(X.astype(np.float32).astype(np.float64), G.astype(np.float32).astype(np.float64),
                                mu0.astype(np.float32).astype(np.float64), S0.astype(np.float32).astype(np.float64))
     assert relF(S, S_o) < 1e-5
@@ -242,6 +244,148 @@ def test_gsm_fit_trajectory_parity(lib, D, B, niter, kind, npass):
     assert e_c < tol
     assert e_m < tol
     assert torch.equal(c_d, c_d.t())
+
+
+@pytest.mark.parametrize("D,B,niter,score", [(10, 2, 500, "builtin"), (10, 2, 500, "numpy"), (5, 2, 500, "builtin"),
+                                              (64, 32, 100, "builtin"), (33, 7, 60, "torch64")])
+def test_gsm_fit_small_fp64_path_config1(lib, D, B, niter, score):
+    """BASELINE configs[0] (examples/example_gsm_numpy.py:38-46: D = 10, batch 2, 500 iterations, numpy fp64) on the
+    default path for D <= 64 - the fp64 single-CTA kernel - against the fp64 oracle on the TRUE (unrounded) example
+    target, identical z-tape: BASELINE north_star tolerance 1e-4 on (mu, Sigma); the achieved figure is ~1e-10."""
+    from gsmvi_b200.gsm import GSM
+    from gsmvi_b200.targets import DenseGaussianTarget
+    mean_t, cov_t = orc.example_target(D, seed=D)
+    _, lp_g_o, icov = orc.gaussian_score_fns(mean_t, cov_t)
+    Z = np.random.RandomState(1).normal(size=(niter + 1, B, D)).astype(np.float32)
+    o = orc.GSM(D, None, lp_g_o)
+    m_o, c_o = o.fit(99, niter=niter, batch_size=B, sampler=orc.CholeskyTapeSampler(Z.astype(np.float64)))
+    tgt = DenseGaussianTarget(mean_t, cov_t)
+    if score == "builtin":
+        g, kw = GSM(D, tgt.lp, tgt.lp_g), {}
+    elif score == "numpy":  # the example's own kind of callable: host fp64 arrays in, host fp64 arrays out
+        g, kw = GSM(D, None, lambda x: -(x - mean_t) @ icov.T), dict(score_input="numpy")
+    else:
+        Pd = torch.as_tensor(icov, dtype=torch.float64, device="cuda")
+        md = torch.as_tensor(mean_t, dtype=torch.float64, device="cuda")
+        g, kw = GSM(D, None, lambda x: -(x - md) @ Pd.t()), dict(score_input="torch64")
+    m_d, c_d = g.fit(99, niter=niter, batch_size=B, z_tape=Z, verbose=False, **kw)
+    assert c_d.dtype == torch.float64
+    e_c = relF(c_d, c_o)
+    e_m = np.linalg.norm(m_d.cpu().double().numpy() - m_o) / np.linalg.norm(m_o)
+    record("gsm_fit_parity_fp64_small", dict(D=D, B=B, niter=niter, score=score, relF_cov=e_c, rel_mean=e_m,
+                                             reverts_dev=g.n_reverts, reverts_oracle=o.n_reverts))
+    assert g.n_reverts == o.n_reverts
+    assert e_c < 1e-4 and e_m < 1e-4  # north_star bar
+    assert e_c < 1e-7 and e_m < 1e-7  # what fp64 on both sides should give on a kappa ~ 3e4 target
+    assert torch.equal(c_d, c_d.t())
+    # the fit also reaches the target itself (GSM's fixed point), as the example checks by eye
+    assert relF(c_d, cov_t) < 1e-6 or niter < 500
+
+
+def test_gsm_small_fp64_path_philox_monitor_and_chunks(lib):
+    """fp64 path with Philox draws: chunked launches between monitor checkpoints give the same fit as one launch per
+    iteration (verbose=True path), and the monitor sees the state at each checkpoint."""
+    from gsmvi_b200.gsm import GSM
+    from gsmvi_b200.monitors import KLMonitor
+    from gsmvi_b200.targets import DenseGaussianTarget
+    D, B, niter = 16, 4, 60
+    mean_t, cov_t = orc.dense_gaussian_target(D, 3)
+    tgt = DenseGaussianTarget(mean_t, cov_t)
+    mon = KLMonitor(batch_size_kl=32, checkpoint=7)
+    m1, c1 = GSM(D, tgt.lp, tgt.lp_g).fit(5, niter=niter, batch_size=B, verbose=False, monitor=mon)
+    m2, c2 = GSM(D, tgt.lp, tgt.lp_g).fit(5, niter=niter, batch_size=B, verbose=True, nprint=3)
+    assert torch.equal(c1, c2) and torch.equal(m1, m2)
+    assert len(mon.rkl) == niter // 7 + 2 and np.isfinite(mon.rkl).all()
+    assert mon.nevals[0] == 1 and mon.nevals[-1] == 1 + B * (niter + 1)  # cumulative (monitors.py:122-123)
+    assert relF(c1, cov_t) < 1e-2
+
+
+@pytest.mark.parametrize("npass,D,B", [(4, 200, 48), (3, 200, 48), (0, 24, 8)])
+def test_gsm_rejected_update_is_reverted_on_device(lib, npass, D, B):
+    """gsm.py:125-129: a proposal whose covariance fails the Cholesky check is dropped and the previous (mu, Sigma) kept.
+    The device path decides and reverts without the host (gsmvi_gsm_commit / the fp64 kernel's predicated commit): a
+    score callable that returns NaN on its third call must cost exactly one reverted iteration, on the device as in the
+    oracle loop, and leave both with the same fit."""
+    from gsmvi_b200.gsm import GSM
+    niter = 6
+    mean_t, cov_t = orc.dense_gaussian_target(D, 2)
+    icov = np.linalg.inv(cov_t)
+    Z = np.random.RandomState(4).normal(size=(niter + 1, B, D)).astype(np.float32)
+    calls = {"o": 0, "d": 0}
+
+    def lp_g_o(x):
+        calls["o"] += 1
+        g = -(x - mean_t) @ icov.T
+        return g * np.nan if calls["o"] == 3 else g
+
+    def lp_g_d(x):
+        calls["d"] += 1
+        g = -(x - mean_t) @ icov.T
+        return g * np.nan if calls["d"] == 3 else g
+
+    o = orc.GSM(D, None, lp_g_o)
+    m_o, c_o = o.fit(0, niter=niter, batch_size=B, sampler=orc.CholeskyTapeSampler(Z.astype(np.float64)))
+    g = GSM(D, None, lp_g_d)
+    m_d, c_d = g.fit(0, niter=niter, batch_size=B, z_tape=Z, verbose=False, npass=npass, score_input="numpy")
+    assert o.n_reverts == 1 and g.n_reverts == 1
+    tol = 1e-9 if npass == 0 else 1e-4
+    assert relF(c_d, c_o) < tol and relF(m_d, m_o) < tol
+    assert torch.isfinite(c_d).all() and torch.equal(c_d, c_d.t())
+
+
+def test_gsm_warm_start_from_lbfgs_style_estimate(lib):
+    """gsmvi/initializers.py:5-17 hands GSM.fit a dense inverse-Hessian estimate as `cov` (examples/
+    example_initializers.py:92-96); such an estimate can be slightly non-symmetric or numerically indefinite.  The fit
+    must start from it (symmetrised, minimally shifted, with a warning) instead of refusing, and still converge."""
+    import warnings
+    from gsmvi_b200.gsm import GSM
+    from gsmvi_b200.targets import DenseGaussianTarget
+    D, B = 96, 32
+    mean_t, cov_t = orc.dense_gaussian_target(D, 6)
+    tgt = DenseGaussianTarget(mean_t, cov_t)
+    rng = np.random.RandomState(0)
+    # BFGS-like estimate: right eigenvectors, a few eigenvalues lost to round-off (tiny negatives) and a skew part
+    w, Q = np.linalg.eigh(cov_t)
+    w_est = w * np.exp(0.3 * rng.normal(size=D))
+    w_est[:3] = -1e-7
+    cov0 = (Q * w_est) @ Q.T + 1e-9 * rng.normal(size=(D, D))
+    assert np.linalg.eigvalsh((cov0 + cov0.T) / 2).min() < 0
+    mean0 = mean_t + 0.05 * rng.normal(size=D)
+    with warnings.catch_warnings(record=True) as wlist:
+        warnings.simplefilter("always")
+        g = GSM(D, tgt.lp, tgt.lp_g)
+        m, c = g.fit(3, mean=mean0, cov=cov0, niter=150, batch_size=B, verbose=False)
+    assert any("not numerically positive definite" in str(x.message) for x in wlist)
+    assert relF(c, cov_t) < 5e-3 and np.max(np.abs(m.cpu().numpy() - mean_t)) < 5e-3
+    # a start that no small shift can repair is still refused (NaN entries)
+    bad = cov_t.copy()
+    bad[0, 0] = np.nan
+    with pytest.raises(ValueError):
+        GSM(D, tgt.lp, tgt.lp_g).fit(3, mean=mean0, cov=bad, niter=2, batch_size=B, verbose=False)
+    # and the engine that refused is still usable afterwards
+    m2, c2 = GSM(D, tgt.lp, tgt.lp_g).fit(3, niter=150, batch_size=B, verbose=False)
+    assert relF(c2, cov_t) < 5e-3
+
+
+def test_gsm_engine_is_reused_across_fits(lib):
+    """GSM.fit keeps its engine (workspaces, graphs, exchange buffers) between calls: a second fit with the same shape
+    must give exactly the result of a first fit with the same arguments, whatever ran on the engine in between."""
+    from gsmvi_b200 import gsm as gsm_mod
+    from gsmvi_b200.gsm import GSM
+    from gsmvi_b200.targets import DenseGaussianTarget
+    D, B = 160, 40
+    mean_t, cov_t = orc.dense_gaussian_target(D, 8)
+    tgt = DenseGaussianTarget(mean_t, cov_t)
+    Z = np.random.RandomState(2).normal(size=(13, B, D)).astype(np.float32)
+    gsm_mod.release_engines()
+    m1, c1 = GSM(D, tgt.lp, tgt.lp_g).fit(1, niter=12, batch_size=B, z_tape=Z, verbose=False)
+    GSM(D, tgt.lp, tgt.lp_g).fit(2, niter=25, batch_size=B, verbose=False)  # Philox fit in between (graph replay)
+    assert len(gsm_mod._ENGINES) == 1
+    m2, c2 = GSM(D, tgt.lp, tgt.lp_g).fit(1, niter=12, batch_size=B, z_tape=Z, verbose=False)
+    assert relF(c2, c1.cpu().double().numpy()) < 1e-6 and relF(m2, m1.cpu().double().numpy()) < 1e-6
+    m3, c3 = GSM(D, tgt.lp, tgt.lp_g).fit(2, niter=25, batch_size=B, verbose=False)
+    m4, c4 = GSM(D, tgt.lp, tgt.lp_g).fit(2, niter=25, batch_size=B, verbose=False)
+    assert relF(c4, c3.cpu().double().numpy()) < 1e-6
 
 
 def test_gsm_fit_user_callable_and_philox(lib):
@@ -339,9 +483,11 @@ def test_gsm_full_size_properties(lib):
     mu64, S64 = mean.cpu().double().numpy(), cov.cpu().double().numpy()
     X = (mu64 + rng.normal(size=(B, D)) @ np.linalg.cholesky(S64).T).astype(np.float32).astype(np.float64)
     Gs = tgt.lp_g(torch.as_tensor(X, dtype=torch.float32, device="cuda")).cpu().double().numpy()
-    mu_d, S_d = gsm_update(X, Gs, mean, cov)
     mu_o, S_o = orc.gsm_update(X, Gs, mu64, S64)
-    e_S, e_mu = relF(S_d, S_o), relF(mu_d, mu_o)
-    dS = relF(S_d.cpu().double().numpy() - S64, S_o - S64)  # error relative to the increment itself
-    record("gsm_update_full_size", dict(D=D, B=B, relF_cov=e_S, rel_mean=e_mu, relF_increment=dS))
-    assert e_S < 1e-5 and e_mu < 1e-5 and dS < 1e-3
+    for npass in (4, 3):  # 4 = gsmvi_gsm_update_h3, the kernel sequence bench.py times at this shape; 3 = 3xTF32 engine
+        mu_d, S_d = gsm_update(X, Gs, mean, cov, npass=npass)
+        e_S, e_mu = relF(S_d, S_o), relF(mu_d, mu_o)
+        dS = relF(S_d.cpu().double().numpy() - S64, S_o - S64)  # error relative to the increment itself
+        record("gsm_update_full_size", dict(D=D, B=B, npass=npass, relF_cov=e_S, rel_mean=e_mu, relF_increment=dS))
+        assert e_S < 1e-5 and e_mu < 1e-5 and dS < 1e-3
+        assert torch.equal(S_d, S_d.t())

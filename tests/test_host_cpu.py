@@ -135,14 +135,14 @@ def test_regularizers_and_keys():
 def test_launch_count_formula():
     """gpu_launches reported by bench.py = gsm.launch_count(...) x steps.  At D = 4096 with the built-in target and Philox
     draws: h3 engine with the look-ahead Cholesky 1 draw + 4 (sample, split X, score, split G) + 7 update + 33 Cholesky
-    (prepare + 32 fused panel launches); two-launch Cholesky: + 31 update GEMMs; 3xTF32 engine: 73 (incl. its two operand splits)."""
+    (prepare + 32 fused panel launches) + 1 commit; two-launch Cholesky: + 31 update GEMMs; 3xTF32 engine: 74 (incl. its two operand splits)."""
     from gsmvi_b200.gsm import launch_count
-    assert launch_count(4096) == 1 + 4 + 7 + 33 == 45
-    assert launch_count(4096, lookahead=False) == 45 + 31
-    assert launch_count(4096, h3=False) == 73
+    assert launch_count(4096) == 1 + 4 + 7 + 33 + 1 == 46  # + the device-side accept / revert (gsmvi_gsm_commit)
+    assert launch_count(4096, lookahead=False) == 46 + 31
+    assert launch_count(4096, h3=False) == 74
     assert launch_count(4000) == launch_count(4096) + 1  # ragged last panel keeps its own update GEMM
     assert launch_count(256) == launch_count(256, lookahead=False)  # below 512 the two-launch form is used
-    assert launch_count(4096, world=8) == 48 and launch_count(4096, tape=True) == 46
+    assert launch_count(4096, world=8) == 49 and launch_count(4096, tape=True) == 47
 
 
 def test_scaled_fp16_split_model_keeps_22_bits():

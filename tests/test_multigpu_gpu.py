@@ -42,6 +42,34 @@ for (D, B, niter) in [(96, 32, 20), (512, 256, 6)]:
     assert e[0] < 2e-5 and e[1] < 2e-5, e
     # both ranks hold identical replicated state
     t = b2c.clone(); dist.broadcast(t, 0); assert torch.equal(t, b2c)
+    # low-rank update (bam.py:72-114, the one example_bam.py uses) under the process group
+    l1m, l1c = BaM(D, tgt.lp, tgt.lp_g, use_lowrank=True).fit(0, Regularizers().custom(lambda i: 100 / (1 + i)), niter=niter, batch_size=B, z_tape=Z, verbose=False)
+    l2m, l2c = BaM(D, tgt.lp, tgt.lp_g, use_lowrank=True).fit(0, Regularizers().custom(lambda i: 100 / (1 + i)), niter=niter, batch_size=B, z_tape=Z, verbose=False, process_group=dist.group.WORLD)
+    e = (relF(l2c, l1c), relF(l2m, l1m), relF(l2c, b1c))
+    if rank == 0: print("BaM low-rank D=%d B=%d sharded-vs-single relF cov %.2e mean %.2e; vs full %.2e" % ((D, B) + e), flush=True)
+    assert e[0] < 2e-5 and e[1] < 2e-5 and e[2] < 1e-4, e
+    t = l2c.clone(); dist.broadcast(t, 0); assert torch.equal(t, l2c)
+# forced revert on the sharded path (gsm.py:125-129): every rank's score callable returns NaN on its third call, so the
+# third update is rejected on every rank by the device-side commit; the exchange counters still advance and the fit must
+# equal the single-GPU fit with the same injection, replicas bit-identical
+D, B, niter = 200, 64, 6
+mean_t, cov_t = orc.dense_gaussian_target(D, 2)
+Pt = torch.as_tensor(np.linalg.inv(cov_t), dtype=torch.float32, device="cuda"); mt = torch.as_tensor(mean_t, dtype=torch.float32, device="cuda")
+Z = np.random.RandomState(4).normal(size=(niter + 1, B, D)).astype(np.float32)
+def make_lp_g():
+    n = {"c": 0}
+    def lp_g(x):
+        n["c"] += 1
+        g = -(x - mt) @ Pt
+        return g * float("nan") if n["c"] == 3 else g
+    return lp_g
+ga = GSM(D, None, make_lp_g()); ma, ca = ga.fit(0, niter=niter, batch_size=B, z_tape=Z, verbose=False, npass=4)
+gb = GSM(D, None, make_lp_g()); mb, cb = gb.fit(0, niter=niter, batch_size=B, z_tape=Z, verbose=False, npass=4, process_group=dist.group.WORLD)
+assert ga.n_reverts == 1 and gb.n_reverts == 1, (ga.n_reverts, gb.n_reverts)
+e = (relF(cb, ca), relF(mb, ma))
+if rank == 0: print("GSM forced revert sharded-vs-single relF cov %.2e mean %.2e" % e, flush=True)
+assert e[0] < 2e-5 and e[1] < 2e-5 and bool(torch.isfinite(cb).all()), e
+t = cb.clone(); dist.broadcast(t, 0); assert torch.equal(t, cb)
 # ensemble of independent fits: each rank fits its slice (no communication), the gathered result equals the unsharded run
 from gsmvi_b200.ensemble import gsm_ensemble_fit, shard_range
 F, D, B, niter = 10, 24, 8, 30
@@ -51,19 +79,78 @@ mu_all, S_all, rev_all = gsm_ensemble_fit(means, covs, key=3, batch_size=B, nite
 mu_loc, S_loc, rev_loc = gsm_ensemble_fit(means, covs, key=3, batch_size=B, niter=niter, process_group=dist.group.WORLD)
 lo, hi = shard_range(F, rank, dist.get_world_size())
 assert torch.equal(S_loc, S_all[lo:hi]) and torch.equal(mu_loc, mu_all[lo:hi]) and torch.equal(rev_loc, rev_all[lo:hi])
+from gsmvi_b200.gsm import release_engines
+release_engines()
 dist.destroy_process_group()
 print("rank", rank, "ok", flush=True)
 '''
 
 
+def _run(tmp_path, text, n, port):
+    script = tmp_path / "worker.py"
+    script.write_text(text)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % n,
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script), ROOT],
+                       capture_output=True, text=True, timeout=1500)
+    sys.stdout.write(r.stdout[-4000:])
+    log = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(log, exist_ok=True)
+    with open(os.path.join(log, "test_multigpu_%dgpu.log" % n), "w") as f:  # retained evidence of the N-rank run
+        f.write(r.stdout[-20000:] + "\n---- stderr ----\n" + r.stderr[-5000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(" ok") == n
+
+
 def test_two_gpu_sharded_fit_matches_single_gpu(tmp_path):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    script = tmp_path / "worker.py"
-    script.write_text(WORKER)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29621", str(script), ROOT],
-                       capture_output=True, text=True, timeout=900)
-    sys.stdout.write(r.stdout[-3000:])
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count(" ok") == 2
+    _run(tmp_path, WORKER, 2, 29621)
+
+
+# 4 and 8 ranks at sizes where the exchange's tile arithmetic is non-trivial: D not a multiple of 128, more lower tiles
+# than ranks, tiles-per-owner that differ between owners; plus the headline shape D = 4096 (528 lower tiles)
+WORKER_N = r'''
+import os, sys
+ROOT = sys.argv[1]
+sys.path.insert(0, os.path.join(ROOT, "gsm-vi_b200")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import numpy as np, torch, torch.distributed as dist
+from gsmvi_b200.gsm import GSM
+from gsmvi_b200.bam import BaM, Regularizers
+from gsmvi_b200.targets import DenseGaussianTarget, dense_gaussian_target
+rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+relF = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+for (D, B, niter) in [(2200, 256, 3), (1000, 64 * world, 4), (4096, 4096, 2)]:
+    mean_t, cov_t = dense_gaussian_target(D, 0)
+    tgt = DenseGaussianTarget(mean_t, cov_t)
+    Z = torch.randn(niter + 1, B, D, generator=torch.Generator().manual_seed(1))
+    m1, c1 = GSM(D, tgt.lp, tgt.lp_g).fit(0, niter=niter, batch_size=B, z_tape=Z, verbose=False)
+    g2 = GSM(D, tgt.lp, tgt.lp_g)
+    m2, c2 = g2.fit(0, niter=niter, batch_size=B, z_tape=Z, verbose=False, process_group=dist.group.WORLD)
+    e = (relF(c2, c1), relF(m2, m1))
+    if rank == 0: print("GSM D=%d B=%d world=%d sharded-vs-single relF cov %.2e mean %.2e reverts %d" % ((D, B, world) + e + (g2.n_reverts,)), flush=True)
+    assert e[0] < 2e-5 and e[1] < 2e-5 and g2.n_reverts == 0, e
+    t = c2.clone(); dist.broadcast(t, 0); assert torch.equal(t, c2)  # replicas bit-identical
+    t = m2.clone(); dist.broadcast(t, 0); assert torch.equal(t, m2)
+    assert torch.equal(c2, c2.t())
+    if D <= 2200:
+        reg = lambda: Regularizers().custom(lambda i: 100 / (1 + i))
+        b1m, b1c = BaM(D, tgt.lp, tgt.lp_g).fit(0, reg(), niter=niter, batch_size=B, z_tape=Z, verbose=False)
+        b2m, b2c = BaM(D, tgt.lp, tgt.lp_g).fit(0, reg(), niter=niter, batch_size=B, z_tape=Z, verbose=False, process_group=dist.group.WORLD)
+        e = (relF(b2c, b1c), relF(b2m, b1m))
+        if rank == 0: print("BaM D=%d B=%d world=%d sharded-vs-single relF cov %.2e mean %.2e" % ((D, B, world) + e), flush=True)
+        assert e[0] < 2e-5 and e[1] < 2e-5, e
+        t = b2c.clone(); dist.broadcast(t, 0); assert torch.equal(t, b2c)
+from gsmvi_b200.gsm import release_engines
+release_engines()
+dist.destroy_process_group()
+print("rank", rank, "ok", flush=True)
+'''
+
+
+@pytest.mark.parametrize("n", [4, 8])
+def test_n_gpu_sharded_fit_matches_single_gpu(tmp_path, n):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < n:
+        pytest.skip("needs %d GPUs" % n)
+    _run(tmp_path, WORKER_N, n, 29630 + n)

@@ -559,6 +559,7 @@ def bam_leg(args, D, B, Bl, npass, world, rank, group, barrier, max_over_ranks, 
            "dtype": "f64 (statistics + solve; sampling / score on the 3xTF32 tensor-core path)",
            "target": {"family": "ill-conditioned Gaussian", "kappa": BAM_KAPPA, "seed": 0, "reg": "%g/(1+i)" % BAM_REG0},
            "ns_iters_mean": k, "reverts": beng.n_reverts, "score_evals_per_s": value * B, "roofline": roofline}
+    beng.close()
     del beng
     torch.cuda.empty_cache()
 

@@ -158,6 +158,106 @@ __global__ void frob_inf64_kernel(const double* __restrict__ A, long long lda, i
   }
 }
 
+// Deterministic form of the reduction above (same quantities): one CTA per row writes the row's sum of squares and
+// absolute row sum to rowbuf[2 i], rowbuf[2 i + 1]; a single CTA then adds / maximises them in a fixed order.  Replicated
+// ranks of a sharded solve take their stopping decisions from this number, so it must not depend on atomic ordering.
+__global__ void frob_rows64_kernel(const double* __restrict__ A, long long lda, int n, double d, double* __restrict__ rowbuf) {
+  const long long i = blockIdx.x;
+  double ss = 0.0, rs = 0.0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const double v = A[i * lda + j];
+    const double e = v - ((i == j) ? d : 0.0);
+    ss += e * e;
+    rs += fabs(v);
+  }
+  __shared__ double s1[256], s2[256];
+  s1[threadIdx.x] = ss;
+  s2[threadIdx.x] = rs;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s1[threadIdx.x] += s1[threadIdx.x + o];
+      s2[threadIdx.x] += s2[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    rowbuf[2 * i] = s1[0];
+    rowbuf[2 * i + 1] = s2[0];
+  }
+}
+__global__ void frob_final64_kernel(const double* __restrict__ rowbuf, int n, double* __restrict__ out) {
+  double ss = 0.0, mx = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    ss += rowbuf[2 * i];
+    mx = fmax(mx, rowbuf[2 * i + 1]);  // NaN rows: fmax drops NaN, the sum of squares keeps it
+  }
+  __shared__ double s1[256], s2[256];
+  s1[threadIdx.x] = ss;
+  s2[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s1[threadIdx.x] += s1[threadIdx.x + o];
+      s2[threadIdx.x] = fmax(s2[threadIdx.x], s2[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[0] = s1[0];
+    out[1] = (s1[0] != s1[0]) ? s1[0] : s2[0];  // a NaN anywhere poisons the norm too
+  }
+}
+
+// ---- tensor-parallel solve across the ranks of a sharded fit: the D x D products of the
+// Newton-Schulz iteration (bam.py:63, get_sqrt bam.py:19-28) are split by rows of the result, each rank's GEMM epilogue
+// stores its rows into every rank's copy of the result (dgemm.cu, peer memory over NVLink), and a barrier separates a
+// product from its consumers.  Every rank therefore holds bit-identical iterates and takes identical decisions.
+struct ShardPtrs {
+  unsigned* cnt[DGEMM_MAX_PEERS];  // the barrier word inside every rank's solve workspace
+};
+__device__ __forceinline__ unsigned ld_acquire_sys64(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Every rank adds one to every rank's barrier word and waits until its own has seen all `world` arrivals of this barrier
+// (the word only grows: target = world * number of barriers so far).  The peers' stores of the kernels before were fenced
+// system-wide by their epilogues; the release / acquire pair orders them before everything after the barrier.
+__global__ void ns_barrier_kernel(ShardPtrs p, int rank, int world, unsigned target, long long timeout_cycles) {
+  if (threadIdx.x < world) {
+    __threadfence_system();
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p.cnt[threadIdx.x]), "r"(1u) : "memory");
+  }
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (static_cast<int>(ld_acquire_sys64(p.cnt[rank]) - target) < 0) {
+      __nanosleep(200);
+      if (timeout_cycles > 0 && clock64() - t0 > timeout_cycles) {
+        printf("gsmvi: BaM solve barrier watchdog (rank %d, have %u want %u)\n", rank, ld_acquire_sys64(p.cnt[rank]), target);
+        __trap();
+      }
+    }
+  }
+}
+// rows [row0, row0 + rows) of an n-column fp64 matrix (leading dimension ld, ld even) from this rank's copy into the same
+// place of every peer's copy: 16-byte stores, consecutive threads on consecutive addresses
+struct BcastArgs {
+  const double* src;
+  double* dst[DGEMM_MAX_PEERS];
+  int ndst;
+  long long count2;  // number of double2 elements
+};
+__global__ void __launch_bounds__(256) peer_bcast_kernel(const BcastArgs a) {
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  const double2* s2 = reinterpret_cast<const double2*>(a.src);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.count2; i += nth) {
+    const double2 v = s2[i];
+    for (int d = 0; d < a.ndst; ++d) reinterpret_cast<double2*>(a.dst[d])[i] = v;
+  }
+  __threadfence_system();
+}
+
 // S32 = (float)(scale*S64) + jitter*I, symmetric by construction of S64 ; bam.py:198-199
 __global__ void bam_finish_cov_kernel(const double* __restrict__ S64, long long lds64, float* __restrict__ S32,
                                       long long lds32, int D, double scale, double jitter) {
@@ -349,6 +449,58 @@ static void dbg_stage(cudaStream_t st, const char* name, const double* A, long l
   fprintf(stderr, "[gsmvi debug] %-22s n=%d frob=%.6e inf=%.6e flag=%d cuda=%d\n", name, n, sqrt(h[0]), h[1], f, (int)e);
 }
 
+// Sharding context of a solve: world == 1 is the single-GPU solve; otherwise peer_ws[r] is rank r's solve workspace
+// (same layout on every rank, own at [rank]) and *epoch_host counts the barriers this workspace has been through.
+struct ShardCtx {
+  int rank = 0, world = 1;
+  double* peer_ws[DGEMM_MAX_PEERS] = {};
+  double* own_ws = nullptr;
+  long long cnt_off = 0;  // offset (in doubles) of the barrier word inside a workspace
+  unsigned* epoch_host = nullptr;
+  long long timeout_cycles = 0;
+};
+
+static int shard_barrier(cudaStream_t st, const ShardCtx& sh) {
+  if (sh.world <= 1) return GSMVI_OK;
+  ShardPtrs p;
+  for (int r = 0; r < DGEMM_MAX_PEERS; ++r)
+    p.cnt[r] = r < sh.world ? reinterpret_cast<unsigned*>(sh.peer_ws[r] + sh.cnt_off) : nullptr;
+  *sh.epoch_host += 1;
+  ns_barrier_kernel<<<1, 32, 0, st>>>(p, sh.rank, sh.world, static_cast<unsigned>(sh.world) * (*sh.epoch_host), sh.timeout_cycles);
+  GSMVI_CUDA(last());
+  return GSMVI_OK;
+}
+
+// rows of an n-row result owned by this rank: 128-row tiles dealt out in contiguous runs
+static inline void shard_rows(const ShardCtx& sh, int n, int* row0, int* rows) {
+  const int tiles = (n + 127) / 128, per = (tiles + sh.world - 1) / sh.world;
+  const int r0 = sh.rank * per * 128;
+  *row0 = r0 < n ? r0 : n;
+  *rows = r0 < n ? ((r0 + per * 128 < n ? r0 + per * 128 : n) - r0) : 0;
+}
+
+// C = alpha * A op(B)^T + diag_add I with A K-major [n, K]: the full product on one GPU, or this rank's rows of it stored
+// into every rank's copy of C (C must lie inside the solve workspace).  No barrier here: the caller places it.
+static int dgemm_sharded(cudaStream_t st, const ShardCtx& sh, int n, int N, int K, const double* A, long long lda, const double* B,
+                         long long ldb, bool b_mn, double* C, long long ldc, DgemmOpts o, const OzCtx& oz) {
+  if (sh.world <= 1) return dgemm_big(st, n, N, K, A, lda, false, B, ldb, b_mn, C, ldc, o, oz);
+  int row0, rows;
+  shard_rows(sh, n, &row0, &rows);
+  if (rows <= 0) return GSMVI_OK;
+  o.row0 = row0;
+  o.ncp = sh.world;
+  for (int r = 0; r < sh.world; ++r) o.Cp[r] = sh.peer_ws[r] + (C - sh.own_ws);
+  return launch_dgemm(st, rows, N, K, A + static_cast<long long>(row0) * lda, lda, false, B, ldb, b_mn, nullptr, ldc, o);
+}
+
+// ||A - d I||_F^2 and ||A||_inf into out[0], out[1], deterministically (rowbuf: 2 n doubles of scratch)
+static int frob_inf64(cudaStream_t st, const double* A, long long ld, int n, double d, double* rowbuf, double* out) {
+  frob_rows64_kernel<<<n, 256, 0, st>>>(A, ld, n, d, rowbuf);
+  frob_final64_kernel<<<1, 256, 0, st>>>(rowbuf, n, out);
+  GSMVI_CUDA(last());
+  return GSMVI_OK;
+}
+
 // Coupled Newton-Schulz square root of the SPD matrix in Y (n x n, overwritten):  on return Y ~= M^{1/2}.
 //   Y0 = M/c, Z0 = I;  T = Z Y;  P = a I + b T;  Y <- Y P;  Z <- P Z        
 // c = ||M||_inf >= lambda_max.  Plain Newton-Schulz is (a, b) = (3/2, -1/2); while the spectrum of T is still wide
@@ -357,14 +509,16 @@ static void dbg_stage(cudaStream_t st, const char* name, const double* A, long l
 // iteration count (19 instead of 38 at kappa(M) = 3.5e11).  lam_min is a lower bound on lambda_min(M).
 // All three products are taken exactly as written (no symmetry shortcut such as Z Y^T): the coupled iteration is
 // stable under rounding only while Y and Z keep their exact coupling - symmetrising either iterate makes it diverge
-// at kappa ~ 1e11 (measured).  Needs 4 scratch n x n buffers.  Synchronises the stream once per iteration
-// to read the residual ||I - Z Y||_F.
+// at kappa ~ 1e11 (measured).  Needs 4 scratch n x n buffers and 2 n doubles (rowbuf).  Synchronises the
+// stream once per iteration to read the residual ||I - Z Y||_F (two launches, fixed summation order: every rank of a
+// sharded solve reads the same bits and stops at the same iteration).
+// Sharded (sh.world > 1): each of the three products is computed by rows across the ranks, the epilogues store into every
+// rank's buffers over NVLink, and two barriers per iteration separate producers from consumers.
 static int ns_sqrt64(cudaStream_t st, double* Y, long long ld, int n, double* Z, double* P, double* Y2, double* Z2,
-                     double* scal_dev, int max_iter, double tol, double lam_min, int* iters_out, int* flag,
-                     const OzCtx& oz = OzCtx()) {
+                     double* scal_dev, double* rowbuf, int max_iter, double tol, double lam_min, int* iters_out, int* flag,
+                     const OzCtx& oz, const ShardCtx& sh) {
   double h[2];
-  GSMVI_CUDA(cudaMemsetAsync(scal_dev, 0, 2 * sizeof(double), st));
-  frob_inf64_kernel<<<n, 256, 0, st>>>(Y, ld, n, 0.0, scal_dev);
+  GSMVI_TRY(frob_inf64(st, Y, ld, n, 0.0, rowbuf, scal_dev));
   GSMVI_CUDA(cudaMemcpyAsync(h, scal_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   GSMVI_CUDA(cudaStreamSynchronize(st));
   const double c = h[1];
@@ -392,21 +546,22 @@ static int ns_sqrt64(cudaStream_t st, double* Y, long long ld, int n, double* Z,
     if (it == 0) {
       // Z0 = I: the products Z Y and P Z are Y and P themselves - one GEMM instead of three
       affine_diag64_kernel<<<grid2(n, n), 256, 0, st>>>(Y, P, ld, n, b, a);                      // P = a I + b Y
-      GSMVI_CUDA(cudaMemsetAsync(scal_dev, 0, 2 * sizeof(double), st));
-      frob_inf64_kernel<<<n, 256, 0, st>>>(P, ld, n, a + b, scal_dev);
-      GSMVI_TRY(dgemm_big(st, n, n, n, Y, ld, false, P, ld, true, Y2, ld, o, oz));               // Y2 = Y P
+      GSMVI_TRY(frob_inf64(st, P, ld, n, a + b, rowbuf, scal_dev));
+      GSMVI_TRY(dgemm_sharded(st, sh, n, n, n, Y, ld, P, ld, true, Y2, ld, o, oz));                // Y2 = Y P
       GSMVI_CUDA(cudaMemcpy2DAsync(Z2, ld * sizeof(double), P, ld * sizeof(double), n * sizeof(double), n,
                                    cudaMemcpyDeviceToDevice, st));                               // Z2 = P
+      GSMVI_TRY(shard_barrier(st, sh));
     } else {
       DgemmOpts p;  // P = a I + b Z Y   (B operand MN-major: the product is exactly Z Y)
       p.alpha = b;
       p.diag_add = a;
-      GSMVI_TRY(dgemm_big(st, n, n, n, Z, ld, false, Y, ld, true, P, ld, p, oz));
-      GSMVI_CUDA(cudaMemsetAsync(scal_dev, 0, 2 * sizeof(double), st));
-      frob_inf64_kernel<<<n, 256, 0, st>>>(P, ld, n, a + b, scal_dev);  // ||P - (a+b) I||_F = |b| ||I - Z Y||_F
-      GSMVI_TRY(dgemm_big(st, n, n, n, Y, ld, false, P, ld, true, Y2, ld, o, oz));   // Y2 = Y P
+      GSMVI_TRY(dgemm_sharded(st, sh, n, n, n, Z, ld, Y, ld, true, P, ld, p, oz));
+      GSMVI_TRY(shard_barrier(st, sh));
+      GSMVI_TRY(frob_inf64(st, P, ld, n, a + b, rowbuf, scal_dev));  // ||P - (a+b) I||_F = |b| ||I - Z Y||_F
+      GSMVI_TRY(dgemm_sharded(st, sh, n, n, n, Y, ld, P, ld, true, Y2, ld, o, oz));   // Y2 = Y P
       // the last round only needs Y: its Z update is skipped
-      if (!last_round) GSMVI_TRY(dgemm_big(st, n, n, n, P, ld, false, Z, ld, true, Z2, ld, o, oz));   // Z2 = P Z
+      if (!last_round) GSMVI_TRY(dgemm_sharded(st, sh, n, n, n, P, ld, Z, ld, true, Z2, ld, o, oz));   // Z2 = P Z
+      GSMVI_TRY(shard_barrier(st, sh));
     }
     double* t = Y; Y = Y2; Y2 = t;
     t = Z; Z = Z2; Z2 = t;
@@ -445,19 +600,30 @@ size_t bam_stats_workspace_bytes(int B, int D) {
   return static_cast<size_t>((2LL * B + D + 2) * ld) * sizeof(double);
 }
 
-size_t bam_solve_workspace_bytes(int B, int D, int lowrank) {
+// Layout of the full solve's workspace (doubles): 6 D x ld buffers | Q, W [D x ldk] | two sets of diagonal-block inverses |
+// rowbuf [2 max(D, K)] | barrier word (8 doubles) | scalars (16) | (1 KiB aligned) int8 digit planes of the optional
+// tensor-core products.  bam_solve_cnt_offset() is where a sharded solve's barrier word lives (same on every rank).
+static inline long long bam_full_fixed_doubles(int B, int D) {
   const long long ld = rup(D, 8);
   const long long nblk = (D + NB64 - 1) / NB64;
+  const long long K = B + 1, ldk = rup(K, 8);
+  return 6 * D * ld + 2 * D * ldk + 2 * nblk * NB64 * NB64;
+}
+long long bam_solve_cnt_offset(int B, int D) {
+  const long long K = B + 1;
+  return bam_full_fixed_doubles(B, D) + 2 * rup(D > K ? D : K, 8);
+}
+
+size_t bam_solve_workspace_bytes(int B, int D, int lowrank) {
+  const long long ld = rup(D, 8);
   const long long K = B + 1, ldk = rup(K, 8), kblk = (K + NB64 - 1) / NB64;
   if (!lowrank) {
-    // 6 D x D fp64 buffers + Q, W [D x ldk] + 2 sets of diagonal-block inverses + scalars (+ the int8 digit planes and
-    // fp64 accumulator of the tensor-core products, 1 KiB aligned, when D is large enough to use them)
-    size_t b = static_cast<size_t>(6 * D * ld + 2 * D * ldk + 2 * nblk * NB64 * NB64 + 16) * sizeof(double);
+    size_t b = static_cast<size_t>(bam_solve_cnt_offset(B, D) + 8 + 16) * sizeof(double);
     if (D >= 1024) b = static_cast<size_t>(rup(static_cast<long long>(b), 1024)) + 1024 + oz_workspace_bytes(D, D, D > K ? D : K, 8);
     return b;
   }
-  // V [D x ld], S [D x ld], Q, A = VQ, W = A F [D x ldk], 6 K x K buffers, inverses, scalars
-  return static_cast<size_t>(2 * D * ld + 3 * D * ldk + 6 * K * ldk + kblk * NB64 * NB64 + 16) * sizeof(double);
+  // V [D x ld], S [D x ld], Q, A = VQ, W = A F [D x ldk], 6 K x K buffers, inverses, rowbuf [2 K], scalars
+  return static_cast<size_t>(2 * D * ld + 3 * D * ldk + 6 * K * ldk + kblk * NB64 * NB64 + 2 * ldk + 16) * sizeof(double);
 }
 
 int bam_stats(cudaStream_t st, const float* X, long long ldx, const float* G, long long ldg, int B, int D, int Btot,
@@ -488,11 +654,47 @@ int bam_stats(cudaStream_t st, const float* X, long long ldx, const float* G, lo
   return GSMVI_OK;
 }
 
+// GSMVI_BAM_TIMING=1: CUDA-event stamps between the stages of the solve, printed per call (synchronises; diagnostics only)
+struct SolveTimer {
+  bool on;
+  cudaStream_t st;
+  cudaEvent_t ev[12];
+  const char* name[12];
+  int n = 0;
+  explicit SolveTimer(cudaStream_t s) : st(s) {
+    static int v = -1;
+    if (v < 0) v = getenv("GSMVI_BAM_TIMING") ? 1 : 0;
+    on = v == 1;
+  }
+  void mark(const char* what) {
+    if (!on || n >= 12) return;
+    cudaEventCreate(&ev[n]);
+    cudaEventRecord(ev[n], st);
+    name[n++] = what;
+  }
+  void report(int rank, int iters) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    if (rank == 0) {
+      fprintf(stderr, "[gsmvi bam solve timing, ms] ns_iters %d |", iters);
+      for (int i = 1; i < n; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+        fprintf(stderr, " %s %.3f", name[i], ms);
+      }
+      fprintf(stderr, "\n");
+    }
+    for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+  }
+};
+
 int bam_solve_full(cudaStream_t st, const double* stats_ws, int B, int D, int Btot, const float* mu0, const float* S0,
                    long long lds0, double reg, double jitter, float* mu_out, float* S_out, long long ldso, double* ws,
-                   int max_ns, int* ns_iters_host, int* flag, int world, int phase) {
+                   int max_ns, int* ns_iters_host, int* flag, int world, int phase, const BamShard* shard) {
   // phase 0: everything.  Sharded batch (world > 1): phase 1 stops after this rank's partial
   // M_r = I/world + 4 W_r W_r^T (D x ld doubles at ws + 3 D ld: sum it over ranks), phase 2 resumes at the square root.
+  // With `shard` (peer-mapped workspaces) phase 2 is tensor-parallel: Newton-Schulz products, T = L R^-T and S = 2 T T^T
+  // are computed by rows across the ranks; without it every rank repeats the whole of phase 2.
   const long long ld = rup(D, 8);
   const int K = B + 1;
   const long long ldk = rup(K, 8);
@@ -511,18 +713,42 @@ int bam_solve_full(cudaStream_t st, const double* stats_ws, int B, int D, int Bt
   const long long nblk = (D + NB64 - 1) / NB64;
   double* dinvL = W + D * ldk;
   double* dinvR = dinvL + nblk * NB64 * NB64;
-  double* scal = dinvR + nblk * NB64 * NB64;
+  double* rowbuf = dinvR + nblk * NB64 * NB64;
+  double* cntw = ws + bam_solve_cnt_offset(B, D);
+  double* scal = cntw + 8;
   OzCtx oz;
   if (D >= 1024 && oz_slices_env() >= 2) {
     oz.ws = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(scal + 16) + 1023) & ~static_cast<uintptr_t>(1023));
     oz.slices = oz_slices_env();
   }
+  ShardCtx sh;
+  if (shard && world > 1 && phase == 2) {
+    if (shard->world != world || world > DGEMM_MAX_PEERS || !shard->epoch_host) return GSMVI_EINVAL;
+    sh.rank = shard->rank;
+    sh.world = world;
+    sh.own_ws = ws;
+    sh.cnt_off = bam_solve_cnt_offset(B, D);
+    sh.epoch_host = shard->epoch_host;
+    for (int r = 0; r < world; ++r) sh.peer_ws[r] = static_cast<double*>(shard->peer_ws[r]);
+    if (sh.peer_ws[sh.rank] != ws) return GSMVI_EINVAL;
+    static long long tmo = -1;
+    if (tmo < 0) {
+      const char* e = getenv("GSMVI_COMM_TIMEOUT_S");
+      const double sec = e ? atof(e) : 300.0;
+      tmo = sec <= 0.0 ? 0 : static_cast<long long>(sec * 2.0e9);
+    }
+    sh.timeout_cycles = tmo;
+    oz = OzCtx();  // the int8 path has no sharded form
+  }
+  SolveTimer tmr(st);
+  tmr.mark("start");
   if (phase != 2) {
   GSMVI_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
   bam_v_kernel<<<grid2(D, D), 256, 0, st>>>(C, ld, S0, lds0, xbar, mu0, reg, b1, ld, D);
   dbg_stage(st, "V", b1, ld, D, scal, flag);
   GSMVI_TRY(potrf64_inplace(st, b1, ld, D, dinvL, flag));                          // V = L L^T
   dbg_stage(st, "L=chol(V)", b1, ld, D, scal, flag);
+  tmr.mark("V+chol(V)");
   bam_build_q_kernel<<<dim3((K + 255) / 256, D), 256, 0, st>>>(Tc + static_cast<long long>(B) * ld, ld, gbar, B, D, reg,
                                                                Btot, world, Q, ldk);  // sum over ranks of Q Q^T = U
   DgemmOpts o;
@@ -535,26 +761,58 @@ int bam_solve_full(cudaStream_t st, const double* stats_ws, int B, int D, int Bt
   m.mirror = true;
   GSMVI_TRY(dgemm_big(st, D, D, K, W, ldk, false, W, ldk, false, b3, ld, m, oz));   // M = I + 4 W W^T  (= I + 4 L^T U L)
   dbg_stage(st, "M", b3, ld, D, scal, flag);
+  tmr.mark("W,M");
   }
   if (phase == 1) {
+    tmr.report(shard ? shard->rank : 0, 0);
     GSMVI_CUDA(last());
     return GSMVI_OK;
   }
   int iters = 0;
-  GSMVI_TRY(ns_sqrt64(st, b3, ld, D, b2, b4, b5, b0, scal, max_ns, 1e-11, 1.0, &iters, flag, oz));  // b3 = N = M^{1/2}
+  GSMVI_TRY(ns_sqrt64(st, b3, ld, D, b2, b4, b5, b0, scal, rowbuf, max_ns, 1e-11, 1.0, &iters, flag, oz, sh));  // b3 = N = M^{1/2}
   if (ns_iters_host) *ns_iters_host = iters;
   dbg_stage(st, "N=sqrt(M)", b3, ld, D, scal, flag);
+  tmr.mark("newton-schulz");
   scale_diag64_kernel<<<grid2(D, D), 256, 0, st>>>(b3, ld, D, 1.0, 1.0);          // I + N
   GSMVI_TRY(potrf64_inplace(st, b3, ld, D, dinvR, flag));                          // I + N = R R^T
   dbg_stage(st, "R=chol(I+N)", b3, ld, D, scal, flag);
-  GSMVI_TRY(trsm64_right_lt(st, b1, ld, b3, ld, dinvR, b4, ld, D, D));             // T = L R^{-T}
-  dbg_stage(st, "T=L R^-T", b4, ld, D, scal, flag);
-  DgemmOpts s;
-  s.tri = true;
-  s.mirror = true;
-  GSMVI_TRY(dgemm_big(st, D, D, D, b4, ld, false, b4, ld, false, b5, ld, s, oz));   // b5 = T T^T ; S = 2 b5
+  tmr.mark("chol(I+N)");
+  if (sh.world > 1) {
+    // rows of T = L R^{-T} are independent: this rank solves its rows, sends them to every rank, then computes its rows of
+    // S / 2 = T T^T with the all-gather fused into the GEMM epilogue
+    int row0, rows;
+    shard_rows(sh, D, &row0, &rows);
+    if (rows > 0) {
+      const long long off = static_cast<long long>(row0) * ld;
+      GSMVI_TRY(trsm64_right_lt(st, b1 + off, ld, b3, ld, dinvR, b4 + off, ld, rows, D));
+      BcastArgs ba;
+      ba.src = b4 + off;
+      ba.ndst = 0;
+      for (int r = 0; r < sh.world; ++r)
+        if (r != sh.rank) ba.dst[ba.ndst++] = sh.peer_ws[r] + (b4 - ws) + off;
+      ba.count2 = static_cast<long long>(rows) * ld / 2;
+      peer_bcast_kernel<<<296, 256, 0, st>>>(ba);
+    }
+    GSMVI_TRY(shard_barrier(st, sh));
+    tmr.mark("trsm+bcast");
+    DgemmOpts s;
+    GSMVI_TRY(dgemm_sharded(st, sh, D, D, D, b4, ld, b4, ld, false, b5, ld, s, oz));  // rows of T T^T
+    GSMVI_TRY(shard_barrier(st, sh));
+    tmr.mark("T T^T");
+  } else {
+    GSMVI_TRY(trsm64_right_lt(st, b1, ld, b3, ld, dinvR, b4, ld, D, D));             // T = L R^{-T}
+    dbg_stage(st, "T=L R^-T", b4, ld, D, scal, flag);
+    tmr.mark("trsm");
+    DgemmOpts s;
+    s.tri = true;
+    s.mirror = true;
+    GSMVI_TRY(dgemm_big(st, D, D, D, b4, ld, false, b4, ld, false, b5, ld, s, oz));   // b5 = T T^T ; S = 2 b5
+    tmr.mark("T T^T");
+  }
   bam_mean_kernel<<<(D + 7) / 8, 256, 0, st>>>(b5, ld, 2.0, gbar, xbar, mu0, reg, mu_out, D);
   bam_finish_cov_kernel<<<grid2(D, D), 256, 0, st>>>(b5, ld, S_out, ldso, D, 2.0, jitter);
+  tmr.mark("mean+finish");
+  tmr.report(sh.rank, iters);
   GSMVI_CUDA(last());
   return GSMVI_OK;
 }
@@ -583,7 +841,8 @@ int bam_solve_lowrank(cudaStream_t st, const double* stats_ws, int B, int D, int
   double* k4 = k3 + K * ldk;
   double* k5 = k4 + K * ldk;
   double* dinv = k5 + K * ldk;
-  double* scal = dinv + kblk * NB64 * NB64;
+  double* rowbuf = dinv + kblk * NB64 * NB64;
+  double* scal = rowbuf + 2 * ldk;
   GSMVI_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
   bam_v_kernel<<<grid2(D, D), 256, 0, st>>>(C, ld, S0, lds0, xbar, mu0, reg, V, ld, D);
   bam_build_q_kernel<<<dim3((K + 255) / 256, D), 256, 0, st>>>(Tc + static_cast<long long>(B) * ld, ld, gbar, B, D, reg,
@@ -596,7 +855,7 @@ int bam_solve_lowrank(cudaStream_t st, const double* stats_ws, int B, int D, int
   h.mirror = true;
   GSMVI_TRY(launch_dgemm(st, K, K, D, A, ldk, true, Q, ldk, true, k0, ldk, h));    // H = A^T Q + I/4
   int iters = 0;
-  GSMVI_TRY(ns_sqrt64(st, k0, ldk, K, k1, k2, k3, k4, scal, max_ns, 1e-11, 0.25, &iters, flag));
+  GSMVI_TRY(ns_sqrt64(st, k0, ldk, K, k1, k2, k3, k4, scal, rowbuf, max_ns, 1e-11, 0.25, &iters, flag, OzCtx(), ShardCtx()));
   if (ns_iters_host) *ns_iters_host = iters;
   scale_diag64_kernel<<<grid2(K, K), 256, 0, st>>>(k0, ldk, K, 1.0, 0.5);          // I/2 + H^{1/2}
   GSMVI_TRY(potrf64_inplace(st, k0, ldk, K, dinv, flag));                          // = R2 R2^T

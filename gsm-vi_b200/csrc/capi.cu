@@ -239,6 +239,18 @@ int gsmvi_bam_solve(const void* stats_workspace, int B, int D, int B_total, cons
                         phase);
 }
 
+int gsmvi_bam_solve_sharded(const void* stats_workspace, int B, int D, int B_total, const float* mu0, const float* Sigma0,
+                            long long lds0, double reg, double jitter, float* mu_out, float* Sigma_out, long long ldso,
+                            void* solve_workspace, int max_ns_iters, int* ns_iters_host, int* bad_flag,
+                            const gsmvi_bam_shard* shard, void* stream) {
+  if (!stats_workspace || !mu0 || !Sigma0 || !mu_out || !Sigma_out || !solve_workspace || !bad_flag || B <= 0 || D <= 0 ||
+      !shard || shard->world < 2 || shard->world > 8 || shard->rank < 0 || shard->rank >= shard->world)
+    return GSMVI_EINVAL;
+  return bam_solve_full(S(stream), static_cast<const double*>(stats_workspace), B, D, B_total, mu0, Sigma0, lds0, reg, jitter, mu_out,
+                        Sigma_out, ldso, static_cast<double*>(solve_workspace), max_ns_iters, ns_iters_host, bad_flag,
+                        shard->world, 2, shard);
+}
+
 int gsmvi_bam_solve_lowrank(const void* stats_workspace, int B, int D, int B_total, const float* mu0, const float* Sigma0,
                             long long lds0, double reg, double jitter, float* mu_out, float* Sigma_out, long long ldso,
                             void* solve_workspace, int max_ns_iters, int* ns_iters_host, int* bad_flag, void* stream) {

@@ -3,12 +3,13 @@
 // Why fp64: the solve S = 2 L (I + (I + 4 L^T U L)^{1/2})^{-1} L^T (gsmvi/bam.py:59-65 symmetrised) mixes scales of
 // 1 and ~1e9; in fp32 the "I +" is rounded away and the update is garbage or NaN (SURVEY.md section 7 hard part 1,
 // section 9 table C; the reference itself runs BaM under jax_enable_x64, examples/example_bam.py:14-15).  tcgen05 has
-// no f64 kind, and on B200 the FP64 CUDA-core and DMMA rates are the same, so this is a register-tiled DFMA kernel:
-// 128x128 CTA tile, BK = 16, 256 threads each owning an 8x8 micro-tile, double-buffered through registers.  A thread's
-// rows are the pairs {2ty, 2ty+1} + 32a and its columns {2tx, 2tx+1} + 32b (a, b = 0..3), so the 16 lanes that differ
-// in tx read 16 consecutive 16-byte words per shared-memory load (conflict-free) and lanes that share ty broadcast:
-// 12 wavefronts per 64 DFMA (the first version, 8x4 tiles with 32-byte-strided reads, needed 0.85 per DFMA and ran the
-// FP64 pipe at 41%, profiles/r01_ncu_dgemm_summary.txt).
+// no f64 kind, so the products run on the FP64 tensor-core path (mma.sync.m16n8k16.f64): 128 x 128 CTA tile, eight warps
+// of 64 x 32, BK = 16.  Two kernels: dgemm_pipe_kernel moves the operand tiles with cp.async through a three-stage ring
+// (30.9 TFLOP/s at 4096^3, cuBLAS DGEMM on the same part 35.3; the default for every large aligned product);
+// dgemm_mma16_kernel stages through registers (any alignment, 64 x 64 tiles for small problems).  The first two
+// generations (DFMA register tiles, m8n8k4) were removed after round 1.
+// Row-sharded mode (tensor-parallel Newton-Schulz across GPUs): the epilogue stores every result element into this GPU's
+// and its NVLink peers' copies of the result matrix, so the all-gather of a sharded product rides on the GEMM itself.
 // Operand conventions match tc_gemm.cuh: K-major operand = [rows, K] row-major, MN-major = [K, rows] row-major.
 #include "dev_once.cuh"
 #include "dgemm.cuh"
@@ -32,6 +33,11 @@ struct DgemmArgs {
   double* C;
   long long ldc;
   int tri, mirror, krange;
+  // row-sharded products (tensor-parallel Newton-Schulz, bam_solve.cu): the M rows computed here are rows row0 .. row0+M-1
+  // of the full result (diag_add, tri, Cin and the stores use the global row), and every finished element is stored into
+  // the ncp full-size result matrices Cp[] - this GPU's and its NVLink peers' (the all-gather rides on the epilogue)
+  int row0, ncp;
+  double* Cp[DGEMM_MAX_PEERS];
 };
 
 // Load a ROWS x DBK tile (rows r0.., k from k0) into registers: each thread takes ROWS*DBK/256 elements.
@@ -57,117 +63,12 @@ __device__ __forceinline__ void dload(const double* __restrict__ P, long long ld
   }
 }
 
-template <int ROWS, bool MN>
-__device__ __forceinline__ void dstore(double* __restrict__ S, const double (&reg)[ROWS * DBK / DTHREADS]) {
-  constexpr int PER = ROWS * DBK / DTHREADS;
-#pragma unroll
-  for (int e = 0; e < PER; ++e) {
-    const int idx = threadIdx.x + e * DTHREADS;
-    int r, k;
-    if (MN) {
-      r = idx % ROWS;
-      k = idx / ROWS;
-    } else {
-      k = idx % DBK;
-      r = idx / DBK;
-    }
-    S[k * (ROWS + 2) + r] = reg[e];  // smem layout [k][row], +2 padding
-  }
-}
-
-// DBM = DBN = 128 (8x8 per thread) for large problems, 64 (4x4 per thread, 2 CTAs/SM) when 128-tiles would not fill the GPU.
-template <int DBM, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(DTHREADS, (DBM == 128) ? 1 : 2) dgemm_kernel(const DgemmArgs a) {
-  constexpr int DBN = DBM, TM = DBM / 16;
-  __shared__ __align__(16) double As[DBK * (DBM + 2)];
-  __shared__ __align__(16) double Bs[DBK * (DBN + 2)];
-  int tm, tn;
-  {
-    const int tiles_n = (a.N + DBN - 1) / DBN;
-    tm = blockIdx.x / tiles_n;
-    tn = blockIdx.x % tiles_n;
-    if (a.tri && tn > tm) return;  // lower tiles only
-  }
-  const int m0 = tm * DBM, n0 = tn * DBN;
-  int k_begin = 0, k_end = a.K;
-  if (a.krange & KR_A_LOWER) k_end = min(k_end, m0 + DBM);
-  if (a.krange & KR_B_LOWER) k_end = min(k_end, n0 + DBN);
-  if (a.krange & KR_A_UPPER) k_begin = max(k_begin, m0);
-  if (a.krange & KR_B_UPPER) k_begin = max(k_begin, n0);
-  k_begin = (k_begin / DBK) * DBK;
-
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads
-  double acc[TM][TM];
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < TM; ++j) acc[i][j] = 0.0;
-
-  double ra[DBM * DBK / DTHREADS], rb[DBN * DBK / DTHREADS];
-  if (k_begin < k_end) {
-    dload<DBM, A_MN>(a.A, a.lda, a.M, a.K, m0, k_begin, ra);
-    dload<DBN, B_MN>(a.B, a.ldb, a.N, a.K, n0, k_begin, rb);
-  }
-  for (int k0 = k_begin; k0 < k_end; k0 += DBK) {
-    __syncthreads();
-    dstore<DBM, A_MN>(As, ra);
-    dstore<DBN, B_MN>(Bs, rb);
-    __syncthreads();
-    if (k0 + DBK < k_end) {
-      dload<DBM, A_MN>(a.A, a.lda, a.M, a.K, m0, k0 + DBK, ra);
-      dload<DBN, B_MN>(a.B, a.ldb, a.N, a.K, n0, k0 + DBK, rb);
-    }
-#pragma unroll
-    for (int k = 0; k < DBK; ++k) {
-      double av[TM], bv[TM];
-      const double* ap = As + k * (DBM + 2) + 2 * ty;
-      const double* bp = Bs + k * (DBN + 2) + 2 * tx;
-#pragma unroll
-      for (int q = 0; q < TM / 2; ++q) {
-        const double2 ta = *reinterpret_cast<const double2*>(ap + 32 * q);
-        av[2 * q] = ta.x;
-        av[2 * q + 1] = ta.y;
-        const double2 tb = *reinterpret_cast<const double2*>(bp + 32 * q);
-        bv[2 * q] = tb.x;
-        bv[2 * q + 1] = tb.y;
-      }
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TM; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
-    }
-  }
-  // epilogue: element (i, j) of the micro-tile is row m0 + 32 (i/2) + 2 ty + (i&1), column n0 + 32 (j/2) + 2 tx + (j&1)
-#pragma unroll
-  for (int i = 0; i < TM; ++i) {
-    const int m = m0 + 32 * (i >> 1) + 2 * ty + (i & 1);
-    if (m >= a.M) continue;
-#pragma unroll
-    for (int j = 0; j < TM; ++j) {
-      const int n = n0 + 32 * (j >> 1) + 2 * tx + (j & 1);
-      if (n >= a.N) continue;
-      if (a.tri && n > m) continue;
-      double v = a.alpha * acc[i][j];
-      if (a.beta != 0.0) v += a.beta * a.Cin[static_cast<long long>(m) * a.ldcin + n];
-      if (m == n) v += a.diag_add;
-      a.C[static_cast<long long>(m) * a.ldc + n] = v;
-      if (a.mirror && n != m) a.C[static_cast<long long>(n) * a.ldc + m] = v;
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ DMMA variant
 // Same tiling and register-staged double buffering, but the inner product runs on the FP64 tensor-core path
 // (mma.sync m8n8k4): a warp owns a (DBM/2) x (DBN/4) sub-tile as 8x8 accumulator blocks, operand fragments are one
 // 8-byte shared-memory load per thread and feed 4 (A) / 8 (B) MMAs each, so the kernel needs 12 shared-memory wavefronts
 // per 32 MMAs where the DFMA version needs 12 per 64 FMAs and is co-limited by shared-memory bandwidth.
 // smem layout [k][row] with row stride DBM + 4 doubles: the 4 (k) x 8 (row) fragment touches 32 distinct 8-byte slots.
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
-
 // m16n8k16: A fragment a_i at row g + 8 (i & 1), k = t + 4 (i >> 1); B fragment b_i at k = t + 4 i, column g;
 // C fragment c0, c1 at row g, columns 2t, 2t+1 and c2, c3 at row g + 8 (g = lane / 4, t = lane % 4).
 __device__ __forceinline__ void dmma16816(double (&c)[4], const double (&a)[8], const double (&b)[4]) {
@@ -203,83 +104,55 @@ __device__ __forceinline__ int sidx(int r, int k) {
   return MN ? k * (ROWS + 4) + r : r * (DBK + 4) + k;
 }
 
-template <int DBM, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(DTHREADS, (DBM == 128) ? 1 : 2) dgemm_mma_kernel(const DgemmArgs a) {
-  constexpr int DBN = DBM;
-  constexpr int WM = DBM / 2, WN = DBN / 4;  // warp sub-tile (8 warps as 2 x 4)
-  constexpr int BI = WM / 8, BJ = WN / 8;    // 8x8 blocks per warp
-  __shared__ __align__(16) double As[DBM * (DBK + 4)];  // covers both [row][k+4] and [k][row+4]
-  __shared__ __align__(16) double Bs[DBN * (DBK + 4)];
-  int tm, tn;
-  {
-    const int tiles_n = (a.N + DBN - 1) / DBN;
-    tm = blockIdx.x / tiles_n;
-    tn = blockIdx.x % tiles_n;
-    if (a.tri && tn > tm) return;  // lower tiles only
-  }
-  const int m0 = tm * DBM, n0 = tn * DBN;
-  int k_begin = 0, k_end = a.K;
-  if (a.krange & KR_A_LOWER) k_end = min(k_end, m0 + DBM);
-  if (a.krange & KR_B_LOWER) k_end = min(k_end, n0 + DBN);
-  if (a.krange & KR_A_UPPER) k_begin = max(k_begin, m0);
-  if (a.krange & KR_B_UPPER) k_begin = max(k_begin, n0);
-  k_begin = (k_begin / DBK) * DBK;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wr = (warp >> 2) * WM, wc = (warp & 3) * WN;  // this warp's sub-tile origin inside the CTA tile
-  const int fr = lane >> 2, fk = lane & 3;                 // fragment row / k of this lane
-  double acc[BI][BJ][2];
+// Epilogue shared by the kernels below: fragment layout of m16n8k16 (c0, c1 at row g, columns 2t, 2t+1; c2, c3 at row g+8).
+template <int BI, int BJ>
+__device__ __forceinline__ void dgemm_epilogue(const DgemmArgs& a, const double (&acc)[BI][BJ][4], int m0, int n0, int wr, int wc,
+                                               int fg, int ft) {
 #pragma unroll
   for (int i = 0; i < BI; ++i)
 #pragma unroll
-    for (int j = 0; j < BJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  double ra[DBM * DBK / DTHREADS], rb[DBN * DBK / DTHREADS];
-  if (k_begin < k_end) {
-    dload<DBM, A_MN>(a.A, a.lda, a.M, a.K, m0, k_begin, ra);
-    dload<DBN, B_MN>(a.B, a.ldb, a.N, a.K, n0, k_begin, rb);
-  }
-  for (int k0 = k_begin; k0 < k_end; k0 += DBK) {
-    __syncthreads();
-    dstore4<DBM, A_MN>(As, ra);
-    dstore4<DBN, B_MN>(Bs, rb);
-    __syncthreads();
-    if (k0 + DBK < k_end) {
-      dload<DBM, A_MN>(a.A, a.lda, a.M, a.K, m0, k0 + DBK, ra);
-      dload<DBN, B_MN>(a.B, a.ldb, a.N, a.K, n0, k0 + DBK, rb);
-    }
+    for (int h = 0; h < 2; ++h) {
+      const int m = m0 + wr + 16 * i + fg + 8 * h;
+      if (m >= a.M) continue;
+      const long long gm = a.row0 + m;  // row of the full result
 #pragma unroll
-    for (int k4 = 0; k4 < DBK; k4 += 4) {
-      double af[BI], bf[BJ];
+      for (int j = 0; j < BJ; ++j) {
+        const int n = n0 + wc + 8 * j + 2 * ft;
+        double v[2];
 #pragma unroll
-      for (int i = 0; i < BI; ++i) af[i] = As[sidx<DBM, A_MN>(wr + fr + 8 * i, k4 + fk)];
+        for (int u = 0; u < 2; ++u) {
+          v[u] = a.alpha * acc[i][j][2 * h + u];
+          if (n + u < a.N) {
+            if (a.beta != 0.0) v[u] += a.beta * a.Cin[gm * a.ldcin + n + u];
+            if (gm == n + u) v[u] += a.diag_add;
+          }
+        }
+        if (a.ncp > 0) {
+          // every destination gets the pair as one 16-byte store where alignment allows (peer stores cross NVLink)
+          const bool pair = (n + 1 < a.N) && ((a.ldc & 1) == 0);
+          for (int d = 0; d < a.ncp; ++d) {
+            double* dst = a.Cp[d] + gm * a.ldc + n;
+            if (pair && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+              *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+            } else {
+              if (n < a.N) dst[0] = v[0];
+              if (n + 1 < a.N) dst[1] = v[1];
+            }
+          }
+          continue;
+        }
 #pragma unroll
-      for (int j = 0; j < BJ; ++j) bf[j] = Bs[sidx<DBN, B_MN>(wc + fr + 8 * j, k4 + fk)];
-#pragma unroll
-      for (int i = 0; i < BI; ++i)
-#pragma unroll
-        for (int j = 0; j < BJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-    }
-  }
-  // epilogue: block (i, j): lane holds row 8 i + lane / 4, columns 8 j + 2 (lane % 4) + {0, 1} of the warp sub-tile
-#pragma unroll
-  for (int i = 0; i < BI; ++i) {
-    const int m = m0 + wr + 8 * i + fr;
-    if (m >= a.M) continue;
-#pragma unroll
-    for (int j = 0; j < BJ; ++j)
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int n = n0 + wc + 8 * j + 2 * fk + u;
-        if (n >= a.N) continue;
-        if (a.tri && n > m) continue;
-        double v = a.alpha * acc[i][j][u];
-        if (a.beta != 0.0) v += a.beta * a.Cin[static_cast<long long>(m) * a.ldcin + n];
-        if (m == n) v += a.diag_add;
-        a.C[static_cast<long long>(m) * a.ldc + n] = v;
-        if (a.mirror && n != m) a.C[static_cast<long long>(n) * a.ldc + m] = v;
+        for (int u = 0; u < 2; ++u) {
+          if (n + u >= a.N) continue;
+          if (a.tri && n + u > gm) continue;
+          a.C[gm * a.ldc + n + u] = v[u];
+          if (a.mirror && n + u != gm) a.C[static_cast<long long>(n + u) * a.ldc + gm] = v[u];
+        }
       }
-  }
+    }
+  // peer stores must be performed system-wide before this grid counts as finished: the barrier kernel that follows
+  // signals the peers with a release that is only cumulative over what this GPU has already made visible
+  if (a.ncp > 1) __threadfence_system();
 }
 
 template <int DBM, bool A_MN, bool B_MN>
@@ -342,26 +215,7 @@ __global__ void __launch_bounds__(DTHREADS, (DBM == 128) ? 1 : 2) dgemm_mma16_ke
 #pragma unroll
       for (int j = 0; j < BJ; ++j) dmma16816(acc[i][j], af[i], bf[j]);
   }
-#pragma unroll
-  for (int i = 0; i < BI; ++i)
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int m = m0 + wr + 16 * i + fg + 8 * h;
-      if (m >= a.M) continue;
-#pragma unroll
-      for (int j = 0; j < BJ; ++j)
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int n = n0 + wc + 8 * j + 2 * ft + u;
-          if (n >= a.N) continue;
-          if (a.tri && n > m) continue;
-          double v = a.alpha * acc[i][j][2 * h + u];
-          if (a.beta != 0.0) v += a.beta * a.Cin[static_cast<long long>(m) * a.ldcin + n];
-          if (m == n) v += a.diag_add;
-          a.C[static_cast<long long>(m) * a.ldc + n] = v;
-          if (a.mirror && n != m) a.C[static_cast<long long>(n) * a.ldc + m] = v;
-        }
-    }
+  dgemm_epilogue<BI, BJ>(a, acc, m0, n0, wr, wc, fg, ft);
 }
 
 // ------------------------------------------------------------------------------------------------ pipelined DMMA variant
@@ -477,59 +331,31 @@ __global__ void __launch_bounds__(DTHREADS, 1) dgemm_pipe_kernel(const DgemmArgs
       for (int j = 0; j < BJ; ++j) dmma16816(acc[i][j], af[i], bf[j]);
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < BI; ++i)
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int m = m0 + wr + 16 * i + fg + 8 * h;
-      if (m >= a.M) continue;
-#pragma unroll
-      for (int j = 0; j < BJ; ++j)
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int n = n0 + wc + 8 * j + 2 * ft + u;
-          if (n >= a.N) continue;
-          if (a.tri && n > m) continue;
-          double v = a.alpha * acc[i][j][2 * h + u];
-          if (a.beta != 0.0) v += a.beta * a.Cin[static_cast<long long>(m) * a.ldcin + n];
-          if (m == n) v += a.diag_add;
-          a.C[static_cast<long long>(m) * a.ldc + n] = v;
-          if (a.mirror && n != m) a.C[static_cast<long long>(n) * a.ldc + m] = v;
-        }
-    }
-}
-
-static int dgemm_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("GSMVI_DGEMM");  // fma: DFMA kernel; mma8: m8n8k4; mma16: m16n8k16; default: pipelined m16n8k16
-    v = !e ? 3 : (e[0] == 'f' ? 0 : ((e[0] == 'm' && e[3] == '8') ? 1 : ((e[0] == 'm') ? 2 : 3)));
-  }
-  return v;
+  dgemm_epilogue<BI, BJ>(a, acc, m0, n0, wr, wc, fg, ft);
 }
 
 int launch_dgemm(cudaStream_t stream, int M, int N, int K, const double* A, long long lda, bool a_mn, const double* B,
                  long long ldb, bool b_mn, double* C, long long ldc, const DgemmOpts& o) {
-  if (M <= 0 || N <= 0 || K < 0 || !C || (K > 0 && (!A || !B))) return GSMVI_EINVAL;
+  if (M <= 0 || N <= 0 || K < 0 || (K > 0 && (!A || !B))) return GSMVI_EINVAL;
+  if (o.ncp == 0 && !C) return GSMVI_EINVAL;
   if (o.beta != 0.0 && !o.Cin) return GSMVI_EINVAL;
+  if (o.ncp < 0 || o.ncp > DGEMM_MAX_PEERS || o.row0 < 0) return GSMVI_EINVAL;
+  if ((o.ncp > 0 || o.row0 > 0) && (o.tri || o.mirror || o.krange != KR_FULL)) return GSMVI_EINVAL;
   DgemmArgs a;
   a.M = M; a.N = N; a.K = K;
   a.alpha = o.alpha; a.beta = o.beta; a.diag_add = o.diag_add;
   a.A = A; a.lda = lda; a.B = B; a.ldb = ldb;
   a.Cin = o.Cin; a.ldcin = o.ldcin; a.C = C; a.ldc = ldc;
   a.tri = o.tri ? 1 : 0; a.mirror = o.mirror ? 1 : 0; a.krange = o.krange;
+  a.row0 = o.row0; a.ncp = o.ncp;
+  for (int d = 0; d < DGEMM_MAX_PEERS; ++d) a.Cp[d] = d < o.ncp ? o.Cp[d] : nullptr;
+  for (int d = 0; d < o.ncp; ++d)
+    if (!a.Cp[d]) return GSMVI_EINVAL;
   const long long tiles128 = static_cast<long long>((M + 127) / 128) * ((N + 127) / 128);
   const bool big = (o.tri ? tiles128 / 2 : tiles128) >= 120;  // enough 128x128 tiles to fill 148 SMs
-#define GSMVI_DG(KERN, BMV)                                                              \
-  {                                                                                      \
-    const int grid = ((M + BMV - 1) / BMV) * ((N + BMV - 1) / BMV);                      \
-    if (!a_mn && !b_mn) KERN<BMV, false, false><<<grid, DTHREADS, 0, stream>>>(a);        \
-    else if (a_mn && !b_mn) KERN<BMV, true, false><<<grid, DTHREADS, 0, stream>>>(a);     \
-    else if (!a_mn && b_mn) KERN<BMV, false, true><<<grid, DTHREADS, 0, stream>>>(a);     \
-    else KERN<BMV, true, true><<<grid, DTHREADS, 0, stream>>>(a);                         \
-  }
   const bool aligned = ((lda | ldb) & 1) == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
-  if (dgemm_variant() == 3 && big && aligned && K > 0) {
+  if (big && aligned && K > 0) {
+    // cp.async three-stage pipeline, 128 x 128 tiles
     static PerDeviceOnce attr_set;
     if (!attr_set.get()) {
       cudaError_t ae = cudaFuncSetAttribute(dgemm_pipe_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES);
@@ -544,14 +370,19 @@ int launch_dgemm(cudaStream_t stream, int M, int N, int K, const double* A, long
     else if (a_mn && !b_mn) dgemm_pipe_kernel<true, false><<<grid, DTHREADS, PIPE_SMEM_BYTES, stream>>>(a);
     else if (!a_mn && b_mn) dgemm_pipe_kernel<false, true><<<grid, DTHREADS, PIPE_SMEM_BYTES, stream>>>(a);
     else dgemm_pipe_kernel<true, true><<<grid, DTHREADS, PIPE_SMEM_BYTES, stream>>>(a);
-  } else if (dgemm_variant() >= 2) {
-    if (big) GSMVI_DG(dgemm_mma16_kernel, 128) else GSMVI_DG(dgemm_mma16_kernel, 64)
-  } else if (dgemm_variant() == 1) {
-    if (big) GSMVI_DG(dgemm_mma_kernel, 128) else GSMVI_DG(dgemm_mma_kernel, 64)
   } else {
-    if (big) GSMVI_DG(dgemm_kernel, 128) else GSMVI_DG(dgemm_kernel, 64)
+    // register-staged kernel: any alignment; 64 x 64 tiles (two CTAs per SM) when 128-tiles would not fill the GPU
+#define GSMVI_DG(BMV)                                                                                  \
+  {                                                                                                    \
+    const int grid = ((M + BMV - 1) / BMV) * ((N + BMV - 1) / BMV);                                    \
+    if (!a_mn && !b_mn) dgemm_mma16_kernel<BMV, false, false><<<grid, DTHREADS, 0, stream>>>(a);        \
+    else if (a_mn && !b_mn) dgemm_mma16_kernel<BMV, true, false><<<grid, DTHREADS, 0, stream>>>(a);     \
+    else if (!a_mn && b_mn) dgemm_mma16_kernel<BMV, false, true><<<grid, DTHREADS, 0, stream>>>(a);     \
+    else dgemm_mma16_kernel<BMV, true, true><<<grid, DTHREADS, 0, stream>>>(a);                         \
   }
+    if (big) GSMVI_DG(128) else GSMVI_DG(64)
 #undef GSMVI_DG
+  }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
 }

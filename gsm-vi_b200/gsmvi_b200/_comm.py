@@ -112,3 +112,63 @@ class CommBuffer:
             self.dist.barrier(group=self.group)
         self.lib.gsmvi_comm_free(self.own)
         self.own = None
+
+
+class BamShardC(ctypes.Structure):
+    """gsmvi_bam_shard of include/gsmvi_b200.h"""
+    _fields_ = [("rank", ctypes.c_int), ("world", ctypes.c_int), ("peer_ws", ctypes.c_void_p * 8),
+                ("epoch_host", ctypes.POINTER(ctypes.c_uint))]
+
+
+class PeerAlloc:
+    """A zero-initialised device allocation of `nbytes` on every rank of `group`, each mapped into every other rank's
+    address space through CUDA IPC (gsmvi_comm_alloc / gsmvi_comm_open).  `ptrs[r]` is rank r's allocation as seen from
+    this process (own at [rank]); `flat` is this rank's allocation as a torch uint8 tensor (no ownership)."""
+
+    def __init__(self, nbytes, group, dist):
+        lib = L.lib()
+        _declare(lib)
+        self.lib, self.dist, self.group = lib, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.nbytes = int(nbytes)
+        own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        L.check(lib.gsmvi_comm_alloc(self.nbytes, ctypes.byref(own), handle), "gsmvi_comm_alloc")
+        self.own = own.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.ptrs, self.opened = [], []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(self.own)
+            else:
+                p = ctypes.c_void_p()
+                L.check(lib.gsmvi_comm_open(h, ctypes.byref(p)), "gsmvi_comm_open")
+                self.ptrs.append(p.value)
+                self.opened.append(p.value)
+
+        class _Raw:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+        self.flat = torch.as_tensor(_Raw(self.own, self.nbytes), device=torch.device("cuda", torch.cuda.current_device()))
+        torch.cuda.synchronize()
+        dist.barrier(group=group)  # every allocation is mapped everywhere before anyone stores into a peer
+
+    def close(self, collective=True):
+        if self.own is None:
+            return
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+        if collective:
+            self.dist.barrier(group=self.group)
+        for p in self.opened:
+            self.lib.gsmvi_comm_close(p)
+        self.opened = []
+        self.flat = None
+        if collective:
+            self.dist.barrier(group=self.group)  # free only after every importer has unmapped
+        self.lib.gsmvi_comm_free(self.own)
+        self.own = None

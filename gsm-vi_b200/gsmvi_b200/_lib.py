@@ -190,6 +190,23 @@ def bam_stats(X, G, B, D, B_total, stats_ws, stage, npass=3):
                                 stream_ptr()), "gsmvi_bam_stats")
 
 
+def bam_solve_sharded(stats_ws, B, D, B_total, mu0, Sigma0, reg, jitter, mu_out, Sigma_out, solve_ws, bad_flag, shard,
+                      max_ns=200):
+    """Tensor-parallel phase 2 of the solve (gsmvi_bam_solve_sharded); `shard` is a _comm.BamShardC.  Returns the number
+    of Newton-Schulz iterations (identical on every rank).  Synchronises the current stream."""
+    f = lib().gsmvi_bam_solve_sharded
+    if not getattr(f, "_declared", False):
+        f.restype = c_i
+        f.argtypes = [c_p, c_i, c_i, c_i, c_p, c_p, c_ll, c_d, c_d, c_p, c_p, c_ll, c_p, c_i, ctypes.POINTER(c_i), c_p, c_p,
+                      c_p]
+        f._declared = True
+    it = c_i(0)
+    check(f(ptr(stats_ws), B, D, B_total, ptr(mu0), ptr(Sigma0), Sigma0.stride(0), float(reg), float(jitter), ptr(mu_out),
+            ptr(Sigma_out), Sigma_out.stride(0), ptr(solve_ws), max_ns, ctypes.byref(it), ptr(bad_flag), ctypes.byref(shard),
+            stream_ptr()), "gsmvi_bam_solve_sharded")
+    return it.value
+
+
 def bam_solve(stats_ws, B, D, B_total, mu0, Sigma0, reg, jitter, mu_out, Sigma_out, solve_ws, bad_flag, lowrank=False,
               max_ns=200, world=1, phase=0):
     """Returns the number of Newton-Schulz iterations run.  Synchronises the current stream."""

@@ -88,8 +88,23 @@ class BaMEngine:
         self.ws_p = torch.empty(L.workspace_bytes(L.WS_POTRF, B, D) // 4, dtype=torch.float32, device=dev)
         self.ws_s = torch.empty(L.workspace_bytes(L.WS_BAM_STATS, B, D) // 8, dtype=torch.float64, device=dev)
         kind = L.WS_BAM_SOLVE_LOWRANK if use_lowrank else L.WS_BAM_SOLVE
-        self.ws_v = torch.empty(L.workspace_bytes(kind, batch_size if use_lowrank else B, D) // 8, dtype=torch.float64,
-                                device=dev)
+        nbytes_v = L.workspace_bytes(kind, batch_size if use_lowrank else B, D)
+        self.peer = None
+        if self.world > 1 and not use_lowrank and self.world <= 8 and __import__("os").environ.get("GSMVI_BAM_TP", "1") != "0":
+            # tensor-parallel solve: the solve workspace of every rank is mapped into every other
+            # rank, the Newton-Schulz / T T^T products are split by rows and their epilogues store through NVLink
+            import ctypes
+            from ._comm import BamShardC, PeerAlloc
+            self.peer = PeerAlloc(nbytes_v, process_group, self.dist)
+            self.ws_v = self.peer.flat.view(torch.float64)
+            self._epoch = ctypes.c_uint(0)
+            self.shard = BamShardC()
+            self.shard.rank, self.shard.world = self.rank, self.world
+            for r in range(self.world):
+                self.shard.peer_ws[r] = self.peer.ptrs[r]
+            self.shard.epoch_host = ctypes.pointer(self._epoch)
+        else:
+            self.ws_v = torch.empty(nbytes_v // 8, dtype=torch.float64, device=dev)
         if use_lowrank and self.world > 1:
             # sharded low-rank update: the K = batch_size + 1 columns of U's exact factor Q come from every rank's centred
             # scores, gathered into a full-batch statistics block; the O(D^2 K) solve is then replicated (bit-identical)
@@ -105,6 +120,7 @@ class BaMEngine:
         self.draws = 0
         L.potrf_check(self.Sb, self.Lb, D, self.bad, self.ws_p, npass)
         if int(self.bad.item()) != 0:
+            self.close(collective=False)  # every rank sees the same start
             raise ValueError("initial covariance is not positive definite")
 
     def _stats_views(self):
@@ -158,7 +174,10 @@ class BaMEngine:
             L.bam_solve(*args, max_ns=self.max_ns, world=self.world, phase=1)
             ld = (D + 7) // 8 * 8
             self.dist.all_reduce(self.ws_v[3 * D * ld: 4 * D * ld], group=self.group)
-            it = L.bam_solve(*args, max_ns=self.max_ns, world=self.world, phase=2)
+            if self.peer is not None:
+                it = L.bam_solve_sharded(*args, self.shard, max_ns=self.max_ns)
+            else:
+                it = L.bam_solve(*args, max_ns=self.max_ns, world=self.world, phase=2)
         self.ns_iters.append(it)
         # bit 1 of the solve's flag: the Newton-Schulz square root did not converge (the reference's scipy sqrtm raises
         # there, and BaM.fit's retry loop - bam.py:188-206 - draws fresh samples).  With a fixed draw tape a retry would see
@@ -193,6 +212,13 @@ class BaMEngine:
     def cov(self):
         return self.S
 
+    def close(self, collective=True):
+        """Release the peer-mapped solve workspace of a tensor-parallel fit (collective: every rank calls it)."""
+        if self.peer is not None:
+            self.ws_v = None
+            self.peer.close(collective=collective)
+            self.peer = None
+
 
 class BaM:
     """Wrapper class for using BaM updates to fit a distribution (gsmvi/bam.py:117-137)."""
@@ -213,6 +239,13 @@ class BaM:
         their meaning; keyword-only extras as in gsm.GSM.fit.  Returns (mean[D], cov[D, D]) as CUDA tensors."""
         eng = BaMEngine(self.D, batch_size, self.lp_g, key, mean, cov, self.use_lowrank, jitter, z_tape, npass,
                         process_group, score_input)
+        try:
+            return self._fit_loop(eng, key, regf, batch_size, niter, nprint, verbose, monitor, retries)
+        except BaseException:
+            eng.close(collective=False)  # a failed rank must not wait for its peers in a barrier
+            raise
+
+    def _fit_loop(self, eng, key, regf, batch_size, niter, nprint, verbose, monitor, retries):
         nevals = 1  # bam.py:168
         if nprint > niter:
             nprint = niter  # bam.py:177
@@ -245,7 +278,9 @@ class BaM:
             monitor(i, [eng.mean(), eng.cov()], self.lp, key, nevals=nevals)
         self.n_reverts = eng.n_reverts
         self.ns_iters = eng.ns_iters
-        return eng.mean().clone(), eng.cov().clone()
+        mean, cov = eng.mean().clone(), eng.cov().clone()
+        eng.close()
+        return mean, cov
 
 
 class Regularizers:

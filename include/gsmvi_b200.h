@@ -229,6 +229,26 @@ int gsmvi_bam_solve(const void* stats_workspace, int B, int D, int B_total, cons
                     long long lds0, double reg, double jitter, float* mu_out, float* Sigma_out, long long ldso, void* solve_workspace,
                     int max_ns_iters, int* ns_iters_host, int* bad_flag, int world, int phase, void* stream);
 
+/* Tensor-parallel form of gsmvi_bam_solve's phase 2 for a batch-sharded fit (one process per GPU; SURVEY.md section 8f-1;
+ * replaces, like gsmvi_bam_solve, the solve of gsmvi/bam.py:59-67 with its host sqrtm, gsmvi/bam.py:19-28).  Every rank's
+ * solve_workspace is a peer-mapped allocation of the same size (gsmvi_comm_alloc / gsmvi_comm_open, zero-initialised);
+ * shard->peer_ws[r] is rank r's workspace as mapped into THIS process (own at [rank]).  The three D x D products of every
+ * Newton-Schulz iteration, T = L R^-T and S = 2 T T^T are computed by rows of the result across the ranks; each GEMM's
+ * epilogue stores its rows into every rank's workspace over NVLink peer memory (the all-gather is fused into the GEMM) and
+ * barrier kernels (release / acquire on a counter word inside the workspaces) separate producers from consumers.  Residuals
+ * are reduced in a fixed order, so every rank reads the same bits, runs the same number of iterations and ends with
+ * bit-identical (mu_out, Sigma_out).  *shard->epoch_host (host word, zero before the first call on these workspaces) counts
+ * barriers across calls.  phase must be 2 (after the all-reduce of the phase-1 partials M_r); every rank makes the call. */
+typedef struct gsmvi_bam_shard {
+  int rank, world;          /* world <= 8 */
+  void* peer_ws[8];
+  unsigned* epoch_host;
+} gsmvi_bam_shard;
+int gsmvi_bam_solve_sharded(const void* stats_workspace, int B, int D, int B_total, const float* mu0, const float* Sigma0,
+                            long long lds0, double reg, double jitter, float* mu_out, float* Sigma_out, long long ldso,
+                            void* solve_workspace, int max_ns_iters, int* ns_iters_host, int* bad_flag,
+                            const gsmvi_bam_shard* shard, void* stream);
+
 /* Low-rank BaM update (K = B + 1 < D).  Replaces bam_lowrank_update (gsmvi/bam.py:72-114) and compute_Q
  * (gsmvi/bam.py:10-17: host ARPACK svds) with the exact factor Q = [sqrt(reg/B) Gc^T, sqrt(reg/(1+reg)) gbar] of U:
  *   A = V Q, H = A^T Q + I/4, BB = (I/2 + H^(1/2))^2, S = V - A BB^-1 A^T.  Same conventions as gsmvi_bam_solve;

@@ -630,7 +630,10 @@ def bam_leg(args, D, B, Bl, npass, world, rank, group, barrier, max_over_ranks, 
                   "d2h_bytes_per_step": world * (8 + state_bytes / ke),
                   "note": "BaM.fit(key, regf, mean=pinned host, cov=pinned host, niter=steps-1, z_tape=pinned host draws): each "
                           "iteration's draws cross host->device inside the timed region, the two PD flags are read back per "
-                          "iteration, (mean, cov) cross at both ends, workspaces are allocated inside the call"}
+                          "iteration, (mean, cov) cross at both ends; the engine (workspaces, peer-mapped solve workspace on a "
+                          "sharded fit) is the one the warm-up call left in BaM.fit's cache; wall clock, max over ranks"}
+    from gsmvi_b200 import gsm as gsm_mod
+    gsm_mod.release_engines()
     return out
 
 

@@ -1,6 +1,7 @@
 // C-ABI of libgsmvi_b200.so (declared in include/gsmvi_b200.h). Plain pointers and sizes only; no torch types.
 #include "../../include/gsmvi_b200.h"
 
+#include "advi.cuh"
 #include "bam_solve.cuh"
 #include "comm.cuh"
 #include "dgemm.cuh"
@@ -270,6 +271,12 @@ int gsmvi_gauss_logq_reduce(const float* Z_or_X, long long ld, int N, int D, con
 int gsmvi_gsm_ensemble_fit(const float* P, const float* c, float* mu, float* Sigma, int F, int D, int B, int niter,
                            unsigned long long seed, const float* z_tape, int* reverts, int first_fit, void* stream) {
   return gsm_ensemble_fit(S(stream), P, c, mu, Sigma, F, D, B, niter, seed, z_tape, reverts, first_fit);
+}
+
+int gsmvi_advi_step(float* L, long long ldl, float* mu, const float* G, long long ldg, const float* Z, long long ldz,
+                    float* GtZ, long long ldgz, float* gsum, float* mL, float* vL, float* m_mu, float* v_mu, int B, int D,
+                    float lr, float b1, float b2, float eps, int t, int npass, void* stream) {
+  return advi_step(S(stream), L, ldl, mu, G, ldg, Z, ldz, GtZ, ldgz, gsum, mL, vL, m_mu, v_mu, B, D, lr, b1, b2, eps, t, npass);
 }
 
 int gsmvi_gsm_commit(const int* bad_flag, const int* bad_flag2, int n, const void* const* src_host, void* const* dst_host,

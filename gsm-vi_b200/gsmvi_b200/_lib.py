@@ -494,3 +494,15 @@ def gsm_small64(mode, mu, Sigma, L_, z_tape, seed, iter0, X, G, P, c, B, D, iter
     check(lib().gsmvi_gsm_small64(mode, ptr(mu), ptr(Sigma), ptr(L_), ptr(z_tape), seed & (2**64 - 1), iter0 & (2**64 - 1),
                                   ptr(X), ptr(G), ptr(P), ptr(c), B, D, iters, ptr(status), ptr(ws), stream_ptr()),
           "gsmvi_gsm_small64")
+
+
+# ------------------------------------------------------------------------------------------------ ADVI
+def advi_step(L_, mu, G, Z, GtZ, gsum, mL, vL, m_mu, v_mu, B, D, lr, b1, b2, eps, t, npass=3):
+    f = lib().gsmvi_advi_step
+    if not getattr(f, "_declared", False):
+        f.restype = c_i
+        f.argtypes = [c_p, c_ll, c_p, c_p, c_ll, c_p, c_ll, c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_f, c_f, c_f,
+                      c_i, c_i, c_p]
+        f._declared = True
+    check(f(ptr(L_), L_.stride(0), ptr(mu), ptr(G), G.stride(0), ptr(Z), Z.stride(0), ptr(GtZ), GtZ.stride(0), ptr(gsum),
+            ptr(mL), ptr(vL), ptr(m_mu), ptr(v_mu), B, D, lr, b1, b2, eps, t, npass, stream_ptr()), "gsmvi_advi_step")

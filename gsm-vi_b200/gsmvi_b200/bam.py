@@ -69,19 +69,11 @@ class BaMEngine:
         B = self.B = batch_size // self.world
         if use_lowrank and batch_size + 1 >= D:
             raise ValueError("the low-rank update needs batch_size + 1 < D (the reference's svds(U, k=B) needs B < D)")
-        self.seed = key_to_seed(key)
-        self.score_input = score_input
         self.Sb, self.S = new_mat(D, D, dev)
         self.Snb, self.Sn = new_mat(D, D, dev)
         self.Lb, _ = new_mat(D, D, dev)
         self.Lnb, _ = new_mat(D, D, dev)
         self.mu, self.mun = new_vec(D, dev), new_vec(D, dev)
-        if mean is not None:
-            self.mu[:D].copy_(to_dev(mean, dev))  # bam.py:163-164
-        if cov is None:
-            self.S.copy_(torch.eye(D, device=dev))  # bam.py:165-166
-        else:
-            self.S.copy_(to_dev(cov, dev))
         self.Zb, self.Z = new_mat(B, D, dev)
         self.Xb, self.X = new_mat(B, D, dev)
         self.Gb, self.G = new_mat(B, D, dev)
@@ -111,6 +103,25 @@ class BaMEngine:
             self.ws_full = torch.zeros(L.workspace_bytes(L.WS_BAM_STATS, batch_size, D) // 8, dtype=torch.float64, device=dev)
         self.bad = torch.zeros(1, dtype=torch.int32, device=dev)
         self.bad2 = torch.zeros(1, dtype=torch.int32, device=dev)
+        try:
+            self.reset(lp_g, key, mean, cov, z_tape, score_input, jitter)
+        except Exception:
+            self.close(collective=False)  # every rank sees the same start
+            raise
+
+    def reset(self, lp_g, key, mean=None, cov=None, z_tape=None, score_input="torch", jitter=1e-6):
+        """Start a new fit on this engine's buffers (bam.py:163-168).  BaM.fit keeps engines - workspaces and, on a sharded
+        fit, the peer-mapped solve workspace - across calls, as GSM.fit does."""
+        D, dev = self.D, self.dev
+        self.lp_g, self.score_input, self.jitter = lp_g, score_input, jitter
+        self.seed = key_to_seed(key)
+        self.mu.zero_()
+        if mean is not None:
+            self.mu[:D].copy_(to_dev(mean, dev))  # bam.py:163-164
+        if cov is None:
+            self.S.copy_(torch.eye(D, device=dev))  # bam.py:165-166
+        else:
+            self.S.copy_(to_dev(cov, dev))
         if z_tape is not None and not isinstance(z_tape, torch.Tensor):
             z_tape = torch.as_tensor(z_tape, dtype=torch.float32)
         self.z_tape = z_tape
@@ -118,9 +129,8 @@ class BaMEngine:
         self.n_reverts = 0
         self.ns_iters = []
         self.draws = 0
-        L.potrf_check(self.Sb, self.Lb, D, self.bad, self.ws_p, npass)
+        L.potrf_check(self.Sb, self.Lb, D, self.bad, self.ws_p, self.npass)
         if int(self.bad.item()) != 0:
-            self.close(collective=False)  # every rank sees the same start
             raise ValueError("initial covariance is not positive definite")
 
     def _stats_views(self):
@@ -237,13 +247,28 @@ class BaM:
             score_input="torch"):
         """Main function to fit a multivariate Gaussian to the target (gsmvi/bam.py:140-216).  Reference arguments keep
         their meaning; keyword-only extras as in gsm.GSM.fit.  Returns (mean[D], cov[D, D]) as CUDA tensors."""
-        eng = BaMEngine(self.D, batch_size, self.lp_g, key, mean, cov, self.use_lowrank, jitter, z_tape, npass,
-                        process_group, score_input)
+        from . import gsm as _gsm
+        ekey = _gsm._engine_key("bam-lowrank" if self.use_lowrank else "bam", self.D, batch_size, npass, process_group)
+        eng = _gsm._ENGINES.pop(ekey, None)
+        if eng is None:
+            while len(_gsm._ENGINES) >= _gsm._ENGINES_MAX:  # same call sequence on every rank: collective evictions
+                _gsm._evict(next(iter(_gsm._ENGINES)), collective=True)
+            eng = BaMEngine(self.D, batch_size, self.lp_g, key, mean, cov, self.use_lowrank, jitter, z_tape, npass,
+                            process_group, score_input)
+        else:
+            try:
+                eng.reset(self.lp_g, key, mean, cov, z_tape, score_input, jitter)
+            except Exception:
+                _gsm._ENGINES[ekey] = eng
+                raise
         try:
-            return self._fit_loop(eng, key, regf, batch_size, niter, nprint, verbose, monitor, retries)
+            out = self._fit_loop(eng, key, regf, batch_size, niter, nprint, verbose, monitor, retries)
         except BaseException:
             eng.close(collective=False)  # a failed rank must not wait for its peers in a barrier
             raise
+        eng.z_tape = None
+        _gsm._ENGINES[ekey] = eng
+        return out
 
     def _fit_loop(self, eng, key, regf, batch_size, niter, nprint, verbose, monitor, retries):
         nevals = 1  # bam.py:168
@@ -278,9 +303,7 @@ class BaM:
             monitor(i, [eng.mean(), eng.cov()], self.lp, key, nevals=nevals)
         self.n_reverts = eng.n_reverts
         self.ns_iters = eng.ns_iters
-        mean, cov = eng.mean().clone(), eng.cov().clone()
-        eng.close()
-        return mean, cov
+        return eng.mean().clone(), eng.cov().clone()
 
 
 class Regularizers:

@@ -274,6 +274,16 @@ int gsmvi_gauss_logq_reduce(const float* Z_or_X, long long ld, int N, int D, con
 int gsmvi_gsm_ensemble_fit(const float* P, const float* c, float* mu, float* Sigma, int F, int D, int B, int niter,
                            unsigned long long seed, const float* z_tape, int* reverts, int first_fit, void* stream);
 
+/* ADVI baseline on the same sampler / score kernels.  One optimiser step of gsmvi/advi.py:69-74:
+ * the gradient of neg_elbo (gsmvi/advi.py:31-45; jax.value_and_grad there) with respect to (mu, lower triangle of the
+ * scale factor L) from this iteration's draws Z [B,D] and the scores G [B,D] = grad log p at x = mu + Z L^T,
+ *   d/dmu = -sum_b g_b,   d/dL_ij = -(G^T Z)_ij - B delta_ij / L_ii  (i >= j),
+ * followed by the Adam update of optax.adam (lr, b1, b2, eps; t = 1-based step).  G^T Z runs on the tensor-core GEMM.
+ * GtZ [D,ldgz], gsum [D]: scratch.  mL, vL [D,ldl], m_mu, v_mu [D]: Adam moments, zero before the first step. */
+int gsmvi_advi_step(float* L, long long ldl, float* mu, const float* G, long long ldg, const float* Z, long long ldz,
+                    float* GtZ, long long ldgz, float* gsum, float* mL, float* vL, float* m_mu, float* v_mu, int B, int D,
+                    float lr, float b1, float b2, float eps, int t, int npass, void* stream);
+
 /* Accept / revert of an iteration's proposal on the device.  Replaces the host-side branch of gsmvi/gsm.py:125-129 and
  * gsmvi/bam.py:208-212 (`if is_good: mean, cov = mean_new, cov_new else: revert`), which costs the reference a device ->
  * host copy of the covariance and a host Cholesky per iteration.  The caller always exchanges its (current, proposal)

@@ -431,6 +431,69 @@ class KLMonitor:
 
 
 # --------------------------------------------------------------------------------------------------------------
+# ADVI (gsmvi/advi.py) - SURVEY.md section 8f-4.  PARITY UNPINNED against the reference itself: advi.py needs jax autodiff
+# (jax.value_and_grad) and optax, neither importable here, and a numpy stand-in cannot differentiate.  The restatement
+# below follows advi.py line by line with the gradient written out in closed form; tests/test_host_cpu.py checks that
+# closed form against central finite differences of neg_elbo (the function the reference differentiates).
+# --------------------------------------------------------------------------------------------------------------
+
+
+def advi_neg_elbo(mu, Lm, Z, lp):
+    """neg_elbo of advi.py:31-45 for fixed standard-normal draws Z [B, D]: x = mu + z L^T (numpyro's reparameterised
+    sample), loss = -(sum_b lp(x_b) - sum_b log q(x_b)) with q = N(mu, L L^T), L = lower triangle of Lm."""
+    Lt = np.tril(Lm)
+    X = mu[None, :] + Z @ Lt.T
+    D = mu.shape[0]
+    logq = -0.5 * np.sum(Z * Z) - Z.shape[0] * (np.sum(np.log(np.abs(np.diag(Lt)))) + 0.5 * D * np.log(2 * np.pi))
+    return -(lp(X) - logq), X
+
+
+def advi_grad(mu, Lm, Z, G):
+    """Gradient of advi_neg_elbo with respect to (mu, lower triangle of L) given the scores G = grad log p at the samples."""
+    B = Z.shape[0]
+    gL = -np.tril(G.T @ Z) - B * np.diag(1.0 / np.diag(Lm))
+    return -G.sum(axis=0), gL
+
+
+class ADVI:
+    """Follows gsmvi/advi.py:8-112 with a draw tape and optax.adam written out (b1 = 0.9, b2 = 0.999, eps = 1e-8)."""
+
+    def __init__(self, D, lp, lp_g):
+        self.D, self.lp, self.lp_g = D, lp, lp_g
+
+    def fit(self, key, lr, Z, mean=None, cov=None, batch_size=8, niter=1000, monitor=None, b1=0.9, b2=0.999, eps=1e-8,
+            dtype=np.float64):
+        D = self.D
+        mean = np.zeros(D, dtype) if mean is None else np.asarray(mean, dtype)  # advi.py:77-78
+        cov = np.identity(D, dtype=dtype) if cov is None else np.asarray(cov, dtype)  # advi.py:79-80
+        Lm = np.linalg.cholesky(cov)  # advi.py:83
+        mu = mean.copy()
+        m_mu, v_mu, m_L, v_L = np.zeros(D, dtype), np.zeros(D, dtype), np.zeros((D, D), dtype), np.zeros((D, D), dtype)
+        losses = []
+        nevals = 1
+        for i in range(niter + 1):  # advi.py:92
+            if monitor is not None and (i % monitor.checkpoint) == 0:  # advi.py:95-100
+                monitor(i, [mu, np.tril(Lm) @ np.tril(Lm).T], self.lp, key, nevals=nevals)
+                nevals = 0
+            z = np.asarray(Z[i], dtype)
+            loss, X = advi_neg_elbo(mu, Lm, z, self.lp)
+            g_mu, g_L = advi_grad(mu, Lm, z, np.asarray(self.lp_g(X), dtype))
+            t = i + 1
+            m_mu = b1 * m_mu + (1 - b1) * g_mu
+            v_mu = b2 * v_mu + (1 - b2) * g_mu**2
+            m_L = b1 * m_L + (1 - b1) * g_L
+            v_L = b2 * v_L + (1 - b2) * g_L**2
+            mu = mu - lr * (m_mu / (1 - b1**t)) / (np.sqrt(v_mu / (1 - b2**t)) + eps)
+            Lm = Lm - np.tril(lr * (m_L / (1 - b1**t)) / (np.sqrt(v_L / (1 - b2**t)) + eps))
+            losses.append(loss)
+            nevals += batch_size
+        cov = np.tril(Lm) @ np.tril(Lm).T  # advi.py:109
+        if monitor is not None:
+            monitor(i, [mu, cov], self.lp, key, nevals=nevals)
+        return mu, cov, losses
+
+
+# --------------------------------------------------------------------------------------------------------------
 # Benchmark targets (examples/example_gsm_numpy.py:8-31 made reproducible; SURVEY.md section 8d)
 # --------------------------------------------------------------------------------------------------------------
 

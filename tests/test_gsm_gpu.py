@@ -347,7 +347,7 @@ def test_gsm_warm_start_from_lbfgs_style_estimate(lib):
     # BFGS-like estimate: right eigenvectors, a few eigenvalues lost to round-off (tiny negatives) and a skew part
     w, Q = np.linalg.eigh(cov_t)
     w_est = w * np.exp(0.3 * rng.normal(size=D))
-    w_est[:3] = -1e-7
+    w_est[:3] = -1e-4 * w.max()
     cov0 = (Q * w_est) @ Q.T + 1e-9 * rng.normal(size=(D, D))
     assert np.linalg.eigvalsh((cov0 + cov0.T) / 2).min() < 0
     mean0 = mean_t + 0.05 * rng.normal(size=D)
@@ -356,7 +356,7 @@ def test_gsm_warm_start_from_lbfgs_style_estimate(lib):
         g = GSM(D, tgt.lp, tgt.lp_g)
         m, c = g.fit(3, mean=mean0, cov=cov0, niter=150, batch_size=B, verbose=False)
     assert any("not numerically positive definite" in str(x.message) for x in wlist)
-    assert relF(c, cov_t) < 5e-3 and np.max(np.abs(m.cpu().numpy() - mean_t)) < 5e-3
+    assert relF(c, cov_t) < 2e-2 and np.max(np.abs(m.cpu().numpy() - mean_t)) < 2e-2
     # a start that no small shift can repair is still refused (NaN entries)
     bad = cov_t.copy()
     bad[0, 0] = np.nan
@@ -364,7 +364,7 @@ def test_gsm_warm_start_from_lbfgs_style_estimate(lib):
         GSM(D, tgt.lp, tgt.lp_g).fit(3, mean=mean0, cov=bad, niter=2, batch_size=B, verbose=False)
     # and the engine that refused is still usable afterwards
     m2, c2 = GSM(D, tgt.lp, tgt.lp_g).fit(3, niter=150, batch_size=B, verbose=False)
-    assert relF(c2, cov_t) < 5e-3
+    assert relF(c2, cov_t) < 2e-2
 
 
 def test_gsm_engine_is_reused_across_fits(lib):

@@ -12,6 +12,9 @@ size_t bam_solve_workspace_bytes(int B, int D, int lowrank);
 int bam_stats(cudaStream_t st, const float* X, long long ldx, const float* G, long long ldg, int B, int D, int Btot,
               double* ws, int stage);
 
+// In-place fp64 Cholesky of the lower triangle (upper zeroed); *flag |= 1 if not PD.
+int potrf64(cudaStream_t st, double* A, long long lda, int n, int* flag);
+
 typedef gsmvi_bam_shard BamShard;
 
 // shard != nullptr (world > 1, phase 2): tensor-parallel solve over peer-mapped workspaces (see gsmvi_bam_solve_sharded)

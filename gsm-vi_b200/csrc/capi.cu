@@ -240,6 +240,10 @@ int gsmvi_bam_solve(const void* stats_workspace, int B, int D, int B_total, cons
                         phase);
 }
 
+int gsmvi_potrf64(double* A, long long lda, int n, int* bad_flag, void* stream) {
+  return potrf64(S(stream), A, lda, n, bad_flag);
+}
+
 int gsmvi_bam_solve_sharded(const void* stats_workspace, int B, int D, int B_total, const float* mu0, const float* Sigma0,
                             long long lds0, double reg, double jitter, float* mu_out, float* Sigma_out, long long ldso,
                             void* solve_workspace, int max_ns_iters, int* ns_iters_host, int* bad_flag,

@@ -105,11 +105,39 @@ __device__ __forceinline__ int sidx(int r, int k) {
 }
 
 // Epilogue shared by the kernels below: fragment layout of m16n8k16 (c0, c1 at row g, columns 2t, 2t+1; c2, c3 at row g+8).
+// Cin is read in batches BEFORE any store of the batch: Cin may alias C (in-place rank-k updates of the Cholesky / TRSM), so
+// the compiler cannot hoist a load above an earlier store by itself, and 64 dependent load -> store round trips per thread
+// made a K = 64 update cost ~60 us where its arithmetic needs 3.
 template <int BI, int BJ>
 __device__ __forceinline__ void dgemm_epilogue(const DgemmArgs& a, const double (&acc)[BI][BJ][4], int m0, int n0, int wr, int wc,
                                                int fg, int ft) {
+  const bool vec_cin = a.beta != 0.0 && (a.ldcin & 1) == 0 && (reinterpret_cast<uintptr_t>(a.Cin) & 15) == 0;
 #pragma unroll
-  for (int i = 0; i < BI; ++i)
+  for (int i = 0; i < BI; ++i) {
+    double cin[2][BJ][2];
+    if (a.beta != 0.0) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int m = m0 + wr + 16 * i + fg + 8 * h;
+        const long long gm = a.row0 + m;
+#pragma unroll
+        for (int j = 0; j < BJ; ++j) {
+          const int n = n0 + wc + 8 * j + 2 * ft;
+          cin[h][j][0] = cin[h][j][1] = 0.0;
+          if (m < a.M && n < a.N) {
+            const double* src = a.Cin + gm * a.ldcin + n;
+            if (vec_cin && n + 1 < a.N) {
+              const double2 t = *reinterpret_cast<const double2*>(src);
+              cin[h][j][0] = t.x;
+              cin[h][j][1] = t.y;
+            } else {
+              cin[h][j][0] = src[0];
+              if (n + 1 < a.N) cin[h][j][1] = src[1];
+            }
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int m = m0 + wr + 16 * i + fg + 8 * h;
@@ -122,10 +150,8 @@ __device__ __forceinline__ void dgemm_epilogue(const DgemmArgs& a, const double 
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           v[u] = a.alpha * acc[i][j][2 * h + u];
-          if (n + u < a.N) {
-            if (a.beta != 0.0) v[u] += a.beta * a.Cin[gm * a.ldcin + n + u];
-            if (gm == n + u) v[u] += a.diag_add;
-          }
+          if (a.beta != 0.0) v[u] += a.beta * cin[h][j][u];
+          if (gm == n + u) v[u] += a.diag_add;
         }
         if (a.ncp > 0) {
           // every destination gets the pair as one 16-byte store where alignment allows (peer stores cross NVLink)
@@ -141,15 +167,21 @@ __device__ __forceinline__ void dgemm_epilogue(const DgemmArgs& a, const double 
           }
           continue;
         }
+        double* dst = a.C + gm * a.ldc + n;
+        if (!a.tri && !a.mirror && n + 1 < a.N && (a.ldc & 1) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+          continue;
+        }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           if (n + u >= a.N) continue;
           if (a.tri && n + u > gm) continue;
-          a.C[gm * a.ldc + n + u] = v[u];
+          dst[u] = v[u];
           if (a.mirror && n + u != gm) a.C[static_cast<long long>(n + u) * a.ldc + gm] = v[u];
         }
       }
     }
+  }
   // peer stores must be performed system-wide before this grid counts as finished: the barrier kernel that follows
   // signals the peers with a release that is only cumulative over what this GPU has already made visible
   if (a.ncp > 1) __threadfence_system();

@@ -506,3 +506,13 @@ def advi_step(L_, mu, G, Z, GtZ, gsum, mL, vL, m_mu, v_mu, B, D, lr, b1, b2, eps
         f._declared = True
     check(f(ptr(L_), L_.stride(0), ptr(mu), ptr(G), G.stride(0), ptr(Z), Z.stride(0), ptr(GtZ), GtZ.stride(0), ptr(gsum),
             ptr(mL), ptr(vL), ptr(m_mu), ptr(v_mu), B, D, lr, b1, b2, eps, t, npass, stream_ptr()), "gsmvi_advi_step")
+
+
+def potrf64(A, n, bad_flag):
+    """In-place fp64 Cholesky (gsmvi_potrf64): A [n, ld] float64 CUDA tensor."""
+    f = lib().gsmvi_potrf64
+    if not getattr(f, "_declared", False):
+        f.restype = c_i
+        f.argtypes = [c_p, c_ll, c_i, c_p, c_p]
+        f._declared = True
+    check(f(ptr(A), A.stride(0), n, ptr(bad_flag), stream_ptr()), "gsmvi_potrf64")

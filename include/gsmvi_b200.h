@@ -229,6 +229,12 @@ int gsmvi_bam_solve(const void* stats_workspace, int B, int D, int B_total, cons
                     long long lds0, double reg, double jitter, float* mu_out, float* Sigma_out, long long ldso, void* solve_workspace,
                     int max_ns_iters, int* ns_iters_host, int* bad_flag, int world, int phase, void* stream);
 
+/* fp64 Cholesky used twice inside the BaM solve (V = L L^T and I + N = R R^T; the reference's np.linalg.solve /
+ * scipy sqrtm path of gsmvi/bam.py:63-65 is LAPACK fp64): A (n x n doubles, leading dimension lda, lower triangle read) is
+ * overwritten by its lower Cholesky factor, upper triangle zeroed; *bad_flag |= 1 on a non-positive pivot.  Exported for
+ * tests and timing. */
+int gsmvi_potrf64(double* A, long long lda, int n, int* bad_flag, void* stream);
+
 /* Tensor-parallel form of gsmvi_bam_solve's phase 2 for a batch-sharded fit (one process per GPU; SURVEY.md section 8f-1;
  * replaces, like gsmvi_bam_solve, the solve of gsmvi/bam.py:59-67 with its host sqrtm, gsmvi/bam.py:19-28).  Every rank's
  * solve_workspace is a peer-mapped allocation of the same size (gsmvi_comm_alloc / gsmvi_comm_open, zero-initialised);

@@ -55,6 +55,29 @@ def test_dgemm_on_int8_tensor_cores_matches_fp64(lib, M, N, K, a_mn, b_mn):
     assert float((C - (-0.5 * ref + 2.0 * Cin)).norm() / ref.norm()) < 5e-11
 
 
+@pytest.mark.parametrize("n", [1, 7, 64, 65, 200, 512, 1000, 2048])
+def test_potrf64_matches_cholesky(lib, n):
+    """The fp64 Cholesky of the BaM solve (register-blocked diagonal kernel, tile TRSM, look-ahead panels) against
+    np.linalg.cholesky."""
+    rng = np.random.RandomState(n)
+    A = rng.normal(size=(n, n))
+    S = A @ A.T / n + 0.05 * np.eye(n)
+    ld = (n + 7) // 8 * 8
+    buf = torch.zeros(n, ld, dtype=torch.float64, device="cuda")
+    buf[:, :n] = torch.as_tensor(S)
+    bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+    lib.potrf64(buf, n, bad)
+    Lref = np.linalg.cholesky(S)
+    Ld = buf[:, :n].cpu().numpy()
+    assert int(bad.item()) == 0
+    assert np.linalg.norm(Ld - Lref) / np.linalg.norm(Lref) < 1e-13
+    assert np.abs(np.triu(Ld, 1)).max() == 0.0
+    S[n // 2, n // 2] = -1.0
+    buf[:, :n] = torch.as_tensor(S)
+    lib.potrf64(buf, n, bad)
+    assert int(bad.item()) == 1
+
+
 def test_dgemm_tri_mirror_and_kranges(lib):
     n = 333
     g = torch.Generator().manual_seed(3)

@@ -330,11 +330,16 @@ def run_ours(args):
     pipe_peak = peaks[peak_key] if h3 else peaks[peak_key] / 2.0
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     executed = 3 * achieved * (7.0 / 9.0) if npass >= 2 else achieved * (7.0 / 9.0)
-    kname = "gemm_h3_kernel" if h3 else "gemm_tf32_kernel"
+    pair = h3 and L.h3_pair_kernel(-1) == 1
+    kname = ("gemm_h3x2_kernel" if pair else "gemm_h3_kernel") if h3 else "gemm_tf32_kernel"
     traffic, traffic_src = measured_traffic(kname, D, B, world)
+    kdesc = {"gemm_h3x2_kernel": "gemm_h3x2_kernel (persistent 2-CTA pairs, tcgen05.mma.cta_group::2 kind::f16, scaled 3xFP16 "
+                                 "split, double-buffered TMEM chunks%s)" % ("; the multi-GPU covariance update keeps the one-CTA "
+                                                                            "push-mode gemm_h3_kernel" if world > 1 else ""),
+             "gemm_h3_kernel": "gemm_h3_kernel (scaled 3xFP16 split, kind::f16)",
+             "gemm_tf32_kernel": "gemm_tf32_kernel<3xTF32>"}[kname]
     roofline = {"bound": "tensor",
-                "kernel": ("gemm_h3_kernel (scaled 3xFP16 split, kind::f16)" if h3 else "gemm_tf32_kernel<3xTF32>") +
-                          ": sample, score, W=G*Sigma, E^T U + U^T D",
+                "kernel": kdesc + ": sample, score, W=G*Sigma, E^T U + U^T D",
                 "achieved": achieved, "peak": pipe_peak, "unit": "TFLOP/s", "frac": achieved / pipe_peak,
                 "traffic": traffic, "traffic_source": traffic_src,
                 "executed_tflops": executed, "executed_frac": executed / pipe_peak,

@@ -80,6 +80,8 @@ int gsmvi_gemm_h3(const void* A_hi, const void* A_lo, const float* scale_a, long
   return launch_gemm_h3(S(stream), M, N, K, a, b, C, ldc, o);
 }
 
+int gsmvi_h3_pair_kernel(int enable) { return h3_pair_kernel(enable); }
+
 int gsmvi_h3_absmax(const float* A, long long lda, int rows, int cols, unsigned* absmax, void* stream) {
   return h3_absmax(S(stream), A, lda, rows, cols, absmax);
 }

@@ -3,6 +3,8 @@
 // example_gsm_numpy.py:24-29), W = G Sigma and the batch-mean covariance update of gsm_update (gsmvi/gsm.py:11-27, 53-54).
 #include "dev_once.cuh"
 #include "h3_gemm.cuh"
+#include "h3x2_gemm.cuh"
+#include <cstdlib>
 
 namespace gsmvi {
 
@@ -104,8 +106,103 @@ int h3_prepare(int M, int N, int K, const HView& A, const HView& B, float* C, lo
   return GSMVI_OK;
 }
 
+// ---- persistent 2-CTA kernel (h3x2_gemm.cuh): used for every launch it can express, GSMVI_H3X2=0 turns it off
+
+template <bool A_MN, bool B_MN>
+static int launch_h3x2_one(cudaStream_t stream, const H3Args& args, const CUtensorMap& tah, const CUtensorMap& tbh,
+                           const CUtensorMap& tal, const CUtensorMap& tbl, int tiles_mp, int n_st, bool pdl) {
+  static PerDeviceOnce attr_set;
+  static PerDeviceInt max_pairs;
+  auto kern = gemm_h3x2_kernel<A_MN, B_MN>;
+  if (!attr_set.get()) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, X2_SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    // how many pairs fit at once (one CTA per SM, two SMs of one TPC per pair): the persistent grid
+    int dev = 0, sms = 0, clusters = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3(2 * (sms / 2));
+    q.blockDim = dim3(X2_THREADS);
+    q.dynamicSmemBytes = X2_SMEM_BYTES;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 2;
+    qa[0].val.clusterDim.y = 1;
+    qa[0].val.clusterDim.z = 1;
+    q.attrs = qa;
+    q.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&clusters, kern, &q) != cudaSuccess || clusters <= 0) {
+      cudaGetLastError();
+      clusters = sms / 2;
+    }
+    max_pairs.ref() = clusters < sms / 2 ? clusters : sms / 2;
+    attr_set.set();
+  }
+  const int pairs = n_st < max_pairs.ref() ? n_st : max_pairs.ref();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(X2_THREADS);
+  cfg.dynamicSmemBytes = X2_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;  // the cluster shape is a compile-time attribute of the kernel (__cluster_dims__)
+  int chunk_kb = X2_CHUNK_KB;
+  if (const char* cs = getenv("GSMVI_X2_CHUNK_KB")) {  // accuracy / speed probe: additions per TMEM accumulator = 4 * chunk_kb
+    const int v = atoi(cs);
+    if (v >= 1 && v <= 64) chunk_kb = v;
+  }
+  int probe = 0;  // GSMVI_X2_PROBE: bottleneck probes of tools/probe_gemm_h3x2.py (bit 0: no TMA loads, bit 1: hi*hi MMAs only)
+  if (const char* ps = getenv("GSMVI_X2_PROBE")) probe = atoi(ps) & 3;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args, tah, tbh, tal, tbl, tiles_mp, n_st, chunk_kb, probe);
+  return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
+}
+
+static int g_h3x2 = -1;  // -1: read GSMVI_H3X2 on first use
+static bool h3x2_enabled() {
+  if (g_h3x2 < 0) {
+    const char* s = getenv("GSMVI_H3X2");
+    g_h3x2 = (s && s[0] == '0') ? 0 : 1;
+  }
+  return g_h3x2 == 1;
+}
+int h3_pair_kernel(int enable) {
+  const int prev = h3x2_enabled() ? 1 : 0;
+  if (enable == 0 || enable == 1) g_h3x2 = enable;
+  return prev;
+}
+
+static bool h3x2_eligible(int M, const H3Opts& o) {
+  return h3x2_enabled() && M > H3_BM && o.splits == 1 && !o.push_base && (o.krange & ~KR_B_LOWER) == 0;
+}
+
+static int launch_gemm_h3x2(cudaStream_t stream, int M, int N, int K, const HView& A, const HView& B, float* C, long long ldc,
+                            const H3Opts& o) {
+  H3Args a;
+  CUtensorMap tm[4];
+  dim3 grid;
+  int rc = h3_prepare(M, N, K, A, B, C, ldc, o, &a, tm, &grid);  // argument block + validation (its maps are rebuilt below)
+  if (rc != GSMVI_OK) return rc;
+  // per CTA and k-block: 128 rows of A, 64 rows of B.  K-major: box = 64 K-elements x rows.  MN-major: 64 MN-elements x 64 K-rows.
+  const int abr = o.a_mn ? H3_BK : 128, bbr = 64;
+  if ((rc = make_tmap_h(&tm[0], A.hi, A.rows, A.cols, A.ld, 64, abr)) != GSMVI_OK) return rc;
+  if ((rc = make_tmap_h(&tm[1], B.hi, B.rows, B.cols, B.ld, 64, bbr)) != GSMVI_OK) return rc;
+  if ((rc = make_tmap_h(&tm[2], A.lo, A.rows, A.cols, A.ld, 64, abr)) != GSMVI_OK) return rc;
+  if ((rc = make_tmap_h(&tm[3], B.lo, B.rows, B.cols, B.ld, 64, bbr)) != GSMVI_OK) return rc;
+  const int tiles_mp = (a.tiles_m + 1) / 2;
+  const int n_st = o.tri ? tiles_mp * (tiles_mp + 1) : tiles_mp * a.tiles_n;
+  if (!o.a_mn && !o.b_mn) return launch_h3x2_one<false, false>(stream, a, tm[0], tm[1], tm[2], tm[3], tiles_mp, n_st, o.pdl);
+  if (o.a_mn && !o.b_mn) return launch_h3x2_one<true, false>(stream, a, tm[0], tm[1], tm[2], tm[3], tiles_mp, n_st, o.pdl);
+  if (!o.a_mn && o.b_mn) return launch_h3x2_one<false, true>(stream, a, tm[0], tm[1], tm[2], tm[3], tiles_mp, n_st, o.pdl);
+  return launch_h3x2_one<true, true>(stream, a, tm[0], tm[1], tm[2], tm[3], tiles_mp, n_st, o.pdl);
+}
+
 int launch_gemm_h3(cudaStream_t stream, int M, int N, int K, const HView& A, const HView& B, float* C, long long ldc,
                    const H3Opts& o) {
+  if (h3x2_eligible(M, o)) return launch_gemm_h3x2(stream, M, N, K, A, B, C, ldc, o);
   H3Args a;
   CUtensorMap tm[4];  // A_hi, B_hi, A_lo, B_lo
   dim3 grid;

@@ -81,6 +81,22 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(bool a_mn, bool b_mn) {
 }
 
 namespace ptx {
+// One lane of the (fully converged) warp: the producer and MMA roles run their loops with all 32 lanes so that every
+// address, descriptor and predicate is warp-uniform to the compiler and lives in uniform registers; only the asynchronous
+// instruction itself is issued by the elected lane.  (Inside an `if (lane == 0)` region the same values count as
+// thread-dependent and every tcgen05.mma / TMA instruction is wrapped in an ELECT + 5 x R2UR "waterfall" loop: ~20 dependent
+// instructions per MMA in a single thread, measured as a 74-cycle issue cost per 64-cycle MMA plus ~460 cycles per k-block.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(
@@ -114,7 +130,7 @@ __device__ __forceinline__ void gemm_h3_body(const H3Args& args, const CUtensorM
   const uint32_t acc_bar = bar_base + 8u * (2 * STAGES);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 8 * (2 * STAGES + 1) + 8);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
 
   // ---- tile coordinates
@@ -179,23 +195,23 @@ __device__ __forceinline__ void gemm_h3_body(const H3Args& args, const CUtensorM
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   // programmatic dependent launch: everything above overlapped the tail of the previous kernel in the stream; from here
   // on its results are needed (no-ops when the kernel was launched without the attribute)
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      for (int it = 0; it < num_kb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+    // ===================== TMA producer (the warp stays converged, one elected lane issues) =====================
+    for (int it = 0; it < num_kb; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+      const int k0 = (kb_begin + it) * H3_BK;
+      const uint32_t sA = stage_base + s * H3_STAGE_BYTES;
+      const uint32_t sB = sA + H3_TILE_BYTES;
+      if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(full_bar(s), H3_STAGE_BYTES);
-        const int k0 = (kb_begin + it) * H3_BK;
-        const uint32_t sA = stage_base + s * H3_STAGE_BYTES;
-        const uint32_t sB = sA + H3_TILE_BYTES;
         if (!A_MN) {
           ptx::tma_load_2d(sA, &tmAhi, full_bar(s), k0, m0);
           ptx::tma_load_2d(sA + 2 * H3_TILE_BYTES, &tmAlo, full_bar(s), k0, m0);
@@ -217,25 +233,25 @@ __device__ __forceinline__ void gemm_h3_body(const H3Args& args, const CUtensorM
           }
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(A_MN, B_MN);
-      // K-major (SWIZZLE_128B): rows of 64 fp16, 8-row groups 1024 B apart (SBO); a k-slice (16 fp16) is 32 B along the row.
-      // MN-major (SWIZZLE_128B): 64-wide MN chunks H3_BK*128 B apart (LBO), 8-deep K groups 1024 B apart (SBO); a k-slice
-      // (16 K rows) is two groups = 2048 B further.
-      constexpr uint32_t A_LBO = A_MN ? H3_BK * 128 : 16, A_SBO = 1024, A_KSTEP = A_MN ? 2048 : H3_UMMA_K * 2;
-      constexpr uint32_t B_LBO = B_MN ? H3_BK * 128 : 16, B_SBO = 1024, B_KSTEP = B_MN ? 2048 : H3_UMMA_K * 2;
-      for (int it = 0; it < num_kb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        ptx::mbar_wait(full_bar(s), ph);
-        ptx::tc_fence_after_sync();
-        const uint32_t sA = stage_base + s * H3_STAGE_BYTES;
-        const uint32_t sB = sA + H3_TILE_BYTES;
-        const uint32_t t_main = tmem_base + (it % H3_N_MAIN) * H3_BN;
+    // ===================== MMA issuer (the warp stays converged, one elected lane issues) =====================
+    constexpr uint32_t idesc = make_idesc_f16(A_MN, B_MN);
+    // K-major (SWIZZLE_128B): rows of 64 fp16, 8-row groups 1024 B apart (SBO); a k-slice (16 fp16) is 32 B along the row.
+    // MN-major (SWIZZLE_128B): 64-wide MN chunks H3_BK*128 B apart (LBO), 8-deep K groups 1024 B apart (SBO); a k-slice
+    // (16 K rows) is two groups = 2048 B further.
+    constexpr uint32_t A_LBO = A_MN ? H3_BK * 128 : 16, A_SBO = 1024, A_KSTEP = A_MN ? 2048 : H3_UMMA_K * 2;
+    constexpr uint32_t B_LBO = B_MN ? H3_BK * 128 : 16, B_SBO = 1024, B_KSTEP = B_MN ? 2048 : H3_UMMA_K * 2;
+    for (int it = 0; it < num_kb; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      ptx::mbar_wait(full_bar(s), ph);
+      ptx::tc_fence_after_sync();
+      const uint32_t sA = stage_base + s * H3_STAGE_BYTES;
+      const uint32_t sB = sA + H3_TILE_BYTES;
+      const uint32_t t_main = tmem_base + (it % H3_N_MAIN) * H3_BN;
+      if (ptx::elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < H3_BK / H3_UMMA_K; ++kk) {
           const uint64_t da = make_smem_desc(sA + kk * A_KSTEP, A_LBO, A_SBO, 2);
@@ -247,10 +263,11 @@ __device__ __forceinline__ void gemm_h3_body(const H3Args& args, const CUtensorM
           ptx::umma_f16(t_main, da, db, idesc, (it >= H3_N_MAIN || kk > 0) ? 1u : 0u);
         }
         ptx::umma_commit(empty_bar(s));
+        if (it + 1 == num_kb) ptx::umma_commit(acc_bar);
       }
-      if (num_kb > 0) ptx::umma_commit(acc_bar);
-      else ptx::mbar_arrive(acc_bar);
+      __syncwarp();
     }
+    if (num_kb == 0 && ptx::elect_one()) ptx::mbar_arrive(acc_bar);
     __syncwarp();
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
@@ -442,6 +459,10 @@ struct H3Opts {
 
 int launch_gemm_h3(cudaStream_t stream, int M, int N, int K, const HView& A, const HView& B, float* C, long long ldc,
                    const H3Opts& o);
+// Select the kernel behind launch_gemm_h3 for the launches both can express: 1 = the persistent 2-CTA kernel of
+// h3x2_gemm.cuh (default; GSMVI_H3X2=0 in the environment starts with 0), 0 = the one-CTA kernel above, anything else = query.
+// Returns the previous setting.
+int h3_pair_kernel(int enable);
 // The argument block, the four tensor maps (A_hi, B_hi, A_lo, B_lo) and the grid (tiles, splits) of that launch, for
 // callers that run gemm_h3_body inside a kernel of their own (potrf_h3.cu).
 int h3_prepare(int M, int N, int K, const HView& A, const HView& B, float* C, long long ldc, const H3Opts& o, H3Args* out,

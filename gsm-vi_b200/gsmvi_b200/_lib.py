@@ -278,6 +278,8 @@ def _declare_h3(L):
     L.gsmvi_gemm_h3.restype = c_i
     L.gsmvi_gemm_h3.argtypes = [c_p, c_p, c_p, c_ll, c_ll, c_ll, c_i, c_p, c_p, c_p, c_ll, c_ll, c_ll, c_i, c_p, c_ll,
                                 c_i, c_i, c_i, c_f, c_f, c_p, c_ll, c_p, c_i, c_i, c_i, c_p, c_i, c_ll, c_p]
+    L.gsmvi_h3_pair_kernel.restype = c_i
+    L.gsmvi_h3_pair_kernel.argtypes = [c_i]
     L.gsmvi_h3_absmax.restype = c_i
     L.gsmvi_h3_absmax.argtypes = [c_p, c_ll, c_i, c_i, c_p, c_p]
     L.gsmvi_h3_split.restype = c_i
@@ -384,6 +386,11 @@ def gsm_update_h3(X, G, Gh, mu, Sigma, Sh, mu_out, Sigma_out, absmax_sout, B, D,
     check(lib().gsmvi_gsm_update_h3(ptr(X), X.stride(0), ptr(G), G.stride(0), Gh.ref, ptr(mu), ptr(Sigma), Sigma.stride(0),
                                     Sh.ref, ptr(mu_out), ptr(Sigma_out), Sigma_out.stride(0), ptr(absmax_sout), B, D,
                                     B_total, mode, ptr(ws), stream_ptr()), "gsmvi_gsm_update_h3")
+
+
+def h3_pair_kernel(enable=-1):
+    """Select (1 / 0) or query (-1) the persistent 2-CTA kernel behind the scaled-3xFP16 GEMM; returns the previous setting."""
+    return lib().gsmvi_h3_pair_kernel(int(enable))
 
 
 def h3_absmax(A, rows, cols, absmax):

@@ -77,6 +77,12 @@ int gsmvi_gemm_h3(const void* A_hi, const void* A_lo, const float* scale_a, long
                   const float* Cin, long long ldcin, const float* bias_n, int tri, int mirror, int krange,
                   unsigned* absmax_out, int splits, long long split_stride, void* stream);
 
+/* Which kernel serves gsmvi_gemm_h3 and the GSM entry points built on it (gsmvi_sample_h3, gsmvi_gauss_score_h3,
+ * gsmvi_gsm_update_h3: gsmvi/gsm.py:11-27, 53-54, 119) when both can express the launch: 1 = the persistent 2-CTA kernel
+ * (tcgen05.mma.cta_group::2, 256 x 128 tiles, double-buffered TMEM chunks; default), 0 = the one-CTA 128 x 128 kernel,
+ * any other value = query only.  Returns the previous setting.  Host-only, no device work. */
+int gsmvi_h3_pair_kernel(int enable);
+
 /* *absmax <- max(*absmax, max |A|) as a float bit pattern (device word; zero it first). */
 int gsmvi_h3_absmax(const float* A, long long lda, int rows, int cols, unsigned* absmax, void* stream);
 

@@ -81,22 +81,6 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(bool a_mn, bool b_mn) {
 }
 
 namespace ptx {
-// One lane of the (fully converged) warp: the producer and MMA roles run their loops with all 32 lanes so that every
-// address, descriptor and predicate is warp-uniform to the compiler and lives in uniform registers; only the asynchronous
-// instruction itself is issued by the elected lane.  (Inside an `if (lane == 0)` region the same values count as
-// thread-dependent and every tcgen05.mma / TMA instruction is wrapped in an ELECT + 5 x R2UR "waterfall" loop: ~20 dependent
-// instructions per MMA in a single thread, measured as a 74-cycle issue cost per 64-cycle MMA plus ~460 cycles per k-block.)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "elect.sync _|p, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(

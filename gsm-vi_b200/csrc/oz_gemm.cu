@@ -175,7 +175,7 @@ gemm_oz_kernel(const OzArgs args, const __grid_constant__ CUtensorMap tmA, const
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   const uint32_t acc_bar = bar_base + 8u * (2 * STAGES);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 8 * (2 * STAGES + 1) + 8);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   int tm, tn;
   if (args.tri) {
@@ -217,33 +217,34 @@ gemm_oz_kernel(const OzArgs args, const __grid_constant__ CUtensorMap tmA, const
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
+  // producer and MMA warps stay converged, one elected lane issues (ptx::elect_one: descriptors in uniform registers)
   if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < total; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+    for (int it = 0; it < total; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+      const int pair = it / args.nkb, kb = it - pair * args.nkb;
+      const int t = args.t_lo + pair, u = args.g - t;  // 1-based digit indices
+      const uint32_t sA = stage_base + s * OZ_STAGE_BYTES;
+      if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(full_bar(s), OZ_STAGE_BYTES);
-        const int pair = it / args.nkb, kb = it - pair * args.nkb;
-        const int t = args.t_lo + pair, u = args.g - t;  // 1-based digit indices
-        const uint32_t sA = stage_base + s * OZ_STAGE_BYTES;
         ptx::tma_load_2d(sA, &tmA, full_bar(s), kb * OZ_BK, (t - 1) * args.rows_a + m0);
         ptx::tma_load_2d(sA + OZ_TILE_BYTES, &tmB, full_bar(s), kb * OZ_BK, (u - 1) * args.rows_b + n0);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_i8();
-      for (int it = 0; it < total; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        ptx::mbar_wait(full_bar(s), ph);
-        ptx::tc_fence_after_sync();
-        const uint32_t sA = stage_base + s * OZ_STAGE_BYTES;
-        const uint32_t sB = sA + OZ_TILE_BYTES;
+    constexpr uint32_t idesc = make_idesc_i8();
+    for (int it = 0; it < total; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      ptx::mbar_wait(full_bar(s), ph);
+      ptx::tc_fence_after_sync();
+      const uint32_t sA = stage_base + s * OZ_STAGE_BYTES;
+      const uint32_t sB = sA + OZ_TILE_BYTES;
+      if (ptx::elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < OZ_BK / OZ_UMMA_K; ++kk) {
           const uint64_t da = make_smem_desc(sA + kk * OZ_UMMA_K, 16, 1024, 2);
@@ -251,10 +252,10 @@ gemm_oz_kernel(const OzArgs args, const __grid_constant__ CUtensorMap tmA, const
           umma_i8(tmem_base, da, db, idesc, (it > 0 || kk > 0) ? 1u : 0u);
         }
         ptx::umma_commit(empty_bar(s));
+        if (it + 1 == total) ptx::umma_commit(acc_bar);
       }
-      ptx::umma_commit(acc_bar);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     ptx::mbar_wait(acc_bar, 0);
     ptx::tc_fence_after_sync();

@@ -501,19 +501,25 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw) 
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before_sync();
         named_bar_sync(2, NCOMP);
-        if (tid == 0) {
+        if (__shfl_sync(0xffffffffu, warp, 0) == 0) {
+          // warp 0 stays converged and one elected lane issues: addresses and descriptors are then warp-uniform to the
+          // compiler (uniform registers) instead of going through an ELECT + R2UR loop per MMA (ptx::elect_one)
           ptx::tc_fence_after_sync();
           // c_format F32, a/b TF32, both K-major, N = R, M = 128 (rows beyond R hold stale data: their outputs are ignored)
           const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(R >> 3) << 17) | (8u << 24);
+          const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t dh = make_smem_desc(pt_addr + kk * 32, 16, 1024, 2);
-            const uint64_t dl = make_smem_desc(pt_addr + 12288 + kk * 32, 16, 1024, 2);
-            ptx::umma_tf32(tmem_base, dh, dh, idesc, kk > 0 ? 1u : 0u);
-            ptx::umma_tf32(tmem_base, dl, dh, idesc, 1u);
-            ptx::umma_tf32(tmem_base, dh, dl, idesc, 1u);
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t dh = make_smem_desc(pt_addr + kk * 32, 16, 1024, 2);
+              const uint64_t dl = make_smem_desc(pt_addr + 12288 + kk * 32, 16, 1024, 2);
+              ptx::umma_tf32(tb, dh, dh, idesc, kk > 0 ? 1u : 0u);
+              ptx::umma_tf32(tb, dl, dh, idesc, 1u);
+              ptx::umma_tf32(tb, dh, dl, idesc, 1u);
+            }
+            ptx::umma_commit(bar_addr);
           }
-          ptx::umma_commit(bar_addr);
+          __syncwarp();
         }
         if (warp < 4 && 32 * warp < R) {
           ptx::mbar_wait(bar_addr, p & 1);

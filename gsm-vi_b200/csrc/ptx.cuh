@@ -52,6 +52,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// One lane of the (fully converged) warp: the producer and MMA roles run their loops with all 32 lanes so that every
+// address, descriptor and predicate is warp-uniform to the compiler and lives in uniform registers; only the asynchronous
+// instruction itself is issued by the elected lane.  (Inside an `if (lane == 0)` region the same values count as
+// thread-dependent and every tcgen05.mma / TMA instruction is wrapped in an ELECT + 5 x R2UR "waterfall" loop: ~20 dependent
+// instructions per MMA in a single thread, measured as a 74-cycle issue cost per 64-cycle MMA plus ~460 cycles per k-block.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -123,7 +123,7 @@ gemm_tf32_kernel(const GemmArgs args, const __grid_constant__ CUtensorMap tmA, c
   const uint32_t acc_bar = bar_base + 8u * (3 * STAGES);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 8 * (3 * STAGES + 1) + 8);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
 
   // ---- tile coordinates
@@ -178,19 +178,19 @@ gemm_tf32_kernel(const GemmArgs args, const __grid_constant__ CUtensorMap tmA, c
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      for (int it = 0; it < num_kb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+    // ===================== TMA producer (the warp stays converged, one elected lane issues: see ptx::elect_one) =========
+    for (int it = 0; it < num_kb; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+      const int k0 = (kb_begin + it) * BK;
+      const uint32_t sA = stage_base + s * Cfg::STAGE_BYTES;
+      const uint32_t sB = sA + TILE_BYTES;
+      if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(full_bar(s), (2 + (A_PRE ? 1 : 0) + (B_PRE ? 1 : 0)) * TILE_BYTES);
-        const int k0 = (kb_begin + it) * BK;
-        const uint32_t sA = stage_base + s * Cfg::STAGE_BYTES;
-        const uint32_t sB = sA + TILE_BYTES;
         if (!A_MN) {
           ptx::tma_load_2d(sA, &tmA, full_bar(s), k0, m0);
         } else {
@@ -222,11 +222,11 @@ gemm_tf32_kernel(const GemmArgs args, const __grid_constant__ CUtensorMap tmA, c
           }
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (converged warp, elected lane) =====================
+    {
       constexpr uint32_t idesc_pos = make_idesc_tf32(A_MN, B_MN, false);
       constexpr uint32_t idesc_neg = make_idesc_tf32(A_MN, B_MN, true);
       // K-major (SWIZZLE_128B): 8-row groups 1024 B apart (SBO), LBO unused.
@@ -244,25 +244,28 @@ gemm_tf32_kernel(const GemmArgs args, const __grid_constant__ CUtensorMap tmA, c
         const uint32_t sB = sA + TILE_BYTES;
         const uint32_t idesc = ((kb_begin + it) * BK >= args.neg_from) ? idesc_neg : idesc_pos;
         const uint32_t t_main = tmem_base + (it % Cfg::N_MAIN) * BN;
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-          const uint64_t da = make_smem_desc(sA + kk * A_KSTEP, A_LBO, A_SBO, A_LT);
-          const uint64_t db = make_smem_desc(sB + kk * B_KSTEP, B_LBO, B_SBO, B_LT);
-          const uint32_t acc_main = (it >= Cfg::N_MAIN || kk > 0) ? 1u : 0u;
-          if (NPASS == 3) {
-            const uint64_t da_lo = make_smem_desc(sA + 2 * TILE_BYTES + kk * A_KSTEP, A_LBO, A_SBO, A_LT);
-            const uint64_t db_lo = make_smem_desc(sB + 2 * TILE_BYTES + kk * B_KSTEP, B_LBO, B_SBO, B_LT);
-            ptx::umma_tf32(tmem_base + Cfg::CORR_COL, da_lo, db, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-            ptx::umma_tf32(tmem_base + Cfg::CORR_COL, da, db_lo, idesc, 1u);
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+            const uint64_t da = make_smem_desc(sA + kk * A_KSTEP, A_LBO, A_SBO, A_LT);
+            const uint64_t db = make_smem_desc(sB + kk * B_KSTEP, B_LBO, B_SBO, B_LT);
+            const uint32_t acc_main = (it >= Cfg::N_MAIN || kk > 0) ? 1u : 0u;
+            if (NPASS == 3) {
+              const uint64_t da_lo = make_smem_desc(sA + 2 * TILE_BYTES + kk * A_KSTEP, A_LBO, A_SBO, A_LT);
+              const uint64_t db_lo = make_smem_desc(sB + 2 * TILE_BYTES + kk * B_KSTEP, B_LBO, B_SBO, B_LT);
+              ptx::umma_tf32(tmem_base + Cfg::CORR_COL, da_lo, db, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+              ptx::umma_tf32(tmem_base + Cfg::CORR_COL, da, db_lo, idesc, 1u);
+            }
+            ptx::umma_tf32(t_main, da, db, idesc, acc_main);
           }
-          ptx::umma_tf32(t_main, da, db, idesc, acc_main);
+          ptx::umma_commit(empty_bar(s));  // smem slot reusable once these MMAs retire
+          if (it + 1 == num_kb) ptx::umma_commit(acc_bar);
         }
-        ptx::umma_commit(empty_bar(s));  // smem slot reusable once these MMAs retire
+        __syncwarp();
       }
-      if (num_kb > 0) ptx::umma_commit(acc_bar);
-      else ptx::mbar_arrive(acc_bar);
+      if (num_kb == 0 && ptx::elect_one()) ptx::mbar_arrive(acc_bar);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ===================== converter warps, then epilogue =====================
     const int ct = threadIdx.x - 64;  // 0..255

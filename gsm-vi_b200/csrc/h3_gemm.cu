@@ -235,7 +235,8 @@ __global__ void __launch_bounds__(256) h3_absmax_kernel(const float* __restrict_
   if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(out, m);
 }
 
-__global__ void __launch_bounds__(256) h3_split_kernel(const float* __restrict__ A, long long lda, int rows, int cols,
+// (six CTAs per SM = at most 42 registers: the split of the new covariance runs beside the Cholesky, whose CTAs leave 11.7k)
+__global__ void __launch_bounds__(256, 6) h3_split_kernel(const float* __restrict__ A, long long lda, int rows, int cols,
                                                        const unsigned* __restrict__ absmax, int sqrt_mode,
                                                        float* __restrict__ scale_out, __half* __restrict__ Hi,
                                                        __half* __restrict__ Lo, long long ldo) {

@@ -117,6 +117,8 @@ class GSMEngine:
             self.dSb, _ = new_mat(D, D, dev)
             self.dmu = new_vec(D, dev)
         self.copy_stream = None
+        self._side_stream = None
+        self._side_ok = __import__("os").environ.get("GSMVI_SIDE_STREAM", "1")[:1] != "0"
         if self.h3:
             # scaled 3xFP16 engine: every GEMM operand lives as an fp16 (hi, lo) pair + power-of-two scale
             H = L.HOperand
@@ -378,21 +380,44 @@ class GSMEngine:
                                    self.ws_u)
             L.h3_absmax(self.Sn, D, D, sl[2:3])
         tm("update(+exchange)")
-        # ---- goodness check = Cholesky of the new covariance, reused as the next sampling factor (gsm.py:125)
+        # ---- goodness check = Cholesky of the new covariance, reused as the next sampling factor (gsm.py:125).  The
+        # factorisation is a latency chain that leaves most of every SM idle, so the two HBM-bound passes that depend on
+        # nothing it produces - the fp16 split of the new covariance and the NEXT iteration's Philox draws (this iteration's
+        # were consumed by the sampler) - run beside it on a second stream (eager launches only; ~70 us of a 2.26 ms step)
+        side = None if (graph or not self._side_ok) else self._side()
+        if side is not None:
+            self._ev_fork.record()
+            with torch.cuda.stream(side):
+                side.wait_event(self._ev_fork)
+                self.Snh.split_from(self.Sn, absmax=sl[2:3])
+                if self.z_tape is None:
+                    L.philox_normal_h3(self.Zh, B, D, self.seed, (i + 1) * self.world + self.rank)
+                    self.z_drawn_for = i + 1
+                self._ev_join.record()
         L.potrf_h3(self.Snb, self.Lnb, self.Lnh, D, self.bad, self.ws_p, zero_upper=False)
         tm("cholesky")
-        self.Snh.split_from(self.Sn, absmax=sl[2:3])
+        if side is not None:
+            torch.cuda.current_stream().wait_event(self._ev_join)
+        else:
+            self.Snh.split_from(self.Sn, absmax=sl[2:3])
         tm("split Sigma")
-        # ---- accept / revert on the device (gsm.py:125-129); then the NEXT iteration's draws (they depend on nothing but
-        # the counter), so the GPU never idles between iterations
+        # ---- accept / revert on the device (gsm.py:125-129); then (single-stream form) the NEXT iteration's draws: they
+        # depend on nothing but the counter, so the GPU never idles between iterations
         L.gsm_commit(self.bad, self._commit_plan(), self.status)
         if graph:
             L.philox_normal_h3(self.Zh, B, D, self.seed, 0, offset_dev=self.ctr)
             self.ctr.add_(self.world)
-        elif self.z_tape is None:
+        elif self.z_tape is None and side is None:
             L.philox_normal_h3(self.Zh, B, D, self.seed, (i + 1) * self.world + self.rank)
             self.z_drawn_for = i + 1
         tm("commit+draw")
+
+    def _side(self):
+        """Second stream (and its fork / join events) for the passes that run beside the Cholesky."""
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream()
+            self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        return self._side_stream
 
     def step_h3(self, i):
         """One iteration on the scaled 3xFP16 engine (same sequence as `step`).  With the built-in target, Philox draws and

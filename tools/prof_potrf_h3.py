@@ -24,3 +24,11 @@ for _ in range(reps):
     L.potrf_h3(S, Lo3, Lh, D, bad, ws3, zero_upper=False)
 e.record(); torch.cuda.synchronize()
 print("potrf_h3 D=%d: %.3f ms per factorisation" % (D, s.elapsed_time(e) / reps))
+
+# stated baseline (SURVEY.md section 9 allows a library call beside ours): cuSOLVER fp32 potrf through torch.linalg.cholesky
+torch.linalg.cholesky(S); torch.cuda.synchronize()
+s.record()
+for _ in range(reps):
+    torch.linalg.cholesky(S)
+e.record(); torch.cuda.synchronize()
+print("cuSOLVER fp32 potrf (torch.linalg.cholesky) D=%d: %.3f ms per factorisation" % (D, s.elapsed_time(e) / reps))

@@ -108,14 +108,15 @@ int h3_prepare(int M, int N, int K, const HView& A, const HView& B, float* C, lo
 
 // ---- persistent 2-CTA kernel (h3x2_gemm.cuh): used for every launch it can express, GSMVI_H3X2=0 turns it off
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool PUSH>
 static int launch_h3x2_one(cudaStream_t stream, const H3Args& args, const CUtensorMap& tah, const CUtensorMap& tbh,
                            const CUtensorMap& tal, const CUtensorMap& tbl, int tiles_mp, int n_st, bool pdl) {
   static PerDeviceOnce attr_set;
   static PerDeviceInt max_pairs;
-  auto kern = gemm_h3x2_kernel<A_MN, B_MN>;
+  constexpr int SMEM = PUSH ? X2_PUSH_SMEM_BYTES : X2_SMEM_BYTES;
+  auto kern = gemm_h3x2_kernel<A_MN, B_MN, PUSH>;
   if (!attr_set.get()) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, X2_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
     // how many pairs fit at once (one CTA per SM, two SMs of one TPC per pair): the persistent grid
     int dev = 0, sms = 0, clusters = 0;
@@ -124,7 +125,7 @@ static int launch_h3x2_one(cudaStream_t stream, const H3Args& args, const CUtens
     cudaLaunchConfig_t q = {};
     q.gridDim = dim3(2 * (sms / 2));
     q.blockDim = dim3(X2_THREADS);
-    q.dynamicSmemBytes = X2_SMEM_BYTES;
+    q.dynamicSmemBytes = SMEM;
     cudaLaunchAttribute qa[1];
     qa[0].id = cudaLaunchAttributeClusterDimension;
     qa[0].val.clusterDim.x = 2;
@@ -143,7 +144,7 @@ static int launch_h3x2_one(cudaStream_t stream, const H3Args& args, const CUtens
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(X2_THREADS);
-  cfg.dynamicSmemBytes = X2_SMEM_BYTES;
+  cfg.dynamicSmemBytes = SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -176,7 +177,8 @@ int h3_pair_kernel(int enable) {
 }
 
 static bool h3x2_eligible(int M, const H3Opts& o) {
-  return h3x2_enabled() && M > H3_BM && o.splits == 1 && !o.push_base && (o.krange & ~KR_B_LOWER) == 0;
+  if (o.push_base && !(o.tri && o.a_mn && o.b_mn)) return false;  // push mode: the covariance update's MN-major form only
+  return h3x2_enabled() && M > H3_BM && o.splits == 1 && (o.krange & ~KR_B_LOWER) == 0;
 }
 
 static int launch_gemm_h3x2(cudaStream_t stream, int M, int N, int K, const HView& A, const HView& B, float* C, long long ldc,
@@ -194,10 +196,11 @@ static int launch_gemm_h3x2(cudaStream_t stream, int M, int N, int K, const HVie
   if ((rc = make_tmap_h(&tm[3], B.lo, B.rows, B.cols, B.ld, 64, bbr)) != GSMVI_OK) return rc;
   const int tiles_mp = (a.tiles_m + 1) / 2;
   const int n_st = o.tri ? tiles_mp * (tiles_mp + 1) : tiles_mp * a.tiles_n;
-  if (!o.a_mn && !o.b_mn) return launch_h3x2_one<false, false>(stream, a, tm[0], tm[1], tm[2], tm[3], tiles_mp, n_st, o.pdl);
-  if (o.a_mn && !o.b_mn) return launch_h3x2_one<true, false>(stream, a, tm[0], tm[1], tm[2], tm[3], tiles_mp, n_st, o.pdl);
-  if (!o.a_mn && o.b_mn) return launch_h3x2_one<false, true>(stream, a, tm[0], tm[1], tm[2], tm[3], tiles_mp, n_st, o.pdl);
-  return launch_h3x2_one<true, true>(stream, a, tm[0], tm[1], tm[2], tm[3], tiles_mp, n_st, o.pdl);
+  if (o.push_base) return launch_h3x2_one<true, true, true>(stream, a, tm[0], tm[1], tm[2], tm[3], tiles_mp, n_st, o.pdl);
+  if (!o.a_mn && !o.b_mn) return launch_h3x2_one<false, false, false>(stream, a, tm[0], tm[1], tm[2], tm[3], tiles_mp, n_st, o.pdl);
+  if (o.a_mn && !o.b_mn) return launch_h3x2_one<true, false, false>(stream, a, tm[0], tm[1], tm[2], tm[3], tiles_mp, n_st, o.pdl);
+  if (!o.a_mn && o.b_mn) return launch_h3x2_one<false, true, false>(stream, a, tm[0], tm[1], tm[2], tm[3], tiles_mp, n_st, o.pdl);
+  return launch_h3x2_one<true, true, false>(stream, a, tm[0], tm[1], tm[2], tm[3], tiles_mp, n_st, o.pdl);
 }
 
 int launch_gemm_h3(cudaStream_t stream, int M, int N, int K, const HView& A, const HView& B, float* C, long long ldc,

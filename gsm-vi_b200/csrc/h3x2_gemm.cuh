@@ -17,7 +17,10 @@
 //     2^-11 of the main ones, so their accumulator runs over the whole K and alternates per TILE; it is read together
 //     with the tile's last chunk, and the store of a tile overlaps the next tile's first chunks.
 // Serves the four batch-sized contractions of a GSM step (gsmvi/gsm.py:11-27, 53-54, 119; examples/example_gsm_numpy.py:24-29).
-// Not handled here (launch_gemm_h3 falls back to the one-CTA kernel): split-K partials, push mode, KR_A_* / KR_B_UPPER ranges.
+// Push mode (PUSH = true; the reduce-scatter of the batch-sharded covariance update, csrc/comm.cu): the epilogue stages the
+// scaled tile in shared memory and sends it to its owner rank's staging slot as 128 bulk copies of one 512-byte row, then
+// release-increments the owner's arrival counter - all under the next tile's MMAs.
+// Not handled here (launch_gemm_h3 falls back to the one-CTA kernel): split-K partials, KR_A_* / KR_B_UPPER ranges.
 #pragma once
 #include "h3_gemm.cuh"
 
@@ -28,6 +31,10 @@ constexpr int X2_A_BYTES = 128 * H3_BK * 2;                        // one part (
 constexpr int X2_B_BYTES = 64 * H3_BK * 2;                         // one part of this CTA's 64 rows of B
 constexpr int X2_STAGE_BYTES = 2 * X2_A_BYTES + 2 * X2_B_BYTES;    // [A_hi | A_lo | B_hi | B_lo] = 48 KiB
 constexpr int X2_SMEM_BYTES = 1024 + BAR_BYTES + X2_STAGES * X2_STAGE_BYTES;
+// push mode (multi-GPU covariance update): three stages + a 128 x 132-float staging tile for the bulk copies to the owner rank
+constexpr int X2_PUSH_STAGES = 3;
+constexpr int X2_PUSH_TILE_BYTES = 128 * 132 * 4;
+constexpr int X2_PUSH_SMEM_BYTES = 1024 + BAR_BYTES + X2_PUSH_STAGES * X2_STAGE_BYTES + X2_PUSH_TILE_BYTES;
 constexpr int X2_CHUNK_KB = 8;                                     // default k-blocks per TMEM accumulation chunk of hi*hi
 constexpr int X2_THREADS = 320;
 constexpr int X2_CORR_COL = 256;                                   // TMEM columns: main0 | main1 | corr0 | corr1
@@ -184,13 +191,13 @@ __device__ __forceinline__ void x2_store32(const H3Args& args, float (&v)[32], c
   }
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool PUSH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X2_THREADS, 1)
 gemm_h3x2_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmBhi,
                  const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, const int tiles_mp,
                  const int n_st, const int chunk_kb, const int probe) {
   extern __shared__ uint8_t x2_smem_raw[];
-  constexpr int STAGES = X2_STAGES;
+  constexpr int STAGES = PUSH ? X2_PUSH_STAGES : X2_STAGES;
   const uint32_t raw_addr = ptx::smem_u32(x2_smem_raw);
   uint8_t* smem = x2_smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   const uint32_t bar_base = ptx::smem_u32(smem);
@@ -369,7 +376,8 @@ gemm_h3x2_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, c
       if (args.tri && t.tn >= args.tiles_n) continue;
       const int tm = 2 * t.tmp + static_cast<int>(rank);
       const int num_kb = tile_kb(t);
-      const bool wanted = !(args.tri && t.tn > tm);  // second-row-only supertile: this CTA's tile lies above the diagonal
+      // not wanted: the tile lies above the diagonal (second-row-only supertile) or below the matrix (odd tile-row count)
+      const bool wanted = tm < args.tiles_m && !(args.tri && t.tn > tm);
       const uint32_t lane_col = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 64;
       const uint32_t t_corr = lane_col + X2_CORR_COL + (ntile & 1u) * H3_BN;
       ++ntile;
@@ -406,7 +414,37 @@ gemm_h3x2_kernel(const H3Args args, const __grid_constant__ CUtensorMap tmAhi, c
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);
       }
-      if (wanted) {
+      if (wanted && PUSH) {
+        // stage the scaled tile (row stride 132 floats: conflict-free float4 stores), then 128 threads send one 512-byte row
+        // each to the owner rank (cp.async.bulk, shared -> peer global: full-size NVLink packets), wait for their copies,
+        // and one thread publishes the tile; the staging tile is free again after the second barrier
+        float* stile = reinterpret_cast<float*>(smem + BAR_BYTES + STAGES * X2_STAGE_BYTES);
+        float* srow = stile + (q * 32 + lane) * 132 + half * 64;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          *reinterpret_cast<float4*>(srow + j) = make_float4(alpha * acc0[j], alpha * acc0[j + 1], alpha * acc0[j + 2], alpha * acc0[j + 3]);
+          *reinterpret_cast<float4*>(srow + 32 + j) = make_float4(alpha * acc1[j], alpha * acc1[j + 1], alpha * acc1[j + 2], alpha * acc1[j + 3]);
+        }
+        const int tl = tm * (tm + 1) / 2 + t.tn, owner = tl % args.push_world;
+        ptx::fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int prow = threadIdx.x - 64;
+        if (prow < 128) {
+          float* tile = args.push_base[owner] + args.push_stage_off +
+                        (static_cast<long long>(args.push_rank) * args.push_tpo + tl / args.push_world) * (128 * 128);
+          const uint32_t src = ptx::smem_u32(stile + prow * 132);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 512;" ::"l"(tile + prow * 128), "r"(src) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) {
+          unsigned* cnt = reinterpret_cast<unsigned*>(args.push_base[owner]) + args.push_cnt_off + tl / args.push_world;
+          asm volatile("fence.proxy.async;" ::: "memory");
+          __threadfence_system();
+          asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(cnt), "r"(1u) : "memory");
+        }
+      } else if (wanted) {
         const int m = tm * 128 + q * 32 + lane;
         const int nbase = t.tn * H3_BN + half * 64;
         const bool diag_tile = args.tri && (tm == t.tn);

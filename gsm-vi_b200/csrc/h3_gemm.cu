@@ -60,6 +60,10 @@ static int launch_h3_one(cudaStream_t stream, const H3Args& args, const CUtensor
   return e == cudaSuccess ? GSMVI_OK : static_cast<int>(e);
 }
 
+int h3_make_tmap(CUtensorMap* out, const __half* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows) {
+  return make_tmap_h(out, ptr, rows, cols, ld, box_cols, box_rows);
+}
+
 int h3_prepare(int M, int N, int K, const HView& A, const HView& B, float* C, long long ldc, const H3Opts& o, H3Args* out,
                CUtensorMap* maps, dim3* grid_out) {
   if (M <= 0 || N <= 0 || K <= 0 || (!C && !o.push_base) || !A.hi || !A.lo || !B.hi || !B.lo || !A.scale || !B.scale) return GSMVI_EINVAL;

@@ -449,6 +449,8 @@ int launch_gemm_h3(cudaStream_t stream, int M, int N, int K, const HView& A, con
 int h3_pair_kernel(int enable);
 // The argument block, the four tensor maps (A_hi, B_hi, A_lo, B_lo) and the grid (tiles, splits) of that launch, for
 // callers that run gemm_h3_body inside a kernel of their own (potrf_h3.cu).
+// fp16 tensor map (SWIZZLE_128B) of a [rows x cols] view with leading dimension ld and the given box
+int h3_make_tmap(CUtensorMap* out, const __half* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows);
 int h3_prepare(int M, int N, int K, const HView& A, const HView& B, float* C, long long ldc, const H3Opts& o, H3Args* out,
                CUtensorMap* maps, dim3* grid_out);
 

@@ -186,7 +186,7 @@ def test_potrf_h3_launch_plan_keeps_every_spin_wait_partner_resident():
             plan = _lib.potrf_h3_plan(D, sms)
             assert [p["j0"] for p in plan] == list(range(0, D, 128))
             ws_floats = lib.gsmvi_workspace_bytes(_lib.WS_POTRF_H3, 0, D) // 4
-            per_buffer = (ws_floats - 64 - 128 * 128) // 2  # floats per partial buffer
+            per_buffer = (ws_floats - 64 - 2 * 128 * 128) // 2  # floats per partial buffer (behind two reduced diagonal tiles)
             for k, p in enumerate(plan):
                 nb = min(128, D - p["j0"])
                 rest = D - p["j0"] - nb
@@ -197,8 +197,9 @@ def test_potrf_h3_launch_plan_keeps_every_spin_wait_partner_resident():
                     row_ctas = p["panel_ctas"] - 1
                     assert row_ctas >= p["helpers"] and row_ctas <= max((rest + 31) // 32, 16)
                     assert (row_ctas >= 1) or rest == 0
-                    if k >= 1:
-                        assert p["helpers"] == 16  # CTA 0 always starts from the helpers' reduced diagonal block
+                    # default (GSMVI_POTRF_LATE_MMA unset): no helper CTAs - CTA 0 starts from the diagonal tile the previous
+                    # launch's update GEMM reduced and forms the K = 128 term itself; with the switch off, 16 helpers
+                    assert p["helpers"] == (16 if (k >= 1 and os.environ.get("GSMVI_POTRF_LATE_MMA", "1")[:1] == "0") else 0)
                     if p["gemm_ctas"]:
                         # the hosted GEMM is the next panel's update: its row tiles and its partial planes fit the buffer
                         Mn = D - p["j0"] - 128

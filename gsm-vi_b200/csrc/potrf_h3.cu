@@ -302,6 +302,8 @@ __global__ void __launch_bounds__(256) potrf_prepare_kernel(const float* __restr
     ready[1] = 0u;  // helper CTA count
     ready[2] = 0u;  // panel epochs: solved row slabs (even values, written by CTA 0's helper warps)
     ready[3] = 0u;  // count of update-GEMM CTAs that have stored a partial of the next diagonal tile
+    ready[4] = 0u;  // row blocks stored / ready[5]: hosted update-GEMM CTAs finished (chained launches wait on these)
+    ready[5] = 0u;
     *flag = 0;
   }
 }
@@ -370,7 +372,36 @@ struct PanelArgs {
   int nb_splits;
   unsigned* nb_count;
   unsigned nb_target;
+  // chained launches (panel k >= 1 of the look-ahead form): the kernel does not wait for the previous grid to drain
+  // (griddepcontrol.wait = completion + flush of the whole grid, measured ~8k cycles from the last CTA's exit to the first
+  // instruction after the wait) but for the two things it produced: all row blocks of the previous panel stored (word
+  // done[0], counted by the row owners) and all CTAs of the update GEMM it hosted finished (done[1]).  Both counters only
+  // grow; the targets are cumulative.  Every CTA of the previous launch is resident before one of this launch can start
+  // (they all ran griddepcontrol.launch_dependents), so nothing here can wait for a CTA that has no SM.
+  int chained;
+  unsigned* done;
+  unsigned rows_target, gemm_target;
 };
+
+// Start of a CTA's dependence on the previous launch (all 256 threads of the panel program).
+__device__ __forceinline__ void wait_previous_launch(const PanelArgs& a) {
+  if (!a.chained) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    return;
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (static_cast<int>(ld_acquire_u32(a.done) - a.rows_target) < 0 || static_cast<int>(ld_acquire_u32(a.done + 1) - a.gemm_target) < 0) {
+      __nanosleep(20);
+      if (clock64() - t0 > 60000000000LL) { printf("gsmvi: potrf chained-launch watchdog (j0=%d block %d)\n", a.j0, blockIdx.x); __trap(); }
+    }
+  }
+  cta_sync();
+  // what follows reads the previous launch's results through L2 (ld.cg) and through TMA (async proxy)
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
 
 // spin (thread 0) until the panel's epoch word reaches `target`, then release the whole CTA
 __device__ __forceinline__ void wait_epoch(const unsigned* ready, unsigned target, int j0) {
@@ -413,8 +444,7 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
   // programmatic dependent launch: the launch itself overlapped the tail of the previous kernel in the stream; everything
   // that reads its results comes after griddepcontrol.wait (CTA 0 first does the set-up that needs none of them)
   if (blockIdx.x != 0) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    wait_previous_launch(a);
     sl = *a.scale_l;
   }
 
@@ -437,8 +467,7 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
       }
       __syncwarp();
     }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    wait_previous_launch(a);
     sl = *a.scale_l;
     PT3C(0);
     if (warp == 0) {
@@ -538,7 +567,7 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
 #pragma unroll
           for (int e = 0; e < PER; ++e) {
             pv[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (off_s[e] >= 0) pv[e] = *reinterpret_cast<const float4*>(pb + (off_s[e] >> 8) * NB + (off_s[e] & 255));
+            if (off_s[e] >= 0) pv[e] = __ldcg(reinterpret_cast<const float4*>(pb + (off_s[e] >> 8) * NB + (off_s[e] & 255)));
           }
 #pragma unroll
           for (int e = 0; e < PER; ++e) { v[e].x -= pv[e].x; v[e].y -= pv[e].y; v[e].z -= pv[e].z; v[e].w -= pv[e].w; }
@@ -902,7 +931,7 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
       hv[r] = (col <= i) ? a.A[static_cast<long long>(j0 + i) * a.lda + j0 + col] : 0.0f;
 #pragma unroll
       for (int sp = 0; sp < MAX_SPLITS; ++sp)
-        hp[r][sp] = (col <= i && sp < a.splits) ? a.partials[sp * a.split_stride + static_cast<long long>(i) * NB + col] : 0.0f;
+        hp[r][sp] = (col <= i && sp < a.splits) ? __ldcg(a.partials + sp * a.split_stride + static_cast<long long>(i) * NB + col) : 0.0f;
     }
     if (a.late && !a.late_mma) {
       stage_lp();
@@ -965,8 +994,8 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
         const int q = tid + (e & 3) * 256, i = q >> 5, j4 = (q & 31) * 4;
         pv[e] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < rows && sp + (e >> 2) < a.splits)
-          pv[e] = *reinterpret_cast<const float4*>(a.partials + (sp + (e >> 2)) * a.split_stride +
-                                                    static_cast<long long>(r0 - j0 + i) * NB + j4);
+          pv[e] = __ldcg(reinterpret_cast<const float4*>(a.partials + (sp + (e >> 2)) * a.split_stride +
+                                                         static_cast<long long>(r0 - j0 + i) * NB + j4));
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -1085,6 +1114,10 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
   }
   if (blockIdx.x == 1) PT3(23);
   cta_sync();
+  if (tid == 0) {  // this row block of the panel is stored (the next launch's CTAs wait for all of them)
+    __threadfence();
+    atomicAdd(a.done, 1u);
+  }
   }  // row blocks
   if (blockIdx.x == 1) PT3(24);
   if (blockIdx.x == 17) PT3(43);
@@ -1145,6 +1178,12 @@ potrf_fused_h3_kernel(const PanelArgs a, const H3Args g, const __grid_constant__
         *reinterpret_cast<float4*>(a.nb_out + i * NB + j4) = v;
       }
     }
+  }
+  // this CTA's share of the hosted update is stored (the next launch's CTAs wait for all of them)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(a.done + 1, 1u);
   }
 }
 
@@ -1258,7 +1297,10 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
     ++plan->count;
   };
   const bool timing = getenv("GSMVI_POTRF_TIMING") != nullptr;
-  static int pdl_env = -1, look_env = -1, late_env = -1;
+  static int pdl_env = -1, look_env = -1, late_env = -1, chain_env = -1;
+  // chained launches are off by default: measured 0.801 ms against 0.784 ms at D = 4096 (profiles/r02_potrf_h3_round2b.txt) -
+  // the ~8k cycles between the last row owner's exit and the next CTA 0's first instruction are not the grid-completion wait
+  if (chain_env < 0) chain_env = env_flag("GSMVI_POTRF_CHAIN", 0);
   if (late_env < 0) late_env = env_flag("GSMVI_POTRF_LATE_MMA", 1);
   if (pdl_env < 0) pdl_env = env_flag("GSMVI_POTRF_PDL", 1);
   if (look_env < 0) look_env = env_flag("GSMVI_POTRF_LOOKAHEAD", 1);
@@ -1277,6 +1319,8 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
   }
   const float* next_base = nullptr;  // reduced diagonal tile the NEXT panel will find (late_mma)
   unsigned base_target = 0;
+  unsigned rows_done = 0, gemm_done = 0;  // row blocks / hosted GEMM CTAs of all launches so far (chained launches wait for them)
+  bool prev_fused = false;
   int next_splits = 0;  // split count of the look-ahead partials the NEXT panel will find in pbuf[(k + 1) & 1]
   for (int j0 = 0, k = 0; j0 < n; j0 += NB, ++k) {
     const int nb = min(NB, n - j0);
@@ -1289,6 +1333,7 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
     pa.d0 = d0; pa.helper_count = ready + 1; pa.helpers = 0; pa.helper_target = 0; pa.late = 0; pa.late_mma = 0;
     pa.base = nullptr; pa.nb_out = nullptr; pa.nb_A = nullptr; pa.nb_partials = nullptr; pa.nb_stride = 0; pa.nb_splits = 0;
     pa.nb_count = ready + 3; pa.nb_target = 0;
+    pa.chained = 0; pa.done = ready + 4; pa.rows_target = rows_done; pa.gemm_target = gemm_done;
     epoch += 8;
     const bool fused = look && nb == NB;
     if (fused) {
@@ -1349,6 +1394,16 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
       if (T > max_ctas - 1 - G) T = max_ctas - 1 - G;
       if (T < (pa.helpers > 0 ? 16 : 0)) return GSMVI_EINVAL;  // cannot happen: G <= max_ctas - 17 by construction
       pa.trsm_ctas = T > 0 ? T : 1;
+      // chained to the previous fused launch: wait for its row blocks and its hosted GEMM instead of the grid's completion
+      pa.chained = (prev_fused && pdl && chain_env == 1) ? 1 : 0;
+      if (pa.chained) {
+        ga.wait_words = ready + 4;
+        ga.wait_rows = pa.rows_target;
+        ga.wait_gemm = pa.gemm_target;
+      }
+      rows_done += static_cast<unsigned>(nblocks);
+      gemm_done += static_cast<unsigned>(G);
+      prev_fused = true;
       const int grid = 1 + T + G;
       if (plan) {
         record(j0, 1, 1 + T, G, host_next ? gtiles : 0, S, pa.splits, pa.helpers);
@@ -1364,6 +1419,8 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
     }
     next_splits = 0;
     next_base = nullptr;
+    prev_fused = false;
+    rows_done += static_cast<unsigned>(nblocks);
     if (j0 > 0) {
       const int tiles = (M + NB - 1) / NB;
       const int S = pick_splits(tiles, j0 / H3_BK, 148);

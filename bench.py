@@ -323,9 +323,10 @@ def run_ours(args):
     peaks, peak_src = measured_peaks()
     # The four launches are timed one by one between synchronisations, i.e. in isolation: the denominator is the BURST
     # figure of MEASURED_PEAKS.json (a kernel timed alone), not the sustained one - unless the clock samples of the timed
-    # region show the part power-capped or running below its maximum clock.
+    # region show the part running below its maximum clock (a sw_power_cap flag with the clock still at its maximum does
+    # not change the denominator: the conservative reading).
     at_max = (clocks.get("sm_mhz") is not None and clocks.get("sm_max_mhz") and
-              clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"] and "sw_power_cap" not in clocks.get("reasons", []))
+              clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"])
     peak_key = "bf16_tflops" if (at_max or clocks.get("sm_mhz") is None) else "bf16_tflops_sustained"
     pipe_peak = peaks[peak_key] if h3 else peaks[peak_key] / 2.0
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
@@ -385,7 +386,11 @@ def run_ours(args):
     # (a) host-fed draws, as the reference works (it samples on the host every iteration, gsmvi/gsm.py:117-119): each
     #     step's draws come from pinned host memory (H2D inside the timed region, streamed one iteration ahead on a copy
     #     stream); (mean, cov) cross at both ends.  On a sharded fit every rank feeds ITS B / world rows.
-    ke = max(4, min(args.steps, 32))  # up to 32 x 64 MiB of pinned draws at the headline shape
+    # iterations of the end-to-end fit: a fit is hundreds of iterations in the reference's examples (niter = 500 .. 5000), so
+    # its fixed part (H2D of (mean, cov), first factorisation, D2H of the result: ~7 ms, ~14 ms when eight ranks move their
+    # 134 MB through the host at once) is amortised over at least 128 iterations where the pinned draw tape allows it
+    # (<= 4 GiB per rank: 64 iterations of 64 MiB at N = 1, 128 from N = 2 on)
+    ke = max(4, min(max(args.steps, 128), int((4 << 30) // (Bl * D * 4))))
     tape = torch.empty(ke, Bl, D, dtype=torch.float32).pin_memory()
     tape.normal_(generator=torch.Generator().manual_seed(1 + rank))
     timed_fit(2, tape)  # untimed warm-up of the API path (first call: engine set-up, cached afterwards)

@@ -107,7 +107,7 @@ __device__ __forceinline__ void h3_split1(float v, float s, __half& hi, __half& 
 template <bool A_MN, bool B_MN>
 __device__ __forceinline__ void gemm_h3_body(const H3Args& args, const CUtensorMap& tmAhi, const CUtensorMap& tmBhi,
                                              const CUtensorMap& tmAlo, const CUtensorMap& tmBlo, uint8_t* smem_raw,
-                                             const int bx, const int by) {
+                                             const int bx, const int by, const bool last_item = true) {
   constexpr int STAGES = H3_STAGES;
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -178,7 +178,7 @@ __device__ __forceinline__ void gemm_h3_body(const H3Args& args, const CUtensorM
   }
   if (warp == 1) {
     ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), H3_TMEM_COLS);
-    ptx::tmem_relinquish();
+    if (last_item) ptx::tmem_relinquish();  // (a CTA that runs the body again must keep its permit to allocate)
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -418,6 +418,11 @@ __device__ __forceinline__ void gemm_h3_body(const H3Args& args, const CUtensorM
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, H3_TMEM_COLS);
   }
+  if (warp == 0 && lane == 0) {
+    // the Cholesky's fused kernel may run this body again in the same CTA (potrf_h3.cu): leave no valid mbarrier behind
+    for (int s = 0; s < 2 * STAGES + 1; ++s) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar_base + 8u * s) : "memory");
+  }
+  __syncthreads();
 }
 
 template <bool A_MN, bool B_MN>

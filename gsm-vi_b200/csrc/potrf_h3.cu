@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(256) potrf_prepare_kernel(const float* __restr
     ready[3] = 0u;  // count of update-GEMM CTAs that have stored a partial of the next diagonal tile
     ready[4] = 0u;  // row blocks stored / ready[5]: hosted update-GEMM CTAs finished (chained launches wait on these)
     ready[5] = 0u;
+    ready[6] = 0u;  // row blocks 0..3 of each panel stored (what the next panel's CTA 0 waits for when chained)
     *flag = 0;
   }
 }
@@ -325,6 +326,15 @@ __global__ void potrf_zero_upper_kernel(float* __restrict__ L, long long ldl, __
 // optional phase timing of one panel (GSMVI_POTRF_TIMING=1): clock64 stamps of CTA 0 / CTA 1, read back by the host
 __device__ long long g_pt3[64];
 #define PT3(i) do { if (TIMING && threadIdx.x == 0 && a.j0 == 8 * NB) g_pt3[i] = clock64(); } while (0)
+// per-panel wall-clock stamps (%globaltimer, ns) of CTA 0: [panel][0] = first instruction after the wait for the previous
+// launch, [1] = diagonal block in shared memory (start phase done), [2] = last stage done
+__device__ unsigned long long g_pt_panel[64][3];
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PTP(i) do { if (TIMING && threadIdx.x == 128 && a.j0 / NB < 64) g_pt_panel[a.j0 / NB][i] = global_ns(); } while (0)
 // CTA 0's stamps come from the first thread of the critical team (physical warp 4)
 #define PT3C(i) do { if (TIMING && threadIdx.x == 128 && a.j0 == 8 * NB) g_pt3[i] = clock64(); } while (0)
 
@@ -378,10 +388,24 @@ struct PanelArgs {
   // done[0], counted by the row owners) and all CTAs of the update GEMM it hosted finished (done[1]).  Both counters only
   // grow; the targets are cumulative.  Every CTA of the previous launch is resident before one of this launch can start
   // (they all ran griddepcontrol.launch_dependents), so nothing here can wait for a CTA that has no SM.
+  // CTA 0 only reads what the first four row blocks of the previous panel stored (the K = 128 term's operand) and the
+  // reduced diagonal tile: it waits for done[2] (row blocks 0..3) and done[1] instead of done[0].
   int chained;
+  int track;  // count finished row blocks / GEMM CTAs in done[] (only needed when launches are chained)
   unsigned* done;
-  unsigned rows_target, gemm_target;
+  unsigned rows_target, gemm_target, first4_target;
 };
+
+// Chained launches only (GSMVI_POTRF_CHAIN=1): thread 0 of the CTA polls the previous launch's completion counters.  Kept out
+// of line: the default path must not carry this code (the panel kernels run from a cold instruction cache every launch, and
+// the same source with this loop inlined measured 0.83 ms per factorisation against 0.78 ms).
+__device__ __noinline__ void poll_previous_launch(const unsigned* w0, unsigned t0w, const unsigned* w1, unsigned t1w, int j0) {
+  const long long t0 = clock64();
+  while (static_cast<int>(ld_acquire_u32(w0) - t0w) < 0 || static_cast<int>(ld_acquire_u32(w1) - t1w) < 0) {
+    __nanosleep(20);
+    if (clock64() - t0 > 60000000000LL) { printf("gsmvi: potrf chained-launch watchdog (j0=%d block %d)\n", j0, blockIdx.x); __trap(); }
+  }
+}
 
 // Start of a CTA's dependence on the previous launch (all 256 threads of the panel program).
 __device__ __forceinline__ void wait_previous_launch(const PanelArgs& a) {
@@ -391,27 +415,31 @@ __device__ __forceinline__ void wait_previous_launch(const PanelArgs& a) {
     return;
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (threadIdx.x == 0) {
-    const long long t0 = clock64();
-    while (static_cast<int>(ld_acquire_u32(a.done) - a.rows_target) < 0 || static_cast<int>(ld_acquire_u32(a.done + 1) - a.gemm_target) < 0) {
-      __nanosleep(20);
-      if (clock64() - t0 > 60000000000LL) { printf("gsmvi: potrf chained-launch watchdog (j0=%d block %d)\n", a.j0, blockIdx.x); __trap(); }
-    }
-  }
+  if (threadIdx.x == 0)
+    poll_previous_launch(blockIdx.x == 0 ? a.done + 2 : a.done, blockIdx.x == 0 ? a.first4_target : a.rows_target, a.done + 1,
+                         a.gemm_target, a.j0);
   cta_sync();
   // what follows reads the previous launch's results through L2 (ld.cg) and through TMA (async proxy)
   asm volatile("fence.proxy.async;" ::: "memory");
 }
 
+// The waits of the panel program keep their polling loops and watchdogs OUT OF LINE: every launch runs this code once
+// from a cold instruction cache, and code that is merely skipped still costs fetches (see poll_previous_launch).
+__device__ __noinline__ void poll_epoch(const unsigned* ready, unsigned target, int j0) {
+  const long long t0 = clock64();
+  while (static_cast<int>(ld_acquire_u32(ready) - target) < 0) {
+    __nanosleep(20);
+    if (clock64() - t0 > 60000000000LL) { printf("gsmvi: potrf panel watchdog (j0=%d epoch %u)\n", j0, target); __trap(); }
+  }
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) { ptx::mbar_wait(bar, parity); }
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
+  if (!ptx::mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+}
+
 // spin (thread 0) until the panel's epoch word reaches `target`, then release the whole CTA
 __device__ __forceinline__ void wait_epoch(const unsigned* ready, unsigned target, int j0) {
-  if (threadIdx.x == 0) {
-    const long long t0 = clock64();
-    while (static_cast<int>(ld_acquire_u32(ready) - target) < 0) {
-      __nanosleep(20);
-      if (clock64() - t0 > 60000000000LL) { printf("gsmvi: potrf panel watchdog (j0=%d epoch %u)\n", j0, target); __trap(); }
-    }
-  }
+  if (threadIdx.x == 0 && static_cast<int>(ld_acquire_u32(ready) - target) < 0) poll_epoch(ready, target, j0);
   cta_sync();
 }
 
@@ -421,7 +449,9 @@ __device__ __forceinline__ void wait_epoch(const unsigned* ready, unsigned targe
 // FULL: nb == 128 (every panel but a ragged last one, which has no rows below it and runs as a single CTA).
 // The straight-line parts are kept small on purpose: each CTA runs this code once per launch with a cold instruction
 // cache, and an earlier fully unrolled version (10.8k SASS instructions) spent more time fetching than computing.
-template <bool FULL, bool TIMING>
+// LEAN: the look-ahead form with the late term on CTA 0's tensor core (the default): no helper CTAs and no split-K partials
+// for CTA 0 - the code of those paths is not compiled into the kernel at all.
+template <bool FULL, bool TIMING, bool LEAN>
 __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, const CUtensorMap* tmLhi,
                                            const CUtensorMap* tmLlo) {
   // [1 KiB-aligned: tf32 hi | lo operand tiles of CTA 0's tensor-core update, 96 x 128 B each] then the fp32 arrays.  The
@@ -432,7 +462,7 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
   float* at = sm + NB * DS;        // [RPC][DS]  TRSM CTAs: their rows of the panel
   float* dT = at + RPC * DS;       // [32][DT]   current 32 x 32 diagonal block, transposed
   float* la = dT + 32 * DT;        // [RPC][DS]  TRSM CTAs, look-ahead: their rows of the previous panel's block-column
-  __shared__ float dinv[32];
+  __shared__ __align__(16) float dinv[32];  // read as float4 by row_follow
   __shared__ int bad;
   __shared__ __align__(8) unsigned long long mma_bar;
   __shared__ __align__(8) unsigned long long late_bar;
@@ -443,15 +473,16 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
   if (tid == 0) bad = 0;
   // programmatic dependent launch: the launch itself overlapped the tail of the previous kernel in the stream; everything
   // that reads its results comes after griddepcontrol.wait (CTA 0 first does the set-up that needs none of them)
+  if (a.chained) sl = *a.scale_l;  // written before the first panel's launch: no need to wait for the previous one
   if (blockIdx.x != 0) {
     wait_previous_launch(a);
-    sl = *a.scale_l;
+    if (!a.chained) sl = *a.scale_l;
   }
 
   if (blockIdx.x == 0) {
     // ------------------------------------------------------------------ diagonal block
     const uint32_t bar_addr = ptx::smem_u32(&mma_bar);
-    const bool late_mma = FULL && a.late_mma != 0;
+    const bool late_mma = FULL && tmLhi != nullptr && a.late_mma != 0;  // (the two-launch kernel passes no tensor maps)
     const uint32_t tmem_cols = late_mma ? 256u : 128u;
     if (warp == 0) {  // tensor-core trailing update below: 128 TMEM columns and one mbarrier (late term: 128 columns more)
       ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), tmem_cols);
@@ -468,8 +499,9 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
       __syncwarp();
     }
     wait_previous_launch(a);
-    sl = *a.scale_l;
+    if (!a.chained) sl = *a.scale_l;
     PT3C(0);
+    PTP(0);
     if (warp == 0) {
       if (late_mma) {
         // the previous panel's block of these 128 rows, fp16 pair: four 128 x 64 boxes (hi | lo, two K halves), SWIZZLE_128B
@@ -495,7 +527,7 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
         ptx::tc_fence_after_sync();
         const uint32_t tb = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(&tmem_slot), 0);
         const uint32_t lt_addr = pt_addr + LATE_TILE_OFF;
-        ptx::mbar_wait(ptx::smem_u32(&late_bar), 0);
+        mbar_wait_lean(ptx::smem_u32(&late_bar), 0);
         ptx::tc_fence_after_sync();
         constexpr uint32_t idesc = make_idesc_f16(false, false);
         if (ptx::elect_one()) {
@@ -538,7 +570,7 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
         PT3C(51);
         issue_late_mma();
         PT3C(52);
-      } else if (a.helpers > 0) {
+      } else if (!LEAN && a.helpers > 0) {
         issue_late_mma();
         // the helper CTAs have formed A11 - sum P in d0: wait for all of them, then one round of loads
         if (tid == 0) {
@@ -561,7 +593,7 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
         }
         issue_late_mma();
 #pragma unroll 1
-        for (int sp = 0; sp < a.splits; ++sp) {
+        for (int sp = 0; sp < (LEAN ? 0 : a.splits); ++sp) {
           const float* pb = a.partials + sp * a.split_stride;
           float4 pv[PER];
 #pragma unroll
@@ -609,7 +641,7 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
     PT3C(53);
     if (late_mma) {
       // s -= L_prev L_prev^T (lower triangle): warp w drains TMEM lane quadrant w % 4, every other 32-column chunk
-      ptx::mbar_wait(bar_addr, 0);
+      mbar_wait_lean(bar_addr, 0);
       ptx::tc_fence_after_sync();
       PT3C(54);
       const int qd = warp & 3, r = 32 * qd + lane;
@@ -643,6 +675,7 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
     }
     const uint32_t late_par = late_mma ? 1u : 0u;  // the late-term commit was phase 0 of the MMA barrier
     PT3C(1);
+    PTP(1);
     float* l11 = a.L + static_cast<long long>(j0) * a.ldl + j0;
     __half* h11 = a.Lhi + static_cast<long long>(j0) * a.ldh + j0;
     __half* o11 = a.Llo + static_cast<long long>(j0) * a.ldh + j0;
@@ -735,7 +768,7 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
           if (b < NB / 32) {
             if (p >= 1) {
               const int qd = role - 4;
-              ptx::mbar_wait(bar_addr, (static_cast<uint32_t>(p - 1) + late_par) & 1u);
+              mbar_wait_lean(bar_addr, (static_cast<uint32_t>(p - 1) + late_par) & 1u);
               ptx::tc_fence_after_sync();
               const int r = 32 * qd + lane;  // accumulator row = row c0 + r of the block
 #pragma unroll 1
@@ -896,6 +929,7 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
     }
     if (tid == 0 && bad) atomicOr(a.flag, 1);
     PT3C(18);
+    PTP(2);
     return;
   }
 
@@ -918,7 +952,7 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
       *reinterpret_cast<float4*>(s + (q >> 5) * DS + (q & 31) * 4) = t[e];
     }
   };
-  if (static_cast<int>(blockIdx.x) <= a.helpers) {
+  if (!LEAN && static_cast<int>(blockIdx.x) <= a.helpers) {
     // helper: rows 8 (blockIdx.x - 1) .. +7 of the diagonal block, A11 - sum P (- the look-ahead term): thread = one
     // column x four rows, so that a warp reads 32 consecutive rows of s (conflict-free float4) and broadcasts its own rows
     const int col = tid & 127, ih = 8 * (blockIdx.x - 1) + 4 * (tid >> 7);
@@ -1114,8 +1148,9 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
   }
   if (blockIdx.x == 1) PT3(23);
   cta_sync();
-  if (tid == 0) {  // this row block of the panel is stored (the next launch's CTAs wait for all of them)
+  if (tid == 0 && a.track) {  // this row block of the panel is stored (the next launch's CTAs wait for all of them)
     __threadfence();
+    if (rb < 4) atomicAdd(a.done + 2, 1u);
     atomicAdd(a.done, 1u);
   }
   }  // row blocks
@@ -1134,7 +1169,7 @@ static_assert(FUSED_SMEM <= 227 * 1024, "fused Cholesky kernel: shared memory");
 template <bool FULL, bool TIMING>
 __global__ void __launch_bounds__(256, 1) potrf_panel_h3_kernel(const PanelArgs a) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
-  panel_body<FULL, TIMING>(a, sm_raw, nullptr, nullptr);
+  panel_body<FULL, TIMING, false>(a, sm_raw, nullptr, nullptr);
 }
 
 // Look-ahead launch of panel k: CTAs [0, panel_ctas) run the panel program above (CTA 0 = diagonal block, then the row
@@ -1142,23 +1177,29 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_h3_kernel(const PanelArgs 
 // the block-columns before panel k (final since the previous launch) - the tensor-core work that used to sit between two
 // panel kernels now fills the SMs the panel leaves idle, and nothing in one role waits for the other.  One CTA per SM
 // (the GEMM role's shared-memory footprint), grid <= number of SMs.
-template <bool TIMING>
+template <bool TIMING, bool LEAN>
 __global__ void __launch_bounds__(H3_THREADS, 1)
 potrf_fused_h3_kernel(const PanelArgs a, const H3Args g, const __grid_constant__ CUtensorMap tmAhi,
                       const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmAlo,
                       const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmLhi,
-                      const __grid_constant__ CUtensorMap tmLlo, const int panel_ctas, const int gemm_tiles) {
+                      const __grid_constant__ CUtensorMap tmLlo, const int panel_ctas, const int gemm_tiles,
+                      const int gemm_items) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
   if (static_cast<int>(blockIdx.x) < panel_ctas) {
-    if (threadIdx.x < 256) panel_body<true, TIMING>(a, sm_raw, &tmLhi, &tmLlo);
+    if (threadIdx.x < 256) panel_body<true, TIMING, LEAN>(a, sm_raw, &tmLhi, &tmLlo);
     return;
   }
-  const int w = blockIdx.x - panel_ctas;
-  gemm_h3_body<false, false>(g, tmAhi, tmBhi, tmAlo, tmBlo, sm_raw, w % gemm_tiles, w / gemm_tiles);
+  // work items (row tile, split) of the hosted update, round-robin over the GEMM-role CTAs (one item each except when the
+  // row owners need the SMs: every 32-row block of the panel gets a CTA of its own first)
+  const int gemm_ctas = static_cast<int>(gridDim.x) - panel_ctas;
+#pragma unroll 1
+  for (int w = blockIdx.x - panel_ctas; w < gemm_items; w += gemm_ctas) {
+  gemm_h3_body<false, false>(g, tmAhi, tmBhi, tmAlo, tmBlo, sm_raw, w % gemm_tiles, w / gemm_tiles, w + gemm_ctas >= gemm_items);
   if (a.nb_out != nullptr && w % gemm_tiles == 0) {
     // row tile 0 of the hosted update is the next panel's diagonal tile.  gemm_h3_body ended with __syncthreads(): this
     // CTA's partial plane is stored; the last of the tile's CTAs reduces all planes (fixed order) into nb_out.
     __shared__ unsigned is_last;
+    __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
       is_last = (atomicAdd(a.nb_count, 1u) + 1u == a.nb_target) ? 1u : 0u;
@@ -1179,11 +1220,15 @@ potrf_fused_h3_kernel(const PanelArgs a, const H3Args g, const __grid_constant__
       }
     }
   }
-  // this CTA's share of the hosted update is stored (the next launch's CTAs wait for all of them)
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(a.done + 1, 1u);
+  }
+  // this CTA's share of the hosted update is stored (the next launch's CTAs wait for all of them)
+  if (a.track) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(a.done + 1, 1u);
+    }
   }
 }
 
@@ -1256,8 +1301,10 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
     cudaError_t e = cudaFuncSetAttribute(potrf_panel_h3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_panel_h3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_panel_h3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_fused_h3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_fused_h3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_fused_h3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_fused_h3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_fused_h3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_fused_h3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set.set();
   }
@@ -1319,6 +1366,7 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
   }
   const float* next_base = nullptr;  // reduced diagonal tile the NEXT panel will find (late_mma)
   unsigned base_target = 0;
+  unsigned first4_done = 0;  // row blocks 0..3 of all panels so far
   unsigned rows_done = 0, gemm_done = 0;  // row blocks / hosted GEMM CTAs of all launches so far (chained launches wait for them)
   bool prev_fused = false;
   int next_splits = 0;  // split count of the look-ahead partials the NEXT panel will find in pbuf[(k + 1) & 1]
@@ -1333,7 +1381,7 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
     pa.d0 = d0; pa.helper_count = ready + 1; pa.helpers = 0; pa.helper_target = 0; pa.late = 0; pa.late_mma = 0;
     pa.base = nullptr; pa.nb_out = nullptr; pa.nb_A = nullptr; pa.nb_partials = nullptr; pa.nb_stride = 0; pa.nb_splits = 0;
     pa.nb_count = ready + 3; pa.nb_target = 0;
-    pa.chained = 0; pa.done = ready + 4; pa.rows_target = rows_done; pa.gemm_target = gemm_done;
+    pa.chained = 0; pa.track = (pdl && chain_env == 1) ? 1 : 0; pa.done = ready + 4; pa.rows_target = rows_done; pa.gemm_target = gemm_done; pa.first4_target = first4_done;
     epoch += 8;
     const bool fused = look && nb == NB;
     if (fused) {
@@ -1353,7 +1401,7 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
       // ---- hosted work: update of panel k+1 (if it is a full panel) with block-columns [0, j0)
       const int nj0 = j0 + NB;
       const bool host_next = k >= 1 && nj0 < n && n - nj0 >= NB;
-      int G = 0, gtiles = 1, S = 0;
+      int G = 0, gtiles = 1, S = 0, gitems = 0;
       H3Args ga = {};
       CUtensorMap tm[4] = {};
       if (host_next) {
@@ -1366,6 +1414,13 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
           if (S > s_ws) S = s_ws;
         }
         G = gtiles * S;
+        gitems = G;
+        {  // every row block of this panel gets its own CTA first; the update's items share what is left
+          static int gcap_env = -1;
+          if (gcap_env < 0) gcap_env = env_flag("GSMVI_POTRF_GCAP", 1);
+          const int room = max_ctas - 1 - (nblocks > 0 ? nblocks : 1);
+          if (gcap_env == 1 && G > room) G = room > 1 ? room : 1;
+        }
         HView va{Lhi + static_cast<long long>(nj0) * Lh.ld, Llo + static_cast<long long>(nj0) * Lh.ld, Mn, j0, Lh.ld, Lh.scale};
         HView vb{Lhi + static_cast<long long>(nj0) * Lh.ld, Llo + static_cast<long long>(nj0) * Lh.ld, NB, j0, Lh.ld, Lh.scale};
         H3Opts o;
@@ -1402,6 +1457,7 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
         ga.wait_gemm = pa.gemm_target;
       }
       rows_done += static_cast<unsigned>(nblocks);
+      first4_done += static_cast<unsigned>(nblocks < 4 ? nblocks : 4);
       gemm_done += static_cast<unsigned>(G);
       prev_fused = true;
       const int grid = 1 + T + G;
@@ -1410,10 +1466,9 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
         continue;
       }
       cudaError_t le;
-      if (timing)
-        le = launch_maybe_pdl(potrf_fused_h3_kernel<true>, grid, H3_THREADS, FUSED_SMEM, stream, pdl, pa, ga, tm[0], tm[1], tm[2], tm[3], tmL[0], tmL[1], 1 + T, gtiles);
-      else
-        le = launch_maybe_pdl(potrf_fused_h3_kernel<false>, grid, H3_THREADS, FUSED_SMEM, stream, pdl, pa, ga, tm[0], tm[1], tm[2], tm[3], tmL[0], tmL[1], 1 + T, gtiles);
+      auto kern = late_mma ? (timing ? potrf_fused_h3_kernel<true, true> : potrf_fused_h3_kernel<false, true>)
+                           : (timing ? potrf_fused_h3_kernel<true, false> : potrf_fused_h3_kernel<false, false>);
+      le = launch_maybe_pdl(kern, grid, H3_THREADS, FUSED_SMEM, stream, pdl, pa, ga, tm[0], tm[1], tm[2], tm[3], tmL[0], tmL[1], 1 + T, gtiles, gitems);
       if (le != cudaSuccess) return static_cast<int>(le);
       continue;
     }
@@ -1421,6 +1476,7 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
     next_base = nullptr;
     prev_fused = false;
     rows_done += static_cast<unsigned>(nblocks);
+    first4_done += static_cast<unsigned>(nblocks < 4 ? nblocks : 4);
     if (j0 > 0) {
       const int tiles = (M + NB - 1) / NB;
       const int S = pick_splits(tiles, j0 / H3_BK, 148);
@@ -1459,6 +1515,16 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
   if (timing && n > NB * 9) {
     long long h[64];
     cudaStreamSynchronize(stream);
+    {
+      static unsigned long long hp[64][3];
+      cudaMemcpyFromSymbol(hp, g_pt_panel, sizeof(hp));
+      const int np = (n + NB - 1) / NB < 64 ? (n + NB - 1) / NB : 64;
+      fprintf(stderr, "[potrf_h3 panels] CTA 0 per panel, ns: start phase / stages / gap to the next panel's start:");
+      for (int k = 0; k < np; ++k)
+        fprintf(stderr, " %d:%lld/%lld/%lld", k, (long long)(hp[k][1] - hp[k][0]), (long long)(hp[k][2] - hp[k][1]),
+                k + 1 < np ? (long long)(hp[k + 1][0] - hp[k][2]) : 0LL);
+      fprintf(stderr, "\n");
+    }
     cudaMemcpyFromSymbol(h, g_pt3, sizeof(h));
     fprintf(stderr, "[potrf_h3 panel 8] CTA0 start phase (cycles since its first stamp): setup + TMA issued %lld, base loads issued %lld, late MMAs issued %lld, "
             "base in smem %lld, late MMAs complete %lld, drained %lld\n", h[50] - h[0], h[51] - h[0], h[52] - h[0], h[53] - h[0], h[54] - h[0], h[1] - h[0]);

@@ -560,17 +560,20 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
         const int gi = (tid >> 5) + 8 * e, gj = 4 * (tid & 31);
         off_s[e] = (gj <= gi) ? ((gi << 8) | gj) : -1;
       }
-      if (a.base != nullptr) {
-        // A11 - sum P was formed by the previous launch (the last of the update GEMM's CTAs that hold a partial of this tile)
+      if (LEAN || a.base != nullptr) {
+        // A11 - sum P was formed by the previous launch (the last of the update GEMM's CTAs that hold a partial of this tile);
+        // LEAN: the first two panels, which have no such term, read A11 itself through the same code
+        const float* src = a.base != nullptr ? a.base : a11;
+        const long long ld = a.base != nullptr ? NB : a.lda;
 #pragma unroll
         for (int e = 0; e < PER; ++e) {
           v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (off_s[e] >= 0) v[e] = __ldcg(reinterpret_cast<const float4*>(a.base + (off_s[e] >> 8) * NB + (off_s[e] & 255)));
+          if (off_s[e] >= 0) v[e] = __ldcg(reinterpret_cast<const float4*>(src + (off_s[e] >> 8) * ld + (off_s[e] & 255)));
         }
         PT3C(51);
         issue_late_mma();
         PT3C(52);
-      } else if (!LEAN && a.helpers > 0) {
+      } else if (a.helpers > 0) {
         issue_late_mma();
         // the helper CTAs have formed A11 - sum P in d0: wait for all of them, then one round of loads
         if (tid == 0) {
@@ -593,7 +596,7 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
         }
         issue_late_mma();
 #pragma unroll 1
-        for (int sp = 0; sp < (LEAN ? 0 : a.splits); ++sp) {
+        for (int sp = 0; sp < a.splits; ++sp) {
           const float* pb = a.partials + sp * a.split_stride;
           float4 pv[PER];
 #pragma unroll

@@ -145,8 +145,10 @@ int gsmvi_potrf_check(const float* Sigma, long long lds, float* L, long long ldl
 
 /* Same contract as gsmvi_potrf_check on the scaled 3xFP16 engine: left-looking panels (one long-K split-K update GEMM +
  * one panel kernel each; for 512 <= D <= ~17k one fused launch per panel whose spare CTAs run the next panel's update
- * GEMM - environment GSMVI_POTRF_LOOKAHEAD=0 selects the two-launch form), L also written as the fp16 pair *L_split (scale from max |Sigma_ii|) for the sampler's and the
- * later panels' TMA loads.  zero_upper = 0: the blocks above the diagonal are left untouched (valid for a buffer that
+ * GEMM and reduce the next diagonal tile, while CTA 0 forms the previous panel's own K = 128 term on its tensor core -
+ * environment GSMVI_POTRF_LOOKAHEAD=0 selects the two-launch form, GSMVI_POTRF_LATE_MMA=0 the round-2a form with 16
+ * helper CTAs, GSMVI_POTRF_CHAIN=1 flag-chained launches), L also written as the fp16 pair *L_split (scale from
+ * max |Sigma_ii|) for the sampler's and the later panels' TMA loads.  zero_upper = 0: the blocks above the diagonal are left untouched (valid for a buffer that
  * was zeroed once).  workspace: gsmvi_workspace_bytes(GSMVI_WS_POTRF_H3, 0, D). */
 int gsmvi_potrf_h3(const float* Sigma, long long lds, float* L, long long ldl, const gsmvi_h3_operand* L_split, int D,
                    int* bad_flag, void* workspace, int zero_upper, void* stream);

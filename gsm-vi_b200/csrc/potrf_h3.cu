@@ -94,27 +94,32 @@ __device__ __forceinline__ void chol32_coop(float* __restrict__ blk, float* __re
         d[r][0] = t0.x; d[r][1] = t0.y; d[r][2] = t0.z; d[r][3] = t0.w; d[r][4] = t1.x; d[r][5] = t1.y; d[r][6] = t1.z; d[r][7] = t1.w;
       }
       float rinv[8];
-      float r;
-      asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d[0][0]));
-      r = r * fmaf(-0.5f * d[0][0], r * r, 1.5f);
+      // The chain from pivot to pivot runs on the raw rsqrt.approx value (relative error 2^-22.9): next diagonal entry =
+      // d - (l * ra)^2, then straight into the next rsqrt.  The Newton step that brings 1 / l_jj to full fp32 accuracy is
+      // taken off that chain (three dependent operations per pivot, 128 pivots per panel); everything that is stored -
+      // the column of L, 1 / l_jj - uses the refined value.
+      float ra;
+      asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(d[0][0]));
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        rinv[j] = r;
+        const float djj = d[j][j];
         float rn = 0.0f;
         if (j < 7) {  // the entries the next pivot depends on first, and its rsqrt right behind them
-          d[j + 1][j] *= r;
-          d[j + 1][j + 1] -= d[j + 1][j] * d[j + 1][j];
-          const float dn = d[j + 1][j + 1];
+          const float t = d[j + 1][j] * ra;
+          const float dn = d[j + 1][j + 1] - t * t;
+          d[j + 1][j + 1] = dn;
           asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(dn));
-          rn = rn * fmaf(-0.5f * dn, rn * rn, 1.5f);
         }
+        const float r = ra * fmaf(-0.5f * djj, ra * ra, 1.5f);
+        rinv[j] = r;
+        if (j < 7) d[j + 1][j] *= r;
 #pragma unroll
         for (int i = j + 2; i < 8; ++i) d[i][j] *= r;
 #pragma unroll
         for (int i = j + 2; i < 8; ++i)
 #pragma unroll
           for (int k = j + 1; k <= i; ++k) d[i][k] -= d[i][j] * d[k][j];
-        r = rn;
+        ra = rn;
       }
       // this row against the pivot block, right-looking: x_j = a_j / l_jj, a_k -= x_j l_kj
 #pragma unroll
@@ -143,15 +148,27 @@ __device__ __forceinline__ void chol32_coop(float* __restrict__ blk, float* __re
       // rank-8 update of columns cq+8 .. 31: thread (row i = lane, column group = warp) takes columns cq+8+warp, +4, ...
       const float4 x0 = *reinterpret_cast<const float4*>(blk + lane * DS + cq);
       const float4 x1 = *reinterpret_cast<const float4*>(blk + lane * DS + cq + 4);
-#pragma unroll 2
-      for (int k = cq + 8 + warp; k < 32; k += 4) {
-        if (k > lane) continue;  // above the diagonal
-        const float4 l0 = *reinterpret_cast<const float4*>(blk + k * DS + cq);
-        const float4 l1 = *reinterpret_cast<const float4*>(blk + k * DS + cq + 4);
-        float acc0 = blk[lane * DS + k], acc1 = 0.0f;
-        acc0 -= x0.x * l0.x; acc1 -= x0.y * l0.y; acc0 -= x0.z * l0.z; acc1 -= x0.w * l0.w;
-        acc0 -= x1.x * l1.x; acc1 -= x1.y * l1.y; acc0 -= x1.z * l1.z; acc1 -= x1.w * l1.w;
-        blk[lane * DS + k] = acc0 + acc1;
+      // all of a thread's (at most six) columns at once: loads first, so that one shared-memory latency is exposed, not six
+      float4 l0[6], l1[6];
+      float cur[6];
+#pragma unroll
+      for (int m = 0; m < 6; ++m) {
+        const int k = cq + 8 + warp + 4 * m;
+        if (k < 32 && k <= lane) {  // on or below the diagonal
+          l0[m] = *reinterpret_cast<const float4*>(blk + k * DS + cq);
+          l1[m] = *reinterpret_cast<const float4*>(blk + k * DS + cq + 4);
+          cur[m] = blk[lane * DS + k];
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < 6; ++m) {
+        const int k = cq + 8 + warp + 4 * m;
+        if (k < 32 && k <= lane) {
+          float acc0 = cur[m], acc1 = 0.0f;
+          acc0 -= x0.x * l0[m].x; acc1 -= x0.y * l0[m].y; acc0 -= x0.z * l0[m].z; acc1 -= x0.w * l0[m].w;
+          acc0 -= x1.x * l1[m].x; acc1 -= x1.y * l1[m].y; acc0 -= x1.z * l1[m].z; acc1 -= x1.w * l1[m].w;
+          blk[lane * DS + k] = acc0 + acc1;
+        }
       }
       named_bar_sync(10, 128);
     }

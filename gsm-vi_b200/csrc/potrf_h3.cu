@@ -219,22 +219,59 @@ __device__ __forceinline__ void row_follow(const float* __restrict__ blk, const 
       }
       *reinterpret_cast<float4*>(myrow + cq) = make_float4(x[0], x[1], x[2], x[3]);
       *reinterpret_cast<float4*>(myrow + cq + 4) = make_float4(x[4], x[5], x[6], x[7]);
-      // ... and its remaining columns: v_k -= sum_j x_j l_kj with row k of the block (its entries in this group are final)
-#pragma unroll 2
-      for (int k4 = cq + 8; k4 < 32; k4 += 4) {
-        float4 o = *reinterpret_cast<const float4*>(myrow + k4);
-        float* ov = reinterpret_cast<float*>(&o);
+      // ... and the warp's 32 rows' remaining columns: V[32 x (24 - 8q)] -= X[32 x 8] L[cq+8.., cq..cq+7]^T on the warp-level
+      // tensor path (mma.sync m16n8k8 tf32, hi*hi + lo*hi + hi*lo; fragments straight from shared memory - the row stride of
+      // 132 words makes the (groupID, threadID_in_group) pattern conflict-free).  As one-thread-per-row FMAs this update
+      // (192 FFMAs + 54 broadcast LDS.128 per thread at q = 0) made a column group of the rows slower than the team's eight
+      // pivots, and the rows fell behind the factorisation they are meant to hide under.
+      if (q < 3) {
+        __syncwarp();
+        const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+        float* rowbase = myrow - lane * DS;  // row 0 of this warp's 32 rows, first column of the block
+        uint32_t ah[2][4], al[2][4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float4 l0 = *reinterpret_cast<const float4*>(blk + (k4 + t) * DS + cq);
-          const float4 l1 = *reinterpret_cast<const float4*>(blk + (k4 + t) * DS + cq + 4);
-          float a0 = x[0] * l0.x, a1 = x[1] * l0.y;
-          a0 = fmaf(x[2], l0.z, a0); a1 = fmaf(x[3], l0.w, a1);
-          a0 = fmaf(x[4], l1.x, a0); a1 = fmaf(x[5], l1.y, a1);
-          a0 = fmaf(x[6], l1.z, a0); a1 = fmaf(x[7], l1.w, a1);
-          ov[t] -= a0 + a1;
+        for (int mt = 0; mt < 2; ++mt) {
+          const float* xa = rowbase + (16 * mt) * DS + cq;
+          const float av[4] = {xa[g * DS + t], xa[(g + 8) * DS + t], xa[g * DS + t + 4], xa[(g + 8) * DS + t + 4]};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float h = tf32_rna_alu(av[e]);
+            ah[mt][e] = __float_as_uint(h);
+            al[mt][e] = __float_as_uint(tf32_rna_alu(av[e] - h));
+          }
         }
-        *reinterpret_cast<float4*>(myrow + k4) = o;
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+          if (nt < 3 - q) {
+            const float* lb = blk + (cq + 8 + 8 * nt + g) * DS + cq;  // row cq+8+8nt+g of the block: B[k][n] = l_{n,k}
+            const float b0 = lb[t], b1 = lb[t + 4];
+            const float b0h = tf32_rna_alu(b0), b1h = tf32_rna_alu(b1);
+            const uint32_t bh[2] = {__float_as_uint(b0h), __float_as_uint(b1h)};
+            const uint32_t bl[2] = {__float_as_uint(tf32_rna_alu(b0 - b0h)), __float_as_uint(tf32_rna_alu(b1 - b1h))};
+            float acc[2][4], cor[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) acc[mt][e] = cor[mt][e] = 0.0f;
+            ptx::mma_tf32_16x8x8(acc[0], ah[0], bh);
+            ptx::mma_tf32_16x8x8(acc[1], ah[1], bh);
+            ptx::mma_tf32_16x8x8(cor[0], al[0], bh);
+            ptx::mma_tf32_16x8x8(cor[1], al[1], bh);
+            ptx::mma_tf32_16x8x8(cor[0], ah[0], bl);
+            ptx::mma_tf32_16x8x8(cor[1], ah[1], bl);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+              for (int hrow = 0; hrow < 2; ++hrow) {
+                float2* dst = reinterpret_cast<float2*>(rowbase + (16 * mt + g + 8 * hrow) * DS + cq + 8 + 8 * nt + 2 * t);
+                float2 o = *dst;
+                o.x -= acc[mt][2 * hrow] + cor[mt][2 * hrow];
+                o.y -= acc[mt][2 * hrow + 1] + cor[mt][2 * hrow + 1];
+                *dst = o;
+              }
+          }
+        }
+        __syncwarp();
       }
     }
   }

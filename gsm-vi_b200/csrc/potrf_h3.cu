@@ -1115,21 +1115,33 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
       }
     }
     cta_sync();
-    const int col = tid & 127, rg = 16 * (tid >> 7);
-    float acc[16];
+    // thread = 4 rows (the warp's: broadcast reads) x 4 columns (lane, lane + 32, ...: conflict-free reads): eight 16-byte
+    // loads per 64 FMAs.  (One column x 16 rows per thread needed seventeen, and the shared-memory pipe, not the FMA pipe,
+    // set the pace of this loop: 544 LDS.128 per thread in eight warps.)
+    float acc[4][4];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) acc[r] = 0.0f;
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+    const float* xrow = la + (4 * warp) * DS;
+    const float* bcol = s + lane * DS;
 #pragma unroll 2
     for (int k = 0; k < NB; k += 4) {
-      const float4 b = *reinterpret_cast<const float4*>(s + col * DS + k);
+      float4 x[4], b[4];
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const float4 x = *reinterpret_cast<const float4*>(la + (rg + r) * DS + k);
-        acc[r] = fmaf(x.x, b.x, fmaf(x.y, b.y, fmaf(x.z, b.z, fmaf(x.w, b.w, acc[r]))));
-      }
+      for (int r = 0; r < 4; ++r) x[r] = *reinterpret_cast<const float4*>(xrow + r * DS + k);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) b[c] = *reinterpret_cast<const float4*>(bcol + (32 * c) * DS + k);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          acc[r][c] = fmaf(x[r].x, b[c].x, fmaf(x[r].y, b[c].y, fmaf(x[r].z, b[c].z, fmaf(x[r].w, b[c].w, acc[r][c]))));
     }
 #pragma unroll
-    for (int r = 0; r < 16; ++r) at[(rg + r) * DS + col] -= acc[r];
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) at[(4 * warp + r) * DS + lane + 32 * c] -= acc[r][c];
     lp_staged = false;  // the stages below overwrite s
   }
   if (blockIdx.x == 1) PT3(21);

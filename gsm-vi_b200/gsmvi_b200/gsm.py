@@ -119,6 +119,7 @@ class GSMEngine:
         self.copy_stream = None
         self._side_stream = None
         self._side_ok = __import__("os").environ.get("GSMVI_SIDE_STREAM", "1")[:1] != "0"
+        self._philox_early = __import__("os").environ.get("GSMVI_SIDE_PHILOX", "early") != "chol"
         if self.h3:
             # scaled 3xFP16 engine: every GEMM operand lives as an fp16 (hi, lo) pair + power-of-two scale
             H = L.HOperand
@@ -355,6 +356,18 @@ class GSMEngine:
         tm("draw")
         L.sample_h3(self.mu, self.Lh, self.Zh, self.Xb, sl[0:1], B, D)
         tm("sample")
+        # The NEXT iteration's Philox draws depend on nothing but the counter and on the sampler having read this
+        # iteration's: they run on the second stream beside the score / W GEMMs (ALU work under tensor-core work, a few
+        # small CTAs next to the GEMM's one big CTA per SM) instead of beside the Cholesky, whose latency chain they slowed
+        # by more than half of what they hid (GSMVI_SIDE_PHILOX=chol keeps the old placement)
+        early = None
+        if not graph and self._side_ok and self._philox_early and self.z_tape is None:
+            early = self._side()
+            self._ev_fork2.record()
+            with torch.cuda.stream(early):
+                early.wait_event(self._ev_fork2)
+                L.philox_normal_h3(self.Zh, B, D, self.seed, (i + 1) * self.world + self.rank)
+                self.z_drawn_for = i + 1
         if tgt is not None:
             # (the GEMMs can also write their result's fp16 split themselves with an a-priori bound as scale -
             # gsmvi_h3_bound_scales / X_split, G_split - but the strided 8-byte stores lengthen the un-overlapped epilogue
@@ -390,7 +403,7 @@ class GSMEngine:
             with torch.cuda.stream(side):
                 side.wait_event(self._ev_fork)
                 self.Snh.split_from(self.Sn, absmax=sl[2:3])
-                if self.z_tape is None:
+                if self.z_tape is None and early is None:
                     L.philox_normal_h3(self.Zh, B, D, self.seed, (i + 1) * self.world + self.rank)
                     self.z_drawn_for = i + 1
                 self._ev_join.record()
@@ -416,7 +429,7 @@ class GSMEngine:
         """Second stream (and its fork / join events) for the passes that run beside the Cholesky."""
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream()
-            self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+            self._ev_fork, self._ev_join, self._ev_fork2 = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         return self._side_stream
 
     def step_h3(self, i):

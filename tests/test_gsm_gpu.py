@@ -113,6 +113,51 @@ def test_potrf_h3_matches_cholesky(lib, D):
     record("potrf_h3", dict(D=D, relF_L=relF(Lv, Lref)))
 
 
+POTRF_FORM_WORKER = r"""
+import os, sys
+ROOT = sys.argv[1]
+sys.path.insert(0, os.path.join(ROOT, "gsm-vi_b200"))
+import numpy as np, torch
+from gsmvi_b200 import _lib as L
+from gsmvi_b200._util import new_mat
+for D in (640, 1000, 2048):
+    rng = np.random.RandomState(D)
+    A = rng.normal(size=(D, D))
+    S = A @ A.T / D + 0.05 * np.eye(D)
+    Sb, Sv = new_mat(D, D, "cuda"); Sv.copy_(torch.as_tensor(S, dtype=torch.float32))
+    Lb, Lv = new_mat(D, D, "cuda"); Lv.fill_(float("nan"))
+    Lh = L.HOperand(D, D, "cuda")
+    bad = torch.ones(1, dtype=torch.int32, device="cuda")
+    ws = torch.empty(L.workspace_bytes(L.WS_POTRF_H3, 0, D) // 4, device="cuda")
+    for _ in range(2):
+        L.potrf_h3(Sb, Lb, Lh, D, bad, ws, zero_upper=True)
+    torch.cuda.synchronize()
+    ref = np.linalg.cholesky(Sv.cpu().double().numpy())
+    err = np.linalg.norm(Lv.cpu().double().numpy() - ref) / np.linalg.norm(ref)
+    print("D=%d bad=%d relF=%.2e" % (D, int(bad.item()), err), flush=True)
+    assert int(bad.item()) == 0 and err < 2e-5, (D, err)
+    # a matrix that is not positive definite is still flagged in this form
+    Sv[D // 2, D // 2] = -1.0
+    L.potrf_h3(Sb, Lb, Lh, D, bad, ws, zero_upper=True)
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 1, D
+print("ok")
+"""
+
+
+@pytest.mark.parametrize("env", [{"GSMVI_POTRF_LATE_MMA": "0"}, {"GSMVI_POTRF_CHAIN": "1"}, {"GSMVI_POTRF_LOOKAHEAD": "0"},
+                                 {"GSMVI_POTRF_PDL": "0"}])
+def test_potrf_h3_alternative_forms(lib, env):
+    """The non-default forms of the factorisation stay selectable (environment, read once per process: hence a subprocess):
+    the round-2a form with helper CTAs, flag-chained launches, the two-launch form, launches without programmatic
+    dependence.  Each must factor like the default and flag an indefinite matrix."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ); e.update(env)
+    r = subprocess.run([sys.executable, "-c", POTRF_FORM_WORKER, root], env=e, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, (env, r.stdout[-2000:], r.stderr[-2000:])
+
+
 @pytest.mark.parametrize("D,kind", [(64, "indef"), (300, "indef"), (300, "nan"), (130, "late"), (640, "indef"), (1000, "nan"), (768, "late")])
 def test_potrf_h3_flags_bad_matrices(lib, D, kind):
     rng = np.random.RandomState(1)

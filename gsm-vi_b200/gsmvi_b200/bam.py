@@ -10,6 +10,7 @@ import torch
 
 from . import _lib as L
 from ._util import device, key_to_seed, new_mat, new_vec, to_dev
+from .gsm import _monitor_params
 
 
 def _update(samples, vs, mu0, S0, reg, lowrank, npass=3, jitter=0.0):
@@ -222,6 +223,10 @@ class BaMEngine:
     def cov(self):
         return self.S
 
+    def chol_buffer(self):
+        """Padded fp32 buffer of the lower Cholesky factor of cov(): the goodness check's factor of the accepted state."""
+        return self.Lb
+
     def close(self, collective=True):
         """Release the peer-mapped solve workspace of a tensor-parallel fit (collective: every rank calls it)."""
         if self.peer is not None:
@@ -280,7 +285,7 @@ class BaM:
             if verbose and (i % every == 0):
                 print(f"Iteration {i} of {niter}")
             if monitor is not None and (i % monitor.checkpoint) == 0:  # bam.py:182-185
-                monitor(i, [eng.mean(), eng.cov()], self.lp, key, nevals=nevals)
+                monitor(i, _monitor_params(eng), self.lp, key, nevals=nevals)
                 nevals = 0
             j = 0
             while True:  # bam.py:188-206: retry on ANY exception (bad sample, failed callback, ...)
@@ -300,7 +305,7 @@ class BaM:
             if not eng.accept_or_revert() and verbose:  # bam.py:208-212
                 print("Bad update for covariance matrix. Revert")
         if monitor is not None:  # bam.py:214-215
-            monitor(i, [eng.mean(), eng.cov()], self.lp, key, nevals=nevals)
+            monitor(i, _monitor_params(eng), self.lp, key, nevals=nevals)
         self.n_reverts = eng.n_reverts
         self.ns_iters = eng.ns_iters
         return eng.mean().clone(), eng.cov().clone()

@@ -60,6 +60,15 @@ def launch_count(D, h3=True, tape=False, builtin_target=True, world=1, lookahead
     return (0 if tape else 1) + 1 + (1 if builtin_target else 0) + upd + potrf + 1 + (2 if world > 1 else 0)
 
 
+def _monitor_params(eng):
+    """[mean, cov] for a monitor call (gsmvi/gsm.py:113), carrying the engine's Cholesky factor of that covariance when the
+    engine keeps one as a plain fp32 matrix (monitors.MonitorParams.chol): KLMonitor then does not factor it again."""
+    from .monitors import MonitorParams
+    params = MonitorParams([eng.mean(), eng.cov()])
+    params.chol = eng.chol_buffer() if hasattr(eng, "chol_buffer") else None
+    return params
+
+
 class GSMEngine:
     """Device-resident state and workspaces of one GSM fit; `step(i)` is one loop body of gsmvi/gsm.py:107-129
     (sample -> score -> update -> goodness check -> accept/revert).  GSM.fit drives it; bench.py times it.
@@ -544,6 +553,11 @@ class GSMEngine:
     def cov(self):
         return self.S
 
+    def chol_buffer(self):
+        """Padded fp32 buffer of the lower Cholesky factor of cov() (zeros above the diagonal): after a step the proposal's
+        factor if it was accepted, the previous state's if not - the device-side commit keeps (mu, Sigma, L) together."""
+        return self.Lb
+
 
 class GSMSmall64Engine:
     """fp64 engine for D <= 64 (csrc/gsm_small64.cu): the reference's numpy path (gsmvi/gsm_numpy.py:60-129, BASELINE
@@ -719,7 +733,7 @@ class GSM:
                 if verbose and (i % every == 0):  # gsm.py:108-109
                     print(f"Iteration {i} of {niter}")
                 if monitor is not None and (i % monitor.checkpoint) == 0:  # gsm.py:111-114
-                    monitor(i, [eng.mean(), eng.cov()], self.lp, key, nevals=nevals)
+                    monitor(i, _monitor_params(eng), self.lp, key, nevals=nevals)
                     nevals = 0
                 if chunked:
                     # fp64 path with the built-in target: every iteration up to the next monitor checkpoint in ONE launch
@@ -737,7 +751,7 @@ class GSM:
                 i += 1
             i = niter
             if monitor is not None:  # gsm.py:131-132
-                monitor(i, [eng.mean(), eng.cov()], self.lp, key, nevals=nevals)
+                monitor(i, _monitor_params(eng), self.lp, key, nevals=nevals)
             self.n_reverts = eng.n_reverts
             mean, cov = eng.mean().clone(), eng.cov().clone()
         except BaseException:

@@ -19,6 +19,12 @@ def _as_float(v):
     return float(np.sum(np.asarray(v, dtype=np.float64)))
 
 
+class MonitorParams(list):
+    """[mean, cov] as the reference passes them to a monitor (gsmvi/gsm.py:113), plus `chol`: the padded fp32 buffer of the
+    lower Cholesky factor of `cov` that the fit's engine already holds (None: the monitor factors `cov` itself)."""
+    chol = None
+
+
 @dataclass
 class KLMonitor:
     """Monitor reverse (and optionally forward) KL divergence during optimisation (gsmvi/monitors.py:43-67)."""
@@ -32,6 +38,18 @@ class KLMonitor:
         self.fkl = []
         self.nevals = []
         self._calls = 0
+        self._bufs = {}  # work buffers of the last (N, D, device): the monitor is called every `checkpoint` iterations
+
+    def _work(self, N, D, dev):
+        key = (N, D, str(dev))
+        w = self._bufs.get(key)
+        if w is None:
+            self._bufs.clear()
+            w = self._bufs[key] = dict(
+                S=new_mat(D, D, dev), L=new_mat(D, D, dev), mu=new_vec(D, dev), Z=new_mat(N, D, dev), X=new_mat(N, D, dev),
+                bad=torch.zeros(1, dtype=torch.int32, device=dev), out=torch.zeros(1, dtype=torch.float64, device=dev),
+                ws=torch.empty(L.workspace_bytes(L.WS_POTRF, N, D) // 4, dtype=torch.float32, device=dev))
+        return w
 
     def reset(self, batch_size_kl=None, checkpoint=None, offset_evals=None, ref_samples=None):
         """gsmvi/monitors.py:69-81."""
@@ -57,22 +75,25 @@ class KLMonitor:
             N = self.batch_size_kl
             mu_t, cov_t = to_dev(mu_in, dev), to_dev(cov_in, dev)
             D = mu_t.shape[0]
-            Sb, S = new_mat(D, D, dev)
-            S.copy_(cov_t)
-            Lb, _ = new_mat(D, D, dev)
-            mu = new_vec(D, dev)
+            w = self._work(N, D, dev)
+            mu = w["mu"]
             mu[:D].copy_(mu_t)
-            bad = torch.zeros(1, dtype=torch.int32, device=dev)
-            ws = torch.empty(L.workspace_bytes(L.WS_POTRF, N, D) // 4, dtype=torch.float32, device=dev)
-            L.potrf_check(Sb, Lb, D, bad, ws)
-            if int(bad.item()) != 0:
-                raise FloatingPointError("covariance is not positive definite")
-            Zb, _ = new_mat(N, D, dev)
-            Xb, X = new_mat(N, D, dev)
+            # the fit loops of this package hand over the factor they already hold (the engine's Cholesky of exactly this
+            # covariance, its goodness check): no second factorisation per checkpoint.  Anyone else passes [mean, cov].
+            Lb = getattr(params, "chol", None)
+            if Lb is None:
+                Sb, S = w["S"]
+                S.copy_(cov_t)
+                Lb, bad = w["L"][0], w["bad"]
+                L.potrf_check(Sb, Lb, D, bad, w["ws"])
+                if int(bad.item()) != 0:
+                    raise FloatingPointError("covariance is not positive definite")
+            Zb = w["Z"][0]
+            Xb, X = w["X"]
             # monitors.py:101-106: q-samples; counter = (iteration, call index) so draws differ from the fit's
             L.philox_normal(Zb, N, D, key_to_seed(key) ^ 0x9E3779B97F4A7C15, (int(i) << 20) + self._calls)
             L.sample(mu, Lb, Zb, Xb, N, D)
-            out = torch.zeros(1, dtype=torch.float64, device=dev)
+            out = w["out"]
             L.gauss_logq_reduce(Zb, N, D, mu, Lb, out, from_z=True)
             logq = float(out.item())
             logl = _as_float(lp(X))

@@ -82,3 +82,47 @@ def test_klmonitor_reverse_and_forward_kl_on_a_gaussian_target(lib):
     assert np.isnan(mon2.fkl[0]) and np.isfinite(mon2.rkl[0])
     mon2(1, [mu_q, -cov_q], lp, key=1)  # not positive definite: swallowed into NaN (monitors.py:117-120)
     assert np.isnan(mon2.rkl[1])
+
+
+@pytest.mark.parametrize("D,B", [(24, 16), (640, 256)])
+def test_klmonitor_inside_a_fit_uses_the_engine_factor(lib, D, B):
+    """Inside GSM.fit the monitor receives the engine's Cholesky factor with [mean, cov] (monitors.MonitorParams.chol) and
+    must not factor the covariance again; the reverse KL it records equals what a stand-alone monitor computes from the same
+    (mean, cov) with the same key and call count (same Philox counters: the estimates differ only by the two factorisations'
+    rounding), and the nevals bookkeeping of gsmvi/gsm.py:111-114, 131-132 is unchanged."""
+    from gsmvi_b200 import monitors as mon_mod
+    from gsmvi_b200.gsm import GSM
+    from gsmvi_b200.monitors import KLMonitor
+    from gsmvi_b200.targets import DenseGaussianTarget
+    mean_t, cov_t = orc.dense_gaussian_target(D, 1)
+    tgt = DenseGaussianTarget(mean_t, cov_t)
+    seen = []
+
+    class Spy(KLMonitor):
+        def __call__(self, i, params, lp, key, nevals=1):
+            seen.append((i, getattr(params, "chol", None) is not None,
+                         params[0].detach().clone(), params[1].detach().clone()))
+            return super().__call__(i, params, lp, key, nevals)
+
+    calls = {"n": 0}
+    real = mon_mod.L.potrf_check
+
+    def counting(*a, **k):
+        calls["n"] += 1
+        return real(*a, **k)
+
+    mon = Spy(batch_size_kl=512, checkpoint=2)
+    mon_mod.L.potrf_check = counting
+    try:
+        GSM(D, tgt.lp, tgt.lp_g).fit(5, niter=4, batch_size=B, verbose=False, monitor=mon)
+    finally:
+        mon_mod.L.potrf_check = real
+    assert [s[0] for s in seen] == [0, 2, 4, 4] and len(mon.rkl) == 4 and all(np.isfinite(mon.rkl))  # gsm.py:111-114, 131-132
+    if D > 64:  # (the fp64 small-D engine keeps its factor in doubles and hands over none)
+        assert all(s[1] for s in seen) and calls["n"] == 0
+    # stand-alone monitor on the recorded states: same key, same call index -> same draws
+    ref = KLMonitor(batch_size_kl=512, checkpoint=2)
+    for (i, _, m, c) in seen:
+        ref(i, [m, c], tgt.lp, 5, nevals=1)
+    for a, b in zip(mon.rkl, ref.rkl):
+        assert abs(a - b) <= 1e-4 * max(1.0, abs(b)), (mon.rkl, ref.rkl)

@@ -445,6 +445,8 @@ struct PanelArgs {
   // CTA 0 only reads what the first four row blocks of the previous panel stored (the K = 128 term's operand) and the
   // reduced diagonal tile: it waits for done[2] (row blocks 0..3) and done[1] instead of done[0].
   int chained;
+  int early_scale;  // *scale_l may be read before the wait for the previous launch (every fused launch after the first:
+                    // the scale was written before the first one's wait returned, and launches start in order)
   int track;  // count finished row blocks / GEMM CTAs in done[] (only needed when launches are chained)
   unsigned* done;
   unsigned rows_target, gemm_target, first4_target;
@@ -527,10 +529,10 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
   if (tid == 0) bad = 0;
   // programmatic dependent launch: the launch itself overlapped the tail of the previous kernel in the stream; everything
   // that reads its results comes after griddepcontrol.wait (CTA 0 first does the set-up that needs none of them)
-  if (a.chained) sl = *a.scale_l;  // written before the first panel's launch: no need to wait for the previous one
+  if (a.early_scale) sl = *a.scale_l;  // ~700 cycles of L2 latency that would otherwise follow the wait, every panel
   if (blockIdx.x != 0) {
     wait_previous_launch(a);
-    if (!a.chained) sl = *a.scale_l;
+    if (!a.early_scale) sl = *a.scale_l;
   }
 
   if (blockIdx.x == 0) {
@@ -553,7 +555,7 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
       __syncwarp();
     }
     wait_previous_launch(a);
-    if (!a.chained) sl = *a.scale_l;
+    if (!a.early_scale) sl = *a.scale_l;
     PT3C(0);
     PTP(0);
     if (warp == 0) {
@@ -1450,7 +1452,7 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
     pa.d0 = d0; pa.helper_count = ready + 1; pa.helpers = 0; pa.helper_target = 0; pa.late = 0; pa.late_mma = 0;
     pa.base = nullptr; pa.nb_out = nullptr; pa.nb_A = nullptr; pa.nb_partials = nullptr; pa.nb_stride = 0; pa.nb_splits = 0;
     pa.nb_count = ready + 3; pa.nb_target = 0;
-    pa.chained = 0; pa.track = (pdl && chain_env == 1) ? 1 : 0; pa.done = ready + 4; pa.rows_target = rows_done; pa.gemm_target = gemm_done; pa.first4_target = first4_done;
+    pa.chained = 0; pa.early_scale = 0; pa.track = (pdl && chain_env == 1) ? 1 : 0; pa.done = ready + 4; pa.rows_target = rows_done; pa.gemm_target = gemm_done; pa.first4_target = first4_done;
     epoch += 8;
     const bool fused = look && nb == NB;
     if (fused) {
@@ -1520,6 +1522,7 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
       pa.trsm_ctas = T > 0 ? T : 1;
       // chained to the previous fused launch: wait for its row blocks and its hosted GEMM instead of the grid's completion
       pa.chained = (prev_fused && pdl && chain_env == 1) ? 1 : 0;
+      pa.early_scale = prev_fused ? 1 : 0;
       if (pa.chained) {
         ga.wait_words = ready + 4;
         ga.wait_rows = pa.rows_target;

@@ -95,9 +95,6 @@ int h3_prepare(int M, int N, int K, const HView& A, const HView& B, float* C, lo
   a.split_lo = o.split_lo;
   a.split_ld = o.split_ld;
   a.split_scale = o.split_scale;
-  a.wait_words = nullptr;  // set by the Cholesky's chained fused launches only (potrf_h3.cu)
-  a.wait_rows = 0u;
-  a.wait_gemm = 0u;
   if (o.split_hi && (!o.split_lo || !o.split_scale || (o.split_ld & 3) != 0 || o.tri || o.splits != 1 || o.push_base)) return GSMVI_EINVAL;
   if (o.push_base && (!o.tri || o.splits != 1 || o.mirror || o.beta != 0.0f || o.bias_n)) return GSMVI_EINVAL;
   const int tiles = o.tri ? a.tiles_m * (a.tiles_m + 1) / 2 : a.tiles_m * a.tiles_n;

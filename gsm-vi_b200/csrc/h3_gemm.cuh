@@ -71,10 +71,6 @@ struct H3Args {
   __half* split_lo;
   long long split_ld;
   const float* split_scale;
-  // chained launch (the Cholesky's fused panel kernels, potrf_h3.cu): instead of griddepcontrol.wait the CTA waits until
-  // wait_words[0] >= wait_rows and wait_words[1] >= wait_gemm (monotone counters of the previous launch's finished work)
-  const unsigned* wait_words;
-  unsigned wait_rows, wait_gemm;
 };
 
 __host__ __device__ constexpr uint32_t make_idesc_f16(bool a_mn, bool b_mn) {
@@ -186,23 +182,8 @@ __device__ __forceinline__ void gemm_h3_body(const H3Args& args, const CUtensorM
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   // programmatic dependent launch: everything above overlapped the tail of the previous kernel in the stream; from here
   // on its results are needed (no-ops when the kernel was launched without the attribute)
-  if (args.wait_words == nullptr) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  } else {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (threadIdx.x == 0) {
-      const long long t0 = clock64();
-      unsigned r0, r1;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(r0) : "l"(args.wait_words) : "memory");
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(r1) : "l"(args.wait_words + 1) : "memory");
-        if (clock64() - t0 > 60000000000LL) { printf("gsmvi: h3 GEMM chained-launch watchdog (block %d)\n", blockIdx.x); __trap(); }
-      } while (static_cast<int>(r0 - args.wait_rows) < 0 || static_cast<int>(r1 - args.wait_gemm) < 0);
-    }
-    __syncthreads();
-    asm volatile("fence.proxy.async;" ::: "memory");  // the operands arrive by TMA (async proxy)
-  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ===================== TMA producer (the warp stays converged, one elected lane issues) =====================

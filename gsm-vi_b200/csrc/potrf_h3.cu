@@ -436,20 +436,19 @@ struct PanelArgs {
   int nb_splits;
   unsigned* nb_count;
   unsigned nb_target;
-  // chained launches (panel k >= 1 of the look-ahead form): the kernel does not wait for the previous grid to drain
-  // (griddepcontrol.wait = completion + flush of the whole grid, measured ~8k cycles from the last CTA's exit to the first
-  // instruction after the wait) but for the two things it produced: all row blocks of the previous panel stored (word
-  // done[0], counted by the row owners) and all CTAs of the update GEMM it hosted finished (done[1]).  Both counters only
-  // grow; the targets are cumulative.  Every CTA of the previous launch is resident before one of this launch can start
-  // (they all ran griddepcontrol.launch_dependents), so nothing here can wait for a CTA that has no SM.
-  // CTA 0 only reads what the first four row blocks of the previous panel stored (the K = 128 term's operand) and the
-  // reduced diagonal tile: it waits for done[2] (row blocks 0..3) and done[1] instead of done[0].
+  // chained launches (GSMVI_POTRF_CHAIN=1, panel k >= 1 of the look-ahead form): CTA 0 - the critical path - does not wait
+  // for the previous grid to drain (griddepcontrol.wait = completion + flush of the whole grid) but for the two things it
+  // reads: the first four row blocks of the previous panel stored (done[2], counted by their owners: the K = 128 term's
+  // operand) and the reduced diagonal tile written (done[1], counted by the update GEMM's last CTA of row tile 0).  Both
+  // counters only grow; the targets are cumulative.  Every other CTA keeps griddepcontrol.wait.  CTA 0 of launch k+1 can
+  // only start once every CTA of launch k has run griddepcontrol.launch_dependents, i.e. is resident: nothing it waits
+  // for can be without an SM.
   int chained;
   int early_scale;  // *scale_l may be read before the wait for the previous launch (every fused launch after the first:
                     // the scale was written before the first one's wait returned, and launches start in order)
   int track;  // count finished row blocks / GEMM CTAs in done[] (only needed when launches are chained)
   unsigned* done;
-  unsigned rows_target, gemm_target, first4_target;
+  unsigned gemm_target, first4_target;
 };
 
 // Chained launches only (GSMVI_POTRF_CHAIN=1): thread 0 of the CTA polls the previous launch's completion counters.  Kept out
@@ -465,15 +464,13 @@ __device__ __noinline__ void poll_previous_launch(const unsigned* w0, unsigned t
 
 // Start of a CTA's dependence on the previous launch (all 256 threads of the panel program).
 __device__ __forceinline__ void wait_previous_launch(const PanelArgs& a) {
-  if (!a.chained) {
+  if (!a.chained || blockIdx.x != 0) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     return;
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (threadIdx.x == 0)
-    poll_previous_launch(blockIdx.x == 0 ? a.done + 2 : a.done, blockIdx.x == 0 ? a.first4_target : a.rows_target, a.done + 1,
-                         a.gemm_target, a.j0);
+  if (threadIdx.x == 0) poll_previous_launch(a.done + 2, a.first4_target, a.done + 1, a.gemm_target, a.j0);
   cta_sync();
   // what follows reads the previous launch's results through L2 (ld.cg) and through TMA (async proxy)
   asm volatile("fence.proxy.async;" ::: "memory");
@@ -1219,10 +1216,9 @@ __device__ __forceinline__ void panel_body(const PanelArgs& a, uint8_t* sm_raw, 
   }
   if (blockIdx.x == 1) PT3(23);
   cta_sync();
-  if (tid == 0 && a.track) {  // this row block of the panel is stored (the next launch's CTAs wait for all of them)
+  if (tid == 0 && a.track && rb < 4) {  // one of the four row blocks the next panel's CTA 0 reads is stored
     __threadfence();
-    if (rb < 4) atomicAdd(a.done + 2, 1u);
-    atomicAdd(a.done, 1u);
+    atomicAdd(a.done + 2, 1u);
   }
   }  // row blocks
   if (blockIdx.x == 1) PT3(24);
@@ -1289,17 +1285,16 @@ potrf_fused_h3_kernel(const PanelArgs a, const H3Args g, const __grid_constant__
         }
         *reinterpret_cast<float4*>(a.nb_out + i * NB + j4) = v;
       }
+      if (a.track) {  // the reduced tile is written: what the next panel's CTA 0 waits for when launches are chained
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          __threadfence();
+          atomicAdd(a.done + 1, 1u);
+        }
+      }
     }
   }
   __syncthreads();
-  }
-  // this CTA's share of the hosted update is stored (the next launch's CTAs wait for all of them)
-  if (a.track) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      atomicAdd(a.done + 1, 1u);
-    }
   }
 }
 
@@ -1416,8 +1411,7 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
   };
   const bool timing = getenv("GSMVI_POTRF_TIMING") != nullptr;
   static int pdl_env = -1, look_env = -1, late_env = -1, chain_env = -1;
-  // chained launches are off by default: measured 0.801 ms against 0.784 ms at D = 4096 (profiles/r02_potrf_h3_round2b.txt) -
-  // the ~8k cycles between the last row owner's exit and the next CTA 0's first instruction are not the grid-completion wait
+  // chained launches: see PanelArgs::chained and profiles/r02_potrf_h3_round2b.txt for what they measured
   if (chain_env < 0) chain_env = env_flag("GSMVI_POTRF_CHAIN", 0);
   if (late_env < 0) late_env = env_flag("GSMVI_POTRF_LATE_MMA", 1);
   if (pdl_env < 0) pdl_env = env_flag("GSMVI_POTRF_PDL", 1);
@@ -1438,7 +1432,7 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
   const float* next_base = nullptr;  // reduced diagonal tile the NEXT panel will find (late_mma)
   unsigned base_target = 0;
   unsigned first4_done = 0;  // row blocks 0..3 of all panels so far
-  unsigned rows_done = 0, gemm_done = 0;  // row blocks / hosted GEMM CTAs of all launches so far (chained launches wait for them)
+  unsigned gemm_done = 0;    // reduced diagonal tiles written by all launches so far (chained CTA 0s wait for theirs)
   bool prev_fused = false;
   int next_splits = 0;  // split count of the look-ahead partials the NEXT panel will find in pbuf[(k + 1) & 1]
   for (int j0 = 0, k = 0; j0 < n; j0 += NB, ++k) {
@@ -1452,7 +1446,7 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
     pa.d0 = d0; pa.helper_count = ready + 1; pa.helpers = 0; pa.helper_target = 0; pa.late = 0; pa.late_mma = 0;
     pa.base = nullptr; pa.nb_out = nullptr; pa.nb_A = nullptr; pa.nb_partials = nullptr; pa.nb_stride = 0; pa.nb_splits = 0;
     pa.nb_count = ready + 3; pa.nb_target = 0;
-    pa.chained = 0; pa.early_scale = 0; pa.track = (pdl && chain_env == 1) ? 1 : 0; pa.done = ready + 4; pa.rows_target = rows_done; pa.gemm_target = gemm_done; pa.first4_target = first4_done;
+    pa.chained = 0; pa.early_scale = 0; pa.track = (pdl && chain_env == 1) ? 1 : 0; pa.done = ready + 4; pa.gemm_target = gemm_done; pa.first4_target = first4_done;
     epoch += 8;
     const bool fused = look && nb == NB;
     if (fused) {
@@ -1523,14 +1517,8 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
       // chained to the previous fused launch: wait for its row blocks and its hosted GEMM instead of the grid's completion
       pa.chained = (prev_fused && pdl && chain_env == 1) ? 1 : 0;
       pa.early_scale = prev_fused ? 1 : 0;
-      if (pa.chained) {
-        ga.wait_words = ready + 4;
-        ga.wait_rows = pa.rows_target;
-        ga.wait_gemm = pa.gemm_target;
-      }
-      rows_done += static_cast<unsigned>(nblocks);
       first4_done += static_cast<unsigned>(nblocks < 4 ? nblocks : 4);
-      gemm_done += static_cast<unsigned>(G);
+      gemm_done += (host_next && late_mma) ? 1u : 0u;  // one reduced diagonal tile per hosting launch
       prev_fused = true;
       const int grid = 1 + T + G;
       if (plan) {
@@ -1547,7 +1535,6 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
     next_splits = 0;
     next_base = nullptr;
     prev_fused = false;
-    rows_done += static_cast<unsigned>(nblocks);
     first4_done += static_cast<unsigned>(nblocks < 4 ? nblocks : 4);
     if (j0 > 0) {
       const int tiles = (M + NB - 1) / NB;

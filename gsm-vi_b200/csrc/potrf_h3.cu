@@ -14,10 +14,16 @@
 // Left-looking means the trailing matrix is never rewritten: total update traffic is ~D^3/(3*128) operand bytes read
 // once instead of a D^2 read-modify-write per panel, and each update is one long-K GEMM instead of a K=128 sliver.
 // Look-ahead form (default for 512 <= n <= ~17k, GSMVI_POTRF_LOOKAHEAD=0 disables): ONE launch per panel.  The fused
-// kernel's first CTAs run the panel program (2); its remaining CTAs each run one (row tile, split) work item of the
-// NEXT panel's update (1) restricted to the block-columns before the current panel - final at launch time, so neither
-// role waits for the other - and the next panel subtracts the current panel's own K = 128 term in fp32 on the CUDA cores
-// (row owners and helper CTAs, operands staged from L2 into shared memory).  See DESIGN.md section 3.2.
+// kernel's first CTAs run the panel program (2); its remaining CTAs run the (row tile, split) work items of the NEXT
+// panel's update (1) restricted to the block-columns before the current panel - final at launch time, so neither role
+// waits for the other - and the last of them that holds a partial of the next diagonal tile reduces all planes of that
+// tile (fixed order) into a buffer the next launch's CTA 0 starts from.  The next panel subtracts the current panel's own
+// K = 128 term itself: CTA 0 on its tensor core (TMA of the fp16 pair, 24 tcgen05 MMAs), the row owners in fp32 on the
+// CUDA cores.  Inside CTA 0 the four-warp team that factors sits on the warps the scheduler serves first, the warps that
+// solve the rows below (eight columns behind the team), publish and feed the trailing update sit underneath.
+// Every launch runs each role once from a cold instruction cache, so what is compiled into the default path matters:
+// polling loops and watchdogs are out of line, the default (LEAN) instantiation does not contain the alternative forms.
+// See DESIGN.md section 3.2 and profiles/r02_potrf_h3_round2b.txt.
 #include "dev_once.cuh"
 #include "potrf.cuh"
 #include "chol_block.cuh"

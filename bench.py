@@ -391,7 +391,20 @@ def run_ours(args):
     # 134 MB through the host at once) is amortised over at least 256 iterations where the pinned draw tape allows it
     # (<= 4 GiB per rank: 64 iterations of 64 MiB at N = 1, 128 at N = 2, 256 from N = 4 on)
     ke = max(4, min(max(args.steps, 256), int((4 << 30) // (Bl * D * 4))))
-    tape = torch.empty(ke, Bl, D, dtype=torch.float32).pin_memory()
+    tape = None
+    while tape is None:
+        try:
+            tape = torch.empty(ke, Bl, D, dtype=torch.float32).pin_memory()
+        except RuntimeError:  # the host cannot pin that much: a shorter fit (every rank takes the same decision below)
+            if ke <= 8:
+                raise
+            ke //= 2
+    if world > 1:  # all ranks must run the same number of iterations
+        kt = torch.tensor([ke], dtype=torch.int64, device="cuda")
+        dist.all_reduce(kt, op=dist.ReduceOp.MIN)
+        if int(kt.item()) < ke:
+            ke = int(kt.item())
+            tape = tape[:ke]
     tape.normal_(generator=torch.Generator().manual_seed(1 + rank))
     timed_fit(2, tape)  # untimed warm-up of the API path (first call: engine set-up, cached afterwards)
     dt_host = timed_fit(ke - 1, tape)

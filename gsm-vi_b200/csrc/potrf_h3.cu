@@ -1489,8 +1489,10 @@ static int potrf_h3_impl(cudaStream_t stream, const float* A, long long lda, flo
         {  // every row block of this panel gets its own CTA first; the update's items share what is left
           static int gcap_env = -1;
           if (gcap_env < 0) gcap_env = env_flag("GSMVI_POTRF_GCAP", 1);
+          // (only while no GEMM CTA has to take more than two items: at larger n, where the row blocks alone outnumber the
+          // SMs, the items keep one CTA each and the row owners loop instead - the update would become the long pole)
           const int room = max_ctas - 1 - (nblocks > 0 ? nblocks : 1);
-          if (gcap_env == 1 && G > room) G = room > 1 ? room : 1;
+          if (gcap_env == 1 && G > room && 2 * room >= G) G = room;
         }
         HView va{Lhi + static_cast<long long>(nj0) * Lh.ld, Llo + static_cast<long long>(nj0) * Lh.ld, Mn, j0, Lh.ld, Lh.scale};
         HView vb{Lhi + static_cast<long long>(nj0) * Lh.ld, Llo + static_cast<long long>(nj0) * Lh.ld, NB, j0, Lh.ld, Lh.scale};

@@ -1,3 +1,4 @@
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/probes/fp32_issue_probe tools/probes/fp32_issue_probe.cu
 // Single-warp issue-rate / latency probes for the fp32 pieces on the Cholesky's critical path (CTA 0 of potrf_h3):
 // independent FFMA vs packed FFMA2 (fma.rn.f32x2), broadcast LDS.128, mma.sync tf32 m16n8k8, rsqrt.approx, shfl.
 #include <cstdio>

@@ -314,3 +314,16 @@ def test_oracle_advi_gradient_matches_finite_differences_of_neg_elbo():
     m, c, losses = orc.ADVI(D, lp, lp_g).fit(0, 1e-2, Zt, batch_size=16, niter=2000)
     assert np.abs(m - mean_t).max() < 0.1 and np.linalg.norm(c - cov_t) / np.linalg.norm(cov_t) < 0.15
     assert losses[-1] < losses[0]
+
+
+def test_monitor_params_is_the_reference_list_plus_a_factor_slot():
+    """monitors.MonitorParams is what the fit loops hand to a monitor: it unpacks like the reference's [mean, cov]
+    (gsmvi/gsm.py:113, monitors.py:95) and carries the engine's Cholesky factor in `chol` (None when there is none, which
+    makes KLMonitor factor the covariance itself - the behaviour for any caller that passes a plain list)."""
+    from gsmvi_b200.monitors import MonitorParams
+    p = MonitorParams(["m", "c"])
+    mean, cov = p
+    assert (mean, cov) == ("m", "c") and len(p) == 2 and p[1] == "c" and isinstance(p, list)
+    assert p.chol is None and getattr(["m", "c"], "chol", None) is None
+    p.chol = "L"
+    assert p.chol == "L" and MonitorParams(["m", "c"]).chol is None  # per instance, not shared
